@@ -1,0 +1,255 @@
+"""ctypes binding of libhelm_b200.so (the C ABI declared in include/helm_b200.h).
+
+There is no CPU fallback: if the CUDA library is missing this module raises at
+import of the solver entry points, and if no CUDA device is usable the C ABI
+returns HELM_E_CUDA, which is raised as ``HelmB200Error``.
+"""
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HELM_MAX_PASSES = 16
+ST_RUNNING, ST_CONVERGED, ST_DIVERGED, ST_SINGULAR = 0, 2, 3, 4
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                         "libhelm_b200.so")
+
+
+class HelmB200Error(RuntimeError):
+    pass
+
+
+class GridHost(C.Structure):
+    _fields_ = [
+        ("n_bus", C.c_int32), ("slack", C.c_int32),
+        ("adj_ptr", C.c_void_p), ("adj_idx", C.c_void_p),
+        ("ytrans", C.c_void_p), ("yfull", C.c_void_p), ("yshunt", C.c_void_p),
+        ("phase_ptr", C.c_void_p), ("phase_idx", C.c_void_p), ("phase_val", C.c_void_p),
+        ("vsp", C.c_void_p), ("pg", C.c_void_p), ("pd", C.c_void_p), ("qd", C.c_void_p),
+        ("qgmax", C.c_void_p), ("qgmin", C.c_void_p), ("bus_type", C.c_void_p),
+    ]
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("mismatch", C.c_double), ("max_coefficients", C.c_int32),
+        ("enforce_q_limits", C.c_int32), ("group", C.c_int32),
+        ("use_graph", C.c_int32), ("poll_every", C.c_int32),
+    ]
+
+
+class PlanInfo(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "n_bus", "nnz_adj", "n_l_blocks", "n_u_blocks", "n_slots", "n_l_levels",
+        "n_u_levels", "n_factor_updates", "n_pv", "reserved")]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("steps", C.c_int64), ("kernel_launches", C.c_int64), ("graph_launches", C.c_int64),
+        ("ms_total", C.c_double), ("ms_kernel", C.c_double * 8),
+    ]
+
+
+KERNEL_NAMES = ("assemble", "factor", "solve", "rhs_conv", "advance", "qlimit", "pass_end", "init")
+
+EXPORTED_SYMBOLS = (
+    "helm_last_error", "helm_plan_create", "helm_plan_destroy", "helm_plan_get_info",
+    "helm_plan_get_perm", "helm_workspace_bytes", "helm_solve_batch_device",
+    "helm_solve_batch_host", "helm_debug_factor_solve", "helm_measure_peaks",
+    "helm_symbolic_create", "helm_symbolic_destroy", "helm_symbolic_array",
+)
+
+_lib = None
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def load():
+    """Load the shared library; raise loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise HelmB200Error(
+            "CUDA library %s not found: build it with helmpy_b200/csrc/build.sh "
+            "(or `python -c 'import __graft_entry__ as g; g.build()'`). "
+            "helmpy_b200 has no CPU fallback." % _LIB_PATH)
+    lib = C.CDLL(_LIB_PATH)
+    lib.helm_last_error.restype = C.c_char_p
+    lib.helm_plan_create.argtypes = [C.POINTER(GridHost), C.POINTER(C.c_void_p)]
+    lib.helm_plan_destroy.argtypes = [C.c_void_p]
+    lib.helm_plan_destroy.restype = None
+    lib.helm_plan_get_info.argtypes = [C.c_void_p, C.POINTER(PlanInfo)]
+    lib.helm_plan_get_perm.argtypes = [C.c_void_p, C.c_void_p]
+    lib.helm_workspace_bytes.argtypes = [C.c_void_p, C.c_int32, C.POINTER(Params)]
+    lib.helm_workspace_bytes.restype = C.c_size_t
+    lib.helm_solve_batch_device.argtypes = [
+        C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_size_t,
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Stats)]
+    lib.helm_solve_batch_host.argtypes = [
+        C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p,
+        C.c_void_p, C.c_void_p, C.POINTER(Stats)]
+    lib.helm_debug_factor_solve.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
+                                            C.c_void_p, C.c_void_p]
+    lib.helm_measure_peaks.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.helm_symbolic_create.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.helm_symbolic_destroy.argtypes = [C.c_void_p]
+    lib.helm_symbolic_destroy.restype = None
+    lib.helm_symbolic_array.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p),
+                                        C.POINTER(C.c_int32)]
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().helm_last_error()
+        raise HelmB200Error("%s failed (code %d): %s" % (what, rc, (msg or b"").decode()))
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def symbolic_arrays(adj_ptr, adj_idx):
+    """Host-only symbolic analysis -> dict of int32 numpy arrays (no CUDA)."""
+    lib = load()
+    adj_ptr = np.ascontiguousarray(adj_ptr, dtype=np.int32)
+    adj_idx = np.ascontiguousarray(adj_idx, dtype=np.int32)
+    h = C.c_void_p()
+    rc = lib.helm_symbolic_create(len(adj_ptr) - 1, _ptr(adj_ptr), _ptr(adj_idx), C.byref(h))
+    if rc != 0:
+        raise HelmB200Error("helm_symbolic_create failed (code %d)" % rc)
+    out = {}
+    try:
+        for name in ("perm", "iperm", "adj_ptr", "adj_idx", "adj_src", "adj_slot", "lptr", "lcol",
+                     "llev_ptr", "urow", "qof", "ulev_ptr", "uptr", "ucol", "dslot", "fptr",
+                     "fsrc", "fdst", "slot_src", "slot_row"):
+            data = C.c_void_p()
+            n = C.c_int32()
+            rc = lib.helm_symbolic_array(h, name.encode(), C.byref(data), C.byref(n))
+            if rc != 0:
+                raise HelmB200Error("helm_symbolic_array(%s) failed" % name)
+            if n.value:
+                buf = (C.c_int32 * n.value).from_address(data.value)
+                out[name] = np.frombuffer(buf, dtype=np.int32).copy()
+            else:
+                out[name] = np.zeros(0, dtype=np.int32)
+    finally:
+        lib.helm_symbolic_destroy(h)
+    return out
+
+
+class Plan:
+    """Owns a ``helm_plan``: symbolic analysis + device-resident grid for one case."""
+
+    def __init__(self, case):
+        lib = load()
+        self._keep = k = {}
+        k["adj_ptr"] = np.ascontiguousarray(case.adj_ptr, dtype=np.int32)
+        k["adj_idx"] = np.ascontiguousarray(case.adj_idx, dtype=np.int32)
+        k["ytrans"] = np.ascontiguousarray(case.Ytrans_val, dtype=np.complex128)
+        k["yfull"] = np.ascontiguousarray(case.Y_val, dtype=np.complex128)
+        k["yshunt"] = np.ascontiguousarray(case.Yshunt, dtype=np.complex128)
+        k["phase_ptr"] = np.ascontiguousarray(case.phase_ptr, dtype=np.int32)
+        k["phase_idx"] = np.ascontiguousarray(case.phase_idx, dtype=np.int32)
+        k["phase_val"] = np.ascontiguousarray(case.phase_val, dtype=np.complex128)
+        for name, attr in (("vsp", "V"), ("pg", "Pg"), ("pd", "Pd"), ("qd", "Qd"),
+                           ("qgmax", "Qgmax"), ("qgmin", "Qgmin")):
+            k[name] = np.ascontiguousarray(getattr(case, attr), dtype=np.float64)
+        k["bus_type"] = np.ascontiguousarray(case.bus_types_code(), dtype=np.uint8)
+        g = GridHost()
+        g.n_bus = case.N
+        g.slack = int(case.slack)
+        for name in ("adj_ptr", "adj_idx", "ytrans", "yfull", "yshunt", "phase_ptr", "phase_idx",
+                     "phase_val", "vsp", "pg", "pd", "qd", "qgmax", "qgmin", "bus_type"):
+            setattr(g, name, k[name].ctypes.data)
+        self.handle = C.c_void_p()
+        check(lib.helm_plan_create(C.byref(g), C.byref(self.handle)), "helm_plan_create")
+        self.N = case.N
+        info = PlanInfo()
+        check(lib.helm_plan_get_info(self.handle, C.byref(info)), "helm_plan_get_info")
+        self.info = {n: getattr(info, n) for n, _ in PlanInfo._fields_}
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None) and self.handle.value and _lib is not None:
+                _lib.helm_plan_destroy(self.handle)
+                self.handle = C.c_void_p()
+        except Exception:
+            pass
+
+    def perm(self):
+        out = np.empty(self.N, dtype=np.int32)
+        check(load().helm_plan_get_perm(self.handle, _ptr(out)), "helm_plan_get_perm")
+        return out
+
+    @staticmethod
+    def make_params(mismatch, max_coefficients, enforce_q_limits, group=0, use_graph=True,
+                    poll_every=0):
+        p = Params()
+        p.mismatch = float(mismatch)
+        p.max_coefficients = int(max_coefficients)
+        p.enforce_q_limits = int(bool(enforce_q_limits))
+        p.group = int(group)
+        p.use_graph = int(bool(use_graph))
+        p.poll_every = int(poll_every)
+        return p
+
+    def workspace_bytes(self, n_scen, params):
+        return int(load().helm_workspace_bytes(self.handle, n_scen, C.byref(params)))
+
+    def solve_host(self, scales, params):
+        """Host-buffer call: numpy in, numpy out (H2D/D2H inside)."""
+        lib = load()
+        scales = np.ascontiguousarray(scales, dtype=np.float64)
+        B = len(scales)
+        vout = np.zeros((B, self.N), dtype=np.complex128)
+        status = np.zeros(B, dtype=np.int32)
+        ncoef = np.zeros((B, HELM_MAX_PASSES), dtype=np.int32)
+        nswitch = np.zeros(B, dtype=np.int32)
+        stats = Stats()
+        check(lib.helm_solve_batch_host(self.handle, B, _ptr(scales), C.byref(params), _ptr(vout),
+                                        _ptr(status), _ptr(ncoef), _ptr(nswitch), C.byref(stats)),
+              "helm_solve_batch_host")
+        return vout, status, ncoef, nswitch, stats_dict(stats)
+
+    def solve_device(self, d_scale, params, workspace, d_vout, d_status, d_ncoef, d_nswitch,
+                     stream_ptr):
+        """Device-pointer call on torch tensors (resident inputs)."""
+        lib = load()
+        stats = Stats()
+        check(lib.helm_solve_batch_device(
+            self.handle, d_scale.numel(), d_scale.data_ptr(), C.byref(params),
+            workspace.data_ptr(), workspace.numel() * workspace.element_size(),
+            d_vout.data_ptr(), d_status.data_ptr(), d_ncoef.data_ptr(), d_nswitch.data_ptr(),
+            stream_ptr, C.byref(stats)), "helm_solve_batch_device")
+        return stats_dict(stats)
+
+    def debug_factor_solve(self, bus_types, rhs, group=1):
+        bus_types = np.ascontiguousarray(bus_types, dtype=np.uint8)
+        rhs = np.ascontiguousarray(rhs, dtype=np.float64)
+        B = bus_types.shape[0]
+        x = np.zeros_like(rhs)
+        check(load().helm_debug_factor_solve(self.handle, B, group, _ptr(bus_types), _ptr(rhs),
+                                             _ptr(x)), "helm_debug_factor_solve")
+        return x
+
+
+def stats_dict(stats):
+    return {
+        "steps": int(stats.steps), "kernel_launches": int(stats.kernel_launches),
+        "graph_launches": int(stats.graph_launches), "ms_total": float(stats.ms_total),
+        "ms_kernel": {KERNEL_NAMES[i]: float(stats.ms_kernel[i]) for i in range(8)},
+    }
+
+
+def measure_peaks():
+    a, b = C.c_double(), C.c_double()
+    check(load().helm_measure_peaks(C.byref(a), C.byref(b)), "helm_measure_peaks")
+    return {"dfma_tflops": a.value, "copy_gbs": b.value}

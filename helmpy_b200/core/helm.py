@@ -1,0 +1,138 @@
+"""HELM solver entry points — host side of the drop-in boundary.
+
+``helm(case, ...)`` keeps the reference's signature, return convention and
+unconditional prints (reference helmpy/core/helm.py:896-985, 651, 655);
+``helm_batch`` is the new scenario-batch call (B independent ``helm`` runs of
+one grid at different load scales).  All arithmetic of the run —
+matrix assembly, numeric LU, per-order right-hand sides, triangular solves,
+V/W recurrences, Pade continuation, convergence test, Q-limit switching and
+the restart loop — executes in the CUDA library behind the C ABI
+(include/helm_b200.h).  There is no CPU path: without the built library or
+without a CUDA device these functions raise ``HelmB200Error``.
+
+Scope of this build: pv_bus_model=2 with the classic slack (the reference's
+default).  Other variants raise ``NotImplementedError``.
+
+Documented deviation: the reference's argument validation
+prints its message and then runs anyway because ``(False, None)`` is truthy
+(helm.py:881-911); here the message is printed and ``None`` is returned.
+"""
+
+import numpy as np
+
+from . import _lib
+from ._lib import HELM_MAX_PASSES, ST_CONVERGED
+
+
+def validate_arguments(case, detailed_run_print, mismatch, scale, max_coefficients,
+                       enforce_Q_limits, results_file_name, save_results, pv_bus_model,
+                       DSB_model, DSB_model_method):
+    """Same checks and messages as reference helm.py:853-892; returns a bool."""
+    if (type(detailed_run_print) is not bool or type(mismatch) is not float
+            or not (type(scale) is float or type(scale) is int)
+            or type(max_coefficients) is not int or type(enforce_Q_limits) is not bool
+            or not (results_file_name is None or type(results_file_name) is str)
+            or type(save_results) is not bool or type(pv_bus_model) is not int
+            or type(DSB_model) is not bool
+            or not (DSB_model_method is None or type(DSB_model_method) is int)):
+        print("Erroneous argument type.")
+        return False
+    if max_coefficients < 5:
+        print("'max_coefficients' must be equal or greater than five (5).")
+        return False
+    if pv_bus_model not in (1, 2):
+        print("'pv_bus_model' must be the integer 1 or 2.",)
+        return False
+    if DSB_model_method is not None and DSB_model_method not in (1, 2):
+        print("'DSB_model_method' must be the integer 1 or 2.",)
+        return False
+    return True
+
+
+def get_plan(case):
+    """Symbolic analysis + device-resident grid for ``case``; cached on the object.
+
+    The plan depends on topology, admittances, generator data and the unscaled
+    loads, so it is rebuilt if the case's scale is not 1 when first used.
+    """
+    plan = getattr(case, "_b200_plan", None)
+    if plan is None:
+        if case.scale != 1:
+            raise _lib.HelmB200Error("build the plan on an unscaled case (call reset_scale())")
+        plan = _lib.Plan(case)
+        case._b200_plan = plan
+    return plan
+
+
+class BatchResult:
+    """Result of ``helm_batch``: voltages [B, N] complex128 (rows of scenarios
+    that did not converge are zero), status [B], coefficients per pass
+    (``run.list_coef`` of each scenario), PV->PQ switch counts, solver stats."""
+
+    def __init__(self, V, status, ncoef, nswitch, stats):
+        self.V = V
+        self.status = status
+        self.ncoef = ncoef
+        self.nswitch = nswitch
+        self.stats = stats
+
+    @property
+    def converged(self):
+        return self.status == ST_CONVERGED
+
+    def list_coef(self, b):
+        row = self.ncoef[b]
+        return [int(x) for x in row[row > 0]]
+
+
+def helm_batch(case, scales, mismatch=1e-4, max_coefficients=100, enforce_Q_limits=True,
+               group=0, use_graph=True, poll_every=0):
+    """Solve ``len(scales)`` load-scaling scenarios of ``case`` on the current GPU.
+
+    Scenario b equals ``helm(case, scale=scales[b], mismatch=..., ...)``
+    (set_scale semantics of reference classes.py:215-219).  ``case`` is not
+    mutated.  Host buffers in, host buffers out.
+    """
+    plan = get_plan(case)
+    prm = _lib.Plan.make_params(mismatch, max_coefficients, enforce_Q_limits, group, use_graph,
+                                poll_every)
+    V, status, ncoef, nswitch, stats = plan.solve_host(np.asarray(scales, dtype=np.float64), prm)
+    return BatchResult(V, status, ncoef, nswitch, stats)
+
+
+def helm(case, detailed_run_print=False, mismatch=1e-4, scale=1, max_coefficients=100,
+         enforce_Q_limits=True, results_file_name=None, save_results=False, pv_bus_model=2,
+         DSB_model=False, DSB_model_method=None):
+    """Drop-in for reference ``helmpy.helm`` (helm.py:896-985).
+
+    Returns the complex bus voltages (ndarray complex128, Buses-sheet order) or
+    ``None`` when the maximum number of coefficients is reached.
+    """
+    if not validate_arguments(case, detailed_run_print, mismatch, scale, max_coefficients,
+                              enforce_Q_limits, results_file_name, save_results, pv_bus_model,
+                              DSB_model, DSB_model_method):
+        return None
+    if DSB_model and DSB_model_method is None:
+        DSB_model_method = 2
+    if pv_bus_model != 2 or DSB_model_method is not None:
+        raise NotImplementedError(
+            "helmpy_b200 currently implements pv_bus_model=2 with the classic slack; "
+            "PV model 1 and the distributed-slack variants are not built yet")
+    res = helm_batch(case, [float(scale)], mismatch=mismatch, max_coefficients=max_coefficients,
+                     enforce_Q_limits=enforce_Q_limits, group=1)
+    coefs = res.list_coef(0)
+    if detailed_run_print:
+        for p, m in enumerate(coefs[:-1]):
+            print("At coefficient %d the system is to be resolved due to PVLIM to PQ switches\n" % m)
+    if res.status[0] != ST_CONVERGED:
+        print('\nMaximum number of coefficients has been reached. The problem has no physical solution')
+        return None
+    print('\nConvergence has been reached. %d coefficients were calculated' % coefs[-1])
+    V = res.V[0].copy()
+    if detailed_run_print or save_results:
+        from . import reporting
+        reporting.report(case, V, scale=scale, mismatch=mismatch, list_coef=coefs,
+                         algorithm='HELM PV2', enforce_Q_limits=enforce_Q_limits,
+                         detailed_run_print=detailed_run_print, save_results=save_results,
+                         results_file_name=results_file_name)
+    return V

@@ -1,0 +1,1055 @@
+// B200-native HELM + Pade hot path: CUDA kernels, per-order step machine, C ABI.
+// Design notes: DESIGN.md.  Reference being replaced: HELMpy helmpy/core/helm.py
+// (cited per kernel below).  sm_100a only; fp64 throughout; no tensor cores
+// (nothing on this path is a dense contraction).
+//
+// Data layout.  Scenarios are packed in lock-step groups of G (1..32).  Every
+// per-scenario array is stored [group][item][G], so the G scenarios of a group
+// sit in adjacent lanes and every access to a per-(item, scenario) value is a
+// contiguous run of G*16 B (values are double2 = complex or a 2-vector).  Series
+// histories are [group][order][bus][G].  LU block values are [group][slot][G]
+// with 4 doubles (one 2x2 block) per element, slots numbered in the order the
+// triangular solves consume them, so each CTA streams its group's factors front
+// to back.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/helm_b200.h"
+#include "symbolic.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+#define CUDA_TRY(expr)                                                                  \
+    do {                                                                                \
+        cudaError_t _e = (expr);                                                        \
+        if (_e != cudaSuccess) {                                                        \
+            g_err = std::string(#expr) + ": " + cudaGetErrorString(_e);                 \
+            return HELM_E_CUDA;                                                         \
+        }                                                                               \
+    } while (0)
+
+// internal per-scenario status (superset of the public codes)
+enum : int { ST_ACTIVE = 0, ST_FROZEN = 1, ST_CONVERGED = 2, ST_DIVERGED = 3, ST_SINGULAR = 4, ST_PAD = 5 };
+// group flags
+enum : int { GF_NEEDFACTOR = 1, GF_PASSEND = 2, GF_DONE = 4 };
+
+// ---- device-side views ------------------------------------------------------------
+struct PlanDev {
+    int N, nL, nU, nslots, nLlev, nUlev, nadj, slack;
+    const int *adj_ptr, *adj_idx, *adj_slot;
+    const double2 *ytr, *yfull, *yshunt;
+    const int *ph_ptr, *ph_idx;
+    const double2 *ph_val;
+    const double *vsp, *pg, *pd, *qd, *qmax, *qmin;
+    const unsigned char *btype0;
+    const int *perm;  // new index -> original bus
+    const int *lptr, *lcol, *llev_ptr;
+    const int *urow, *ulev_ptr, *uptr, *ucol, *dslot;
+    const int *slot_src, *slot_row;
+    const int *fptr, *fsrc, *fdst;
+};
+
+struct WorkDev {
+    int B, G, ngroups, K;  // K = history planes = max_coef + 1
+    double mismatch;
+    int max_coef, enforce_q;
+    double *scale;                    // [Bp]
+    int *s_status, *s_mconv, *s_fail, *s_viol, *s_npass, *s_nswitch, *s_ncoef;  // [Bp], ncoef [Bp*MAXP]
+    int *g_n, *g_flags;               // [ngroups]
+    int *active_groups;               // [1]
+    unsigned char *btype;             // [group][N][G]
+    double *Qg, *VVant;               // [group][N][G]
+    double2 *Pcur;                    // [group][N][G]
+    double2 *rhs, *xb;                // [group][N][G]
+    double2 *lu;                      // [group][nslots][G][2]
+    double2 *Vh, *Hh, *Eh;            // [group][K][N][G]
+    double2 *vout;                    // [B][N] original order
+};
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ double2 cmulc(double2 a, double2 b) {  // a * conj(b)
+    return make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 crecip_guard(double2 d) {
+    // 1/d with the zero-denominator guard of the epsilon table
+    double den = d.x * d.x + d.y * d.y;
+    if (!(den > 0.0) || !(den < 1.7e308)) {
+        if (den == 0.0) return make_double2(1e120, 0.0);
+        if (!(den == den)) return make_double2(den, den);  // NaN propagates -> check fails
+        return make_double2(0.0, 0.0);                     // |d| overflowed: 1/d ~ 0
+    }
+    double inv = 1.0 / den;
+    return make_double2(d.x * inv, -d.y * inv);
+}
+
+template <int G>
+__device__ __forceinline__ size_t ix(int grp, int count, int item, int s) {
+    return ((size_t)grp * count + item) * G + s;
+}
+template <int G>
+__device__ __forceinline__ size_t hx(const WorkDev &w, int N, int grp, int k, int i, int s) {
+    return (((size_t)grp * w.K + k) * N + i) * G + s;
+}
+
+// ---- K_asm: scatter A into the LU slots (reference helm.py:46-60) -------------------
+// One thread per (slot, scenario).  Fill slots get zero blocks.
+template <int G>
+__global__ void k_assemble(PlanDev p, WorkDev w) {
+    int grp = blockIdx.y;
+    if (!(w.g_flags[grp] & GF_NEEDFACTOR)) return;
+    int flat = blockIdx.x * blockDim.x + threadIdx.x;
+    int slot = flat / G, s = flat % G;
+    if (slot >= p.nslots) return;
+    if (w.s_status[grp * G + s] != ST_ACTIVE) return;
+    int r = p.slot_row[slot];
+    int a = p.slot_src[slot];
+    unsigned char bt = w.btype[ix<G>(grp, p.N, r, s)];
+    bool diag = (p.dslot[r] == slot);
+    double2 r0 = make_double2(0.0, 0.0), r1 = make_double2(0.0, 0.0);
+    if (bt == HELM_BUS_SLACK) {
+        if (diag) { r0.x = 1.0; r1.y = 1.0; }                         // helm.py:47-49
+    } else if (a >= 0) {
+        double2 y = p.ytr[a];
+        r0 = make_double2(y.x, -y.y);                                 // helm.py:52-53 / 59-60
+        if (bt == HELM_BUS_PQ) r1 = make_double2(y.y, y.x);           // helm.py:54-55
+        else if (diag) r1 = make_double2(1.0, 0.0);                   // helm.py:57
+    }
+    double2 *dst = w.lu + ix<G>(grp, p.nslots, slot, s) * 2;
+    dst[0] = r0;
+    dst[1] = r1;
+}
+
+struct Blk { double a, b, c, d; };  // [[a b][c d]]
+__device__ __forceinline__ Blk ldblk(const double2 *lu, size_t e) {
+    double2 r0 = lu[e * 2], r1 = lu[e * 2 + 1];
+    return Blk{r0.x, r0.y, r1.x, r1.y};
+}
+__device__ __forceinline__ void stblk(double2 *lu, size_t e, Blk m) {
+    lu[e * 2] = make_double2(m.a, m.b);
+    lu[e * 2 + 1] = make_double2(m.c, m.d);
+}
+__device__ __forceinline__ Blk bmul(Blk x, Blk y) {
+    return Blk{x.a * y.a + x.b * y.c, x.a * y.b + x.b * y.d, x.c * y.a + x.d * y.c, x.c * y.b + x.d * y.d};
+}
+
+// ---- K2f: numeric 2x2-block LU on the fixed pattern (replaces SuperLU gstrf, helm.py:106)
+// One CTA per group; rows of one L-level are independent; thread (slot, s)
+// eliminates whole rows (up-looking).  L_rk = A_rk * inv(D_k); D_r stored inverted.
+template <int G, int T>
+__global__ void __launch_bounds__(T) k_factor(PlanDev p, WorkDev w) {
+    int grp = blockIdx.x;
+    if (!(w.g_flags[grp] & GF_NEEDFACTOR)) return;
+    const int R = T / G;
+    int s = threadIdx.x % G, slot = threadIdx.x / G;
+    int sg = grp * G + s;
+    bool active = w.s_status[sg] == ST_ACTIVE;
+    double2 *lu = w.lu + (size_t)grp * p.nslots * G * 2;
+    bool singular = false;
+    for (int l = 0; l < p.nLlev; ++l) {
+        int r1 = p.llev_ptr[l + 1];
+        if (active) {
+            for (int r = p.llev_ptr[l] + slot; r < r1; r += R) {
+                for (int e = p.lptr[r]; e < p.lptr[r + 1]; ++e) {
+                    int k = p.lcol[e];
+                    Blk a = ldblk(lu, (size_t)e * G + s);
+                    Blk dk = ldblk(lu, (size_t)p.dslot[k] * G + s);
+                    Blk m = bmul(a, dk);
+                    stblk(lu, (size_t)e * G + s, m);
+                    for (int u = p.fptr[e]; u < p.fptr[e + 1]; ++u) {
+                        Blk src = ldblk(lu, (size_t)p.fsrc[u] * G + s);
+                        size_t di = (size_t)p.fdst[u] * G + s;
+                        Blk dst = ldblk(lu, di);
+                        Blk pr = bmul(m, src);
+                        dst.a -= pr.a; dst.b -= pr.b; dst.c -= pr.c; dst.d -= pr.d;
+                        stblk(lu, di, dst);
+                    }
+                }
+                size_t dd = (size_t)p.dslot[r] * G + s;
+                Blk d = ldblk(lu, dd);
+                double det = d.a * d.d - d.b * d.c;
+                if (det == 0.0 || !(det == det)) { singular = true; det = 1.0; }
+                double inv = 1.0 / det;
+                stblk(lu, dd, Blk{d.d * inv, -d.b * inv, -d.c * inv, d.a * inv});
+            }
+        }
+        __syncthreads();
+    }
+    if (singular) w.s_status[sg] = ST_SINGULAR;
+}
+
+// ---- K2: level-scheduled block SpTRSV (replaces SuperLU gstrs, helm.py:602) -----------
+// One CTA per group.  x = U^-1 L^-1 rhs; forward phase writes y into xb, backward
+// phase works in place.  Rows of one level are independent: thread (slot, s).
+template <int G, int T>
+__global__ void __launch_bounds__(T) k_solve(PlanDev p, WorkDev w) {
+    int grp = blockIdx.x;
+    if (w.g_flags[grp] & GF_DONE) return;
+    const int R = T / G;
+    int s = threadIdx.x % G, slot = threadIdx.x / G;
+    bool active = w.s_status[grp * G + s] == ST_ACTIVE;
+    const double2 *lu = w.lu + (size_t)grp * p.nslots * G * 2;
+    const double2 *rhs = w.rhs + (size_t)grp * p.N * G;
+    double2 *xb = w.xb + (size_t)grp * p.N * G;
+    for (int l = 0; l < p.nLlev; ++l) {
+        int r1 = p.llev_ptr[l + 1];
+        if (active) {
+            for (int r = p.llev_ptr[l] + slot; r < r1; r += R) {
+                double2 acc = rhs[(size_t)r * G + s];
+                int e1 = p.lptr[r + 1];
+                for (int e = p.lptr[r]; e < e1; ++e) {
+                    int c = p.lcol[e];
+                    Blk m = ldblk(lu, (size_t)e * G + s);
+                    double2 xc = xb[(size_t)c * G + s];
+                    acc.x -= m.a * xc.x + m.b * xc.y;
+                    acc.y -= m.c * xc.x + m.d * xc.y;
+                }
+                xb[(size_t)r * G + s] = acc;
+            }
+        }
+        __syncthreads();
+    }
+    for (int l = 0; l < p.nUlev; ++l) {
+        int q1 = p.ulev_ptr[l + 1];
+        if (active) {
+            for (int q = p.ulev_ptr[l] + slot; q < q1; q += R) {
+                int r = p.urow[q];
+                double2 acc = xb[(size_t)r * G + s];
+                int u0 = p.uptr[q], nu = p.uptr[q + 1] - u0;
+                size_t base = (size_t)(p.nL + u0 + q);
+                for (int t = 0; t < nu; ++t) {
+                    int c = p.ucol[u0 + t];
+                    Blk m = ldblk(lu, (base + 1 + t) * G + s);
+                    double2 xc = xb[(size_t)c * G + s];
+                    acc.x -= m.a * xc.x + m.b * xc.y;
+                    acc.y -= m.c * xc.x + m.d * xc.y;
+                }
+                Blk d = ldblk(lu, base * G + s);
+                xb[(size_t)r * G + s] = make_double2(d.a * acc.x + d.b * acc.y, d.c * acc.x + d.d * acc.y);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- RHS of order jn >= 2 for bus i (reference helm.py:293-398) -----------------------
+// v = V_i[jn-1] (just solved), neighbours' V_k[jn-1] are read from the solution
+// buffer xb; older orders from the history Vh.  Hh holds W (PQ) or barras_CC (PV).
+template <int G>
+__device__ __forceinline__ double2 rhs_next(const PlanDev &p, const WorkDev &w, int grp, int i, int s,
+                                            int j /* = jn-1 */, unsigned char bt, double2 v,
+                                            double2 wj /* W_i[j], PQ only */, double sc) {
+    const int N = p.N;
+    const double2 *xb = w.xb + (size_t)grp * N * G;
+    if (bt == HELM_BUS_SLACK) return make_double2(0.0, 0.0);                     // helm.py:395-397
+    if (bt == HELM_BUS_PQ) {                                                     // helm.py:367-385
+        double Pi = p.pg[i] * sc - p.pd[i] * sc;
+        double Qi = w.Qg[ix<G>(grp, N, i, s)] - p.qd[i] * sc;
+        double2 pp = make_double2(0.0, 0.0);
+        for (int a = p.ph_ptr[i]; a < p.ph_ptr[i + 1]; ++a)
+            pp = cadd(pp, cmul(p.ph_val[a], xb[(size_t)p.ph_idx[a] * G + s]));
+        double2 sconj = make_double2(Pi, -Qi);
+        double2 t = cmul(sconj, make_double2(wj.x, -wj.y));
+        double2 ysv = cmul(p.yshunt[i], v);
+        return make_double2(t.x - ysv.x - pp.x, t.y - ysv.y - pp.y);
+    }
+    // PV bus, model 2 (helm.py:293-364); n = j+1 >= 2
+    double2 PP = make_double2(0.0, 0.0);
+    for (int a = p.adj_ptr[i]; a < p.adj_ptr[i + 1]; ++a)
+        PP = cadd(PP, cmul(p.ytr[a], xb[(size_t)p.adj_idx[a] * G + s]));         // helm.py:310-312
+    w.Hh[hx<G>(w, N, grp, j, i, s)] = PP;                                        // barras_CC[i][n-1]
+    double2 ppp = make_double2(0.0, 0.0);
+    // x = 1 .. n-2 : conj(V[n-x]) * CC[x];  V[n-1] = v is the x=1 term
+    for (int x = 1; x <= j - 1; ++x) {
+        double2 vv = (x == 1) ? v : w.Vh[hx<G>(w, N, grp, j + 1 - x, i, s)];
+        double2 cc = w.Hh[hx<G>(w, N, grp, x, i, s)];
+        ppp = cadd(ppp, cmulc(cc, vv));
+    }
+    double2 v1 = (j == 1) ? v : w.Vh[hx<G>(w, N, grp, 1, i, s)];
+    ppp = cadd(ppp, cmulc(PP, v1));                                              // helm.py:314
+    double cc_ = 0.0 - ppp.x;
+    double2 ysh = p.yshunt[i];
+    size_t vvi = ix<G>(grp, N, i, s);
+    if (ysh.x != 0.0) {                                                          // conduc_buses
+        if (j >= 2) cc_ -= ysh.x * (w.VVant[vvi] + 2.0 * v.x);                   // helm.py:317-318
+        else cc_ -= ysh.x * 2.0 * v.x;                                           // helm.py:336-337
+    }
+    if (p.ph_ptr[i + 1] > p.ph_ptr[i]) {                                         // helm.py:320-327
+        double2 acc = make_double2(0.0, 0.0);
+        for (int x = 0; x <= j; ++x) {
+            double2 pp = make_double2(0.0, 0.0);
+            for (int a = p.ph_ptr[i]; a < p.ph_ptr[i + 1]; ++a) {
+                int k = p.ph_idx[a];
+                double2 vk = (x == 0) ? xb[(size_t)k * G + s] : w.Vh[hx<G>(w, N, grp, j - x, k, s)];
+                pp = cadd(pp, cmul(p.ph_val[a], vk));
+            }
+            double2 vx = (x == j) ? v : w.Vh[hx<G>(w, N, grp, x, i, s)];
+            acc = cadd(acc, cmulc(pp, vx));
+        }
+        cc_ -= acc.x;
+    }
+    // VV = sum_{k=1}^{n-1} V[k] conj(V[n-k])  (helm.py:356-361)
+    double vvre = 0.0;
+    for (int k = 1; k <= j; ++k) {
+        double2 a = (k == j) ? v : w.Vh[hx<G>(w, N, grp, k, i, s)];
+        double2 b = (j + 1 - k == j) ? v : w.Vh[hx<G>(w, N, grp, j + 1 - k, i, s)];
+        vvre += a.x * b.x + a.y * b.y;
+    }
+    w.VVant[vvi] = vvre;
+    return make_double2(cc_, -vvre * 0.5);
+}
+
+// ---- K_init: order-0 germ and RHS of order 1 (helm.py:110-139, 551-556, n == 1 branches) ---
+template <int G>
+__global__ void k_init(PlanDev p, WorkDev w) {
+    int grp = blockIdx.y;
+    if (!(w.g_flags[grp] & GF_NEEDFACTOR)) return;
+    int flat = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = flat / G, s = flat % G;
+    if (i >= p.N) return;
+    int sg = grp * G + s;
+    if (w.s_status[sg] != ST_ACTIVE) return;
+    const int N = p.N;
+    double sc = w.scale[sg];
+    size_t bi = ix<G>(grp, N, i, s);
+    unsigned char bt = w.btype[bi];
+    double2 one = make_double2(1.0, 0.0);
+    w.Vh[hx<G>(w, N, grp, 0, i, s)] = one;
+    w.Hh[hx<G>(w, N, grp, 0, i, s)] = one;     // W[0] = 1
+    w.Eh[hx<G>(w, N, grp, 0, i, s)] = one;     // partial sum S_0
+    w.VVant[bi] = 0.0;
+    double2 r;
+    if (bt == HELM_BUS_SLACK) {
+        r = make_double2(p.vsp[i] - 1.0, 0.0);                                   // helm.py:393-394
+        w.Pcur[bi] = make_double2(p.vsp[i], 0.0);
+    } else if (bt == HELM_BUS_PQ) {
+        double Pi = p.pg[i] * sc - p.pd[i] * sc;
+        double Qi = w.Qg[bi] - p.qd[i] * sc;
+        double2 pp = make_double2(0.0, 0.0);
+        for (int a = p.ph_ptr[i]; a < p.ph_ptr[i + 1]; ++a) pp = cadd(pp, p.ph_val[a]);
+        double2 ysh = p.yshunt[i];
+        r = make_double2(Pi - ysh.x - pp.x, -Qi - ysh.y - pp.y);
+    } else {
+        double cc = (p.pg[i] * sc - p.pd[i] * sc) - p.yshunt[i].x;               // helm.py:347-352
+        for (int a = p.ph_ptr[i]; a < p.ph_ptr[i + 1]; ++a) cc -= p.ph_val[a].x;
+        double vs = p.vsp[i];
+        r = make_double2(cc, (vs * vs - 1.0) * 0.5);                             // helm.py:354-355, 364
+    }
+    w.rhs[bi] = r;
+}
+
+// ---- K1: V/W update, epsilon-table column, Pade check, RHS of the next order ------------
+// One thread per (bus, scenario).  Replaces compute_complex_voltages (helm.py:402-420),
+// calculate_inverse_voltages_w_array (423-433), the per-bus evaluators (293-398) and the
+// Pade/convergence test (608-641, analytic_continuation.py).  The Pade value is obtained
+// with Wynn's epsilon algorithm kept incrementally: each order appends one anti-diagonal.
+template <int G>
+__global__ void k_rhs_conv(PlanDev p, WorkDev w) {
+    int grp = blockIdx.y;
+    int gf = w.g_flags[grp];
+    if (gf & (GF_DONE | GF_PASSEND)) return;
+    int flat = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = flat / G, s = flat % G;
+    if (i >= p.N) return;
+    int sg = grp * G + s;
+    if (w.s_status[sg] != ST_ACTIVE) return;
+    const int N = p.N;
+    const int j = w.g_n[grp] + 1;  // order just solved
+    size_t bi = ix<G>(grp, N, i, s);
+    unsigned char bt = w.btype[bi];
+    double2 v = w.xb[bi];
+    w.Vh[hx<G>(w, N, grp, j, i, s)] = v;                                          // helm.py:412-414
+    if (bt == HELM_BUS_SLACK) {
+        w.rhs[bi] = make_double2(0.0, 0.0);
+        return;
+    }
+    // --- epsilon anti-diagonal of order j (Wynn; analytic_continuation.py:9-26 is the
+    //     reference's own statement of the algorithm)
+    {
+        double2 prev1 = w.Eh[hx<G>(w, N, grp, 0, i, s)];   // eps_0^(j-1) = S_{j-1}
+        double2 prev2 = make_double2(0.0, 0.0);            // eps_{-1} = 0
+        double2 cur = cadd(prev1, v);                      // S_j
+        w.Eh[hx<G>(w, N, grp, 0, i, s)] = cur;
+        for (int k = 1; k <= j; ++k) {
+            double2 d = (k == 1) ? v : csub(cur, prev1);
+            double2 e = cadd(prev2, crecip_guard(d));
+            prev2 = prev1;
+            if (k < j) prev1 = w.Eh[hx<G>(w, N, grp, k, i, s)];
+            w.Eh[hx<G>(w, N, grp, k, i, s)] = e;
+            cur = e;
+        }
+        if ((j & 1) == 0) {                                // m = j+1 odd: cur = [j/2 / j/2] Pade at s = 1
+            if (j >= 4) {                                  // helm.py:611: m > 3
+                double2 old = w.Pcur[bi];
+                double mag1 = hypot(old.x, old.y), rad1 = atan2(old.y, old.x);
+                double mag2 = hypot(cur.x, cur.y), rad2 = atan2(cur.y, cur.x);
+                bool ok = (fabs(mag1 - mag2) <= w.mismatch) && (fabs(rad1 - rad2) <= w.mismatch);  // helm.py:618
+                if (!ok) w.s_fail[sg] = 1;
+            }
+            w.Pcur[bi] = cur;
+        }
+    }
+    double2 wj = make_double2(0.0, 0.0);
+    if (bt == HELM_BUS_PQ) {                                                      // helm.py:423-433
+        double2 aux = make_double2(0.0, 0.0);
+        for (int k = 0; k < j; ++k) {
+            double2 wk = w.Hh[hx<G>(w, N, grp, k, i, s)];
+            double2 vk = (k == 0) ? v : w.Vh[hx<G>(w, N, grp, j - k, i, s)];
+            aux = cadd(aux, cmul(wk, vk));
+        }
+        wj = make_double2(-aux.x, -aux.y);
+        w.Hh[hx<G>(w, N, grp, j, i, s)] = wj;
+    }
+    w.rhs[bi] = rhs_next<G>(p, w, grp, i, s, j, bt, v, wj, w.scale[sg]);
+}
+
+// ---- K_adv: per-group bookkeeping after an order (helm.py:608-657 control flow) ----------
+__global__ void k_advance(WorkDev w) {
+    int grp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (grp >= w.ngroups) return;
+    int gf = w.g_flags[grp];
+    if (gf & (GF_DONE | GF_PASSEND)) return;
+    int j = w.g_n[grp] + 1, m = j + 1;
+    bool checked = ((j & 1) == 0) && j >= 4;
+    int nact = 0;
+    for (int s = 0; s < w.G; ++s) {
+        int sg = grp * w.G + s;
+        if (w.s_status[sg] == ST_ACTIVE) {
+            if (checked && !w.s_fail[sg]) {
+                w.s_status[sg] = ST_FROZEN;
+                w.s_mconv[sg] = m;
+            } else if (m > w.max_coef - 1) {
+                w.s_status[sg] = ST_DIVERGED;                                     // helm.py:654-657
+            } else {
+                nact++;
+            }
+        }
+        w.s_fail[sg] = 0;
+    }
+    w.g_n[grp] = j;
+    gf &= ~GF_NEEDFACTOR;
+    if (nact == 0) gf |= GF_PASSEND;
+    w.g_flags[grp] = gf;
+}
+
+// ---- K4: Q-limit check on the Pade voltages, result write-out (helm.py:452-490, 985) -----
+template <int G>
+__global__ void k_qlimit(PlanDev p, WorkDev w) {
+    int grp = blockIdx.y;
+    if (!(w.g_flags[grp] & GF_PASSEND)) return;
+    int flat = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = flat / G, s = flat % G;
+    if (i >= p.N) return;
+    int sg = grp * G + s;
+    if (w.s_status[sg] != ST_FROZEN) return;
+    const int N = p.N;
+    size_t bi = ix<G>(grp, N, i, s);
+    double2 vi = w.Pcur[bi];
+    if (sg < w.B) w.vout[(size_t)sg * N + p.perm[i]] = vi;
+    if (!w.enforce_q) return;
+    if (w.btype[bi] != HELM_BUS_PV) return;
+    const double2 *pc = w.Pcur + (size_t)grp * N * G;
+    double q = 0.0;
+    for (int a = p.adj_ptr[i]; a < p.adj_ptr[i + 1]; ++a) {                       // helm.py:461-464
+        double2 y = p.yfull[a];
+        double2 vk = pc[(size_t)p.adj_idx[a] * G + s];
+        q += vi.y * (y.x * vk.x - y.y * vk.y) - vi.x * (y.x * vk.y + y.y * vk.x);
+    }
+    double qg = q + p.qd[i] * w.scale[sg];                                        // helm.py:481
+    double lim = qg;
+    if (qg > p.qmax[i] || qg < p.qmin[i]) {                                       // helm.py:483-486
+        lim = (qg > p.qmax[i]) ? p.qmax[i] : p.qmin[i];
+        w.btype[bi] = HELM_BUS_PQ;
+        w.s_viol[sg] = 1;
+        atomicAdd(&w.s_nswitch[sg], 1);
+    }
+    w.Qg[bi] = lim;
+}
+
+// ---- K_pend: pass bookkeeping (helm.py:936-955, 644-653) ----------------------------------
+__global__ void k_pass_end(WorkDev w) {
+    int grp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (grp >= w.ngroups) return;
+    int gf = w.g_flags[grp];
+    if (!(gf & GF_PASSEND)) return;
+    int any = 0;
+    for (int s = 0; s < w.G; ++s) {
+        int sg = grp * w.G + s;
+        if (w.s_status[sg] == ST_FROZEN) {
+            int np = w.s_npass[sg];
+            if (np < HELM_MAX_PASSES) w.s_ncoef[sg * HELM_MAX_PASSES + np] = w.s_mconv[sg];
+            w.s_npass[sg] = np + 1;
+            if (w.s_viol[sg] && np + 1 < 4 * HELM_MAX_PASSES) {
+                w.s_status[sg] = ST_ACTIVE;
+                w.s_viol[sg] = 0;
+                any = 1;
+            } else {
+                w.s_status[sg] = ST_CONVERGED;
+            }
+        }
+    }
+    gf &= ~GF_PASSEND;
+    if (any) {
+        gf |= GF_NEEDFACTOR;
+        w.g_n[grp] = 0;
+    } else {
+        gf |= GF_DONE;
+        atomicSub(w.active_groups, 1);
+    }
+    w.g_flags[grp] = gf;
+}
+
+// ---- K_setup: initial per-scenario state ---------------------------------------------------
+template <int G>
+__global__ void k_setup(PlanDev p, WorkDev w, const double *scale_in) {
+    int grp = blockIdx.y;
+    int flat = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = flat / G, s = flat % G;
+    int sg = grp * G + s;
+    if (i < p.N) {
+        size_t bi = ix<G>(grp, p.N, i, s);
+        w.btype[bi] = p.btype0[i];
+        w.Qg[bi] = 0.0;                                                          // classes.py:252
+        w.VVant[bi] = 0.0;
+        w.Pcur[bi] = make_double2(0.0, 0.0);
+    }
+    if (flat < G) {
+        bool real = sg < w.B;
+        w.scale[sg] = real ? scale_in[sg] : 1.0;
+        w.s_status[sg] = real ? ST_ACTIVE : ST_PAD;
+        w.s_mconv[sg] = 0; w.s_fail[sg] = 0; w.s_viol[sg] = 0; w.s_npass[sg] = 0; w.s_nswitch[sg] = 0;
+        for (int k = 0; k < HELM_MAX_PASSES; ++k) w.s_ncoef[sg * HELM_MAX_PASSES + k] = 0;
+    }
+    if (flat == 0) {
+        w.g_n[grp] = 0;
+        w.g_flags[grp] = GF_NEEDFACTOR;
+        if (grp == 0) *w.active_groups = w.ngroups;
+    }
+}
+
+__global__ void k_export(WorkDev w, int *status, int *ncoef, int *nswitch) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= w.B) return;
+    int st = w.s_status[b];
+    status[b] = (st == ST_CONVERGED) ? HELM_ST_CONVERGED
+              : (st == ST_DIVERGED)  ? HELM_ST_DIVERGED
+              : (st == ST_SINGULAR)  ? HELM_ST_SINGULAR : HELM_ST_RUNNING;
+    if (nswitch) nswitch[b] = w.s_nswitch[b];
+    if (ncoef)
+        for (int k = 0; k < HELM_MAX_PASSES; ++k) ncoef[b * HELM_MAX_PASSES + k] = w.s_ncoef[b * HELM_MAX_PASSES + k];
+}
+
+// ---- microbenchmarks for the roofline denominators ------------------------------------------
+__global__ void k_dfma_peak(double *out, int iters) {
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    double b = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+__global__ void k_copy(const double2 *__restrict__ a, double2 *__restrict__ b, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) b[i] = a[i];
+}
+
+}  // namespace
+
+// =================================================================================================
+// Host side
+// =================================================================================================
+struct helm_plan {
+    helm::Symbolic S;
+    PlanDev d;
+    std::vector<void *> dev_allocs;
+    int n_pv = 0;
+    int n_factor_updates = 0;
+    // cached workspace for the host-buffer entry point
+    void *ws = nullptr;
+    size_t ws_bytes = 0;
+    double *d_scale = nullptr, *d_vout = nullptr;
+    int *d_status = nullptr, *d_ncoef = nullptr, *d_nswitch = nullptr;
+    int cached_B = 0;
+    int *h_pinned = nullptr;
+    double *h_vout_pinned = nullptr;
+    size_t h_vout_bytes = 0;
+    cudaStream_t stream = nullptr;
+};
+
+namespace {
+
+template <typename T>
+int upload(helm_plan *pl, const std::vector<T> &v, const T **out) {
+    void *d = nullptr;
+    size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+    CUDA_TRY(cudaMalloc(&d, bytes));
+    pl->dev_allocs.push_back(d);
+    if (!v.empty()) CUDA_TRY(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = (const T *)d;
+    return HELM_OK;
+}
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+int pick_group(int n_scen, int requested) {
+    if (requested == 1 || requested == 2 || requested == 4 || requested == 8 || requested == 16 || requested == 32)
+        return requested;
+    if (n_scen >= 2048) return 8;
+    if (n_scen >= 512) return 4;
+    if (n_scen >= 64) return 2;
+    return 1;
+}
+
+struct WsLayout {
+    size_t total = 0;
+    size_t off_scale, off_sint, off_gint, off_btype, off_Qg, off_VVant, off_Pcur, off_rhs, off_xb, off_lu, off_Vh, off_Hh, off_Eh;
+    int G, ngroups, Bp, K;
+};
+
+WsLayout layout(const helm_plan *pl, int B, const helm_params *prm) {
+    WsLayout L;
+    L.G = pick_group(B, prm->group);
+    L.ngroups = (B + L.G - 1) / L.G;
+    L.Bp = L.ngroups * L.G;
+    L.K = prm->max_coefficients + 1;
+    size_t N = pl->S.N, per = (size_t)L.Bp * N;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes); return r; };
+    L.off_scale = take(sizeof(double) * L.Bp);
+    L.off_sint = take(sizeof(int) * L.Bp * (6 + HELM_MAX_PASSES));
+    L.off_gint = take(sizeof(int) * (2 * L.ngroups + 4));
+    L.off_btype = take(per);
+    L.off_Qg = take(per * sizeof(double));
+    L.off_VVant = take(per * sizeof(double));
+    L.off_Pcur = take(per * sizeof(double2));
+    L.off_rhs = take(per * sizeof(double2));
+    L.off_xb = take(per * sizeof(double2));
+    L.off_lu = take((size_t)L.Bp * pl->S.nslots * 2 * sizeof(double2));
+    L.off_Vh = take(per * L.K * sizeof(double2));
+    L.off_Hh = take(per * L.K * sizeof(double2));
+    L.off_Eh = take(per * L.K * sizeof(double2));
+    L.total = o;
+    return L;
+}
+
+WorkDev bind(const helm_plan *pl, const WsLayout &L, int B, const helm_params *prm, void *ws, double *vout) {
+    WorkDev w;
+    char *b = (char *)ws;
+    w.B = B; w.G = L.G; w.ngroups = L.ngroups; w.K = L.K;
+    w.mismatch = prm->mismatch; w.max_coef = prm->max_coefficients; w.enforce_q = prm->enforce_q_limits;
+    w.scale = (double *)(b + L.off_scale);
+    int *si = (int *)(b + L.off_sint);
+    w.s_status = si; w.s_mconv = si + L.Bp; w.s_fail = si + 2 * L.Bp; w.s_viol = si + 3 * L.Bp;
+    w.s_npass = si + 4 * L.Bp; w.s_nswitch = si + 5 * L.Bp; w.s_ncoef = si + 6 * L.Bp;
+    int *gi = (int *)(b + L.off_gint);
+    w.g_n = gi; w.g_flags = gi + L.ngroups; w.active_groups = gi + 2 * L.ngroups;
+    w.btype = (unsigned char *)(b + L.off_btype);
+    w.Qg = (double *)(b + L.off_Qg);
+    w.VVant = (double *)(b + L.off_VVant);
+    w.Pcur = (double2 *)(b + L.off_Pcur);
+    w.rhs = (double2 *)(b + L.off_rhs);
+    w.xb = (double2 *)(b + L.off_xb);
+    w.lu = (double2 *)(b + L.off_lu);
+    w.Vh = (double2 *)(b + L.off_Vh);
+    w.Hh = (double2 *)(b + L.off_Hh);
+    w.Eh = (double2 *)(b + L.off_Eh);
+    w.vout = (double2 *)vout;
+    return w;
+}
+
+constexpr int T_ELEM = 256;   // threads per CTA of the per-(item, scenario) kernels
+constexpr int T_SOLVE = 256;  // threads per CTA of the factor / solve kernels
+
+enum { KI_ASM = 0, KI_FACTOR, KI_SOLVE, KI_RHS, KI_ADV, KI_QLIM, KI_PEND, KI_INIT, KI_COUNT };
+
+template <int G>
+void launch_kernel(int which, const PlanDev &p, const WorkDev &w, cudaStream_t st) {
+    dim3 gridBus((p.N * G + T_ELEM - 1) / T_ELEM, w.ngroups);
+    dim3 gridSlot((p.nslots * G + T_ELEM - 1) / T_ELEM, w.ngroups);
+    int gridGrp = (w.ngroups + 127) / 128;
+    switch (which) {
+        case KI_ASM: k_assemble<G><<<gridSlot, T_ELEM, 0, st>>>(p, w); break;
+        case KI_FACTOR: k_factor<G, T_SOLVE><<<w.ngroups, T_SOLVE, 0, st>>>(p, w); break;
+        case KI_INIT: k_init<G><<<gridBus, T_ELEM, 0, st>>>(p, w); break;
+        case KI_SOLVE: k_solve<G, T_SOLVE><<<w.ngroups, T_SOLVE, 0, st>>>(p, w); break;
+        case KI_RHS: k_rhs_conv<G><<<gridBus, T_ELEM, 0, st>>>(p, w); break;
+        case KI_ADV: k_advance<<<gridGrp, 128, 0, st>>>(w); break;
+        case KI_QLIM: k_qlimit<G><<<gridBus, T_ELEM, 0, st>>>(p, w); break;
+        case KI_PEND: k_pass_end<<<gridGrp, 128, 0, st>>>(w); break;
+    }
+}
+
+void launch_any(int G, int which, const PlanDev &p, const WorkDev &w, cudaStream_t st) {
+    switch (G) {
+        case 1: launch_kernel<1>(which, p, w, st); break;
+        case 2: launch_kernel<2>(which, p, w, st); break;
+        case 4: launch_kernel<4>(which, p, w, st); break;
+        case 8: launch_kernel<8>(which, p, w, st); break;
+        case 16: launch_kernel<16>(which, p, w, st); break;
+        default: launch_kernel<32>(which, p, w, st); break;
+    }
+}
+
+void launch_setup(int G, const PlanDev &p, const WorkDev &w, const double *d_scale, cudaStream_t st) {
+    dim3 gridBus((p.N * G + T_ELEM - 1) / T_ELEM, w.ngroups);
+    switch (G) {
+        case 1: k_setup<1><<<gridBus, T_ELEM, 0, st>>>(p, w, d_scale); break;
+        case 2: k_setup<2><<<gridBus, T_ELEM, 0, st>>>(p, w, d_scale); break;
+        case 4: k_setup<4><<<gridBus, T_ELEM, 0, st>>>(p, w, d_scale); break;
+        case 8: k_setup<8><<<gridBus, T_ELEM, 0, st>>>(p, w, d_scale); break;
+        case 16: k_setup<16><<<gridBus, T_ELEM, 0, st>>>(p, w, d_scale); break;
+        default: k_setup<32><<<gridBus, T_ELEM, 0, st>>>(p, w, d_scale); break;
+    }
+}
+
+// kernels of one per-order step, in order
+const int STEP_SEQ[] = {KI_ASM, KI_FACTOR, KI_INIT, KI_SOLVE, KI_RHS, KI_ADV, KI_QLIM, KI_PEND};
+constexpr int STEP_LEN = sizeof(STEP_SEQ) / sizeof(int);
+
+}  // namespace
+
+extern "C" {
+
+const char *helm_last_error(void) { return g_err.c_str(); }
+
+int helm_plan_create(const helm_grid_host *g, helm_plan **out) {
+    if (!g || !out) { g_err = "null argument"; return HELM_E_ARG; }
+    helm_plan *pl = new helm_plan();
+    std::string err;
+    if (!helm::build_symbolic(g->n_bus, g->adj_ptr, g->adj_idx, pl->S, err)) {
+        g_err = err;
+        delete pl;
+        return HELM_E_STRUCT;
+    }
+    const helm::Symbolic &S = pl->S;
+    const int N = S.N;
+    PlanDev &d = pl->d;
+    d.N = N; d.nL = S.nL; d.nU = S.nU; d.nslots = S.nslots;
+    d.nLlev = (int)S.llev_ptr.size() - 1; d.nUlev = (int)S.ulev_ptr.size() - 1;
+    d.nadj = S.nnz_adj; d.slack = S.iperm[g->slack];
+    pl->n_factor_updates = (int)S.fsrc.size();
+    // permute the grid data into the elimination numbering
+    std::vector<double2> ytr(S.nnz_adj), yfull(S.nnz_adj), ysh(N), phv;
+    std::vector<int> php(N + 1, 0), phi;
+    std::vector<double> vsp(N), pg(N), pd(N), qd(N), qmax(N), qmin(N);
+    std::vector<unsigned char> bt(N);
+    for (int a = 0; a < S.nnz_adj; ++a) {
+        int src = S.adj_src[a];
+        ytr[a] = make_double2(g->ytrans[2 * src], g->ytrans[2 * src + 1]);
+        yfull[a] = make_double2(g->yfull[2 * src], g->yfull[2 * src + 1]);
+    }
+    for (int r = 0; r < N; ++r) {
+        int o = S.perm[r];
+        ysh[r] = make_double2(g->yshunt[2 * o], g->yshunt[2 * o + 1]);
+        vsp[r] = g->vsp[o]; pg[r] = g->pg[o]; pd[r] = g->pd[o]; qd[r] = g->qd[o];
+        qmax[r] = g->qgmax[o]; qmin[r] = g->qgmin[o]; bt[r] = g->bus_type[o];
+        if (bt[r] == HELM_BUS_PV) pl->n_pv++;
+        for (int a = g->phase_ptr[o]; a < g->phase_ptr[o + 1]; ++a) {
+            phi.push_back(S.iperm[g->phase_idx[a]]);
+            phv.push_back(make_double2(g->phase_val[2 * a], g->phase_val[2 * a + 1]));
+        }
+        php[r + 1] = (int)phi.size();
+    }
+    int rc;
+#define UP(vec, field) if ((rc = upload(pl, vec, &d.field)) != HELM_OK) { helm_plan_destroy(pl); return rc; }
+    UP(S.adj_ptr, adj_ptr) UP(S.adj_idx, adj_idx) UP(S.adj_slot, adj_slot)
+    UP(ytr, ytr) UP(yfull, yfull) UP(ysh, yshunt)
+    UP(php, ph_ptr) UP(phi, ph_idx) UP(phv, ph_val)
+    UP(vsp, vsp) UP(pg, pg) UP(pd, pd) UP(qd, qd) UP(qmax, qmax) UP(qmin, qmin) UP(bt, btype0)
+    UP(S.perm, perm) UP(S.lptr, lptr) UP(S.lcol, lcol) UP(S.llev_ptr, llev_ptr)
+    UP(S.urow, urow) UP(S.ulev_ptr, ulev_ptr) UP(S.uptr, uptr) UP(S.ucol, ucol) UP(S.dslot, dslot)
+    UP(S.slot_src, slot_src) UP(S.slot_row, slot_row)
+    UP(S.fptr, fptr) UP(S.fsrc, fsrc) UP(S.fdst, fdst)
+#undef UP
+    *out = pl;
+    return HELM_OK;
+}
+
+void helm_plan_destroy(helm_plan *pl) {
+    if (!pl) return;
+    for (void *p : pl->dev_allocs) cudaFree(p);
+    if (pl->ws) cudaFree(pl->ws);
+    if (pl->d_scale) cudaFree(pl->d_scale);
+    if (pl->d_vout) cudaFree(pl->d_vout);
+    if (pl->d_status) cudaFree(pl->d_status);
+    if (pl->d_ncoef) cudaFree(pl->d_ncoef);
+    if (pl->d_nswitch) cudaFree(pl->d_nswitch);
+    if (pl->h_pinned) cudaFreeHost(pl->h_pinned);
+    if (pl->h_vout_pinned) cudaFreeHost(pl->h_vout_pinned);
+    if (pl->stream) cudaStreamDestroy(pl->stream);
+    delete pl;
+}
+
+int helm_plan_get_info(const helm_plan *pl, helm_plan_info *info) {
+    if (!pl || !info) { g_err = "null argument"; return HELM_E_ARG; }
+    info->n_bus = pl->S.N; info->nnz_adj = pl->S.nnz_adj;
+    info->n_l_blocks = pl->S.nL; info->n_u_blocks = pl->S.nU; info->n_slots = pl->S.nslots;
+    info->n_l_levels = pl->d.nLlev; info->n_u_levels = pl->d.nUlev;
+    info->n_factor_updates = pl->n_factor_updates; info->n_pv = pl->n_pv; info->reserved = 0;
+    return HELM_OK;
+}
+
+int helm_plan_get_perm(const helm_plan *pl, int32_t *perm_out) {
+    if (!pl || !perm_out) { g_err = "null argument"; return HELM_E_ARG; }
+    std::copy(pl->S.perm.begin(), pl->S.perm.end(), perm_out);
+    return HELM_OK;
+}
+
+size_t helm_workspace_bytes(const helm_plan *pl, int32_t n_scen, const helm_params *prm) {
+    if (!pl || !prm || n_scen <= 0) return 0;
+    return layout(pl, n_scen, prm).total;
+}
+
+static int check_params(const helm_params *prm) {
+    if (!prm) { g_err = "null params"; return HELM_E_ARG; }
+    if (prm->max_coefficients < 5) { g_err = "max_coefficients must be >= 5 (helm.py:882-884)"; return HELM_E_ARG; }
+    if (!(prm->mismatch > 0)) { g_err = "mismatch must be positive"; return HELM_E_ARG; }
+    return HELM_OK;
+}
+
+int helm_solve_batch_device(helm_plan *pl, int32_t B, const double *d_scale, const helm_params *prm,
+                            void *d_ws, size_t ws_bytes, double *d_vout, int32_t *d_status,
+                            int32_t *d_ncoef, int32_t *d_nswitch, void *stream_, helm_stats *stats) {
+    if (!pl || !d_scale || !d_ws || !d_vout || !d_status || B <= 0) { g_err = "null/invalid argument"; return HELM_E_ARG; }
+    int rc = check_params(prm);
+    if (rc) return rc;
+    WsLayout L = layout(pl, B, prm);
+    if (ws_bytes < L.total) { g_err = "workspace too small"; return HELM_E_NOMEM; }
+    cudaStream_t st = (cudaStream_t)stream_;
+    WorkDev w = bind(pl, L, B, prm, d_ws, d_vout);
+    const PlanDev &p = pl->d;
+    const bool profile = getenv("HELM_B200_PROFILE") != nullptr;
+    const bool use_graph = prm->use_graph && !profile;
+    int poll_every = prm->poll_every > 0 ? prm->poll_every : 4;
+    if (!pl->h_pinned) CUDA_TRY(cudaMallocHost((void **)&pl->h_pinned, 64));
+
+    cudaEvent_t ev0, ev1;
+    CUDA_TRY(cudaEventCreate(&ev0));
+    CUDA_TRY(cudaEventCreate(&ev1));
+    CUDA_TRY(cudaEventRecord(ev0, st));
+    launch_setup(L.G, p, w, d_scale, st);
+
+    helm_stats local;
+    memset(&local, 0, sizeof(local));
+    local.kernel_launches = 1;
+
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    if (use_graph) {
+        CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        for (int rep = 0; rep < poll_every; ++rep)
+            for (int k = 0; k < STEP_LEN; ++k) launch_any(L.G, STEP_SEQ[k], p, w, st);
+        CUDA_TRY(cudaStreamEndCapture(st, &graph));
+        CUDA_TRY(cudaGraphInstantiate(&gexec, graph, 0));
+    }
+    std::vector<cudaEvent_t> pev;
+    if (profile) {
+        pev.resize(STEP_LEN + 1);
+        for (auto &e : pev) cudaEventCreate(&e);
+    }
+    const long max_steps = (long)(prm->max_coefficients + 2) * 4 * HELM_MAX_PASSES;
+    long steps = 0;
+    int active = 1;
+    while (active > 0 && steps < max_steps) {
+        if (use_graph) {
+            CUDA_TRY(cudaGraphLaunch(gexec, st));
+            local.graph_launches++;
+            local.kernel_launches += (int64_t)poll_every * STEP_LEN;
+            steps += poll_every;
+        } else {
+            for (int rep = 0; rep < poll_every; ++rep) {
+                for (int k = 0; k < STEP_LEN; ++k) {
+                    if (profile) cudaEventRecord(pev[k], st);
+                    launch_any(L.G, STEP_SEQ[k], p, w, st);
+                }
+                if (profile) {
+                    cudaEventRecord(pev[STEP_LEN], st);
+                    cudaEventSynchronize(pev[STEP_LEN]);
+                    for (int k = 0; k < STEP_LEN; ++k) {
+                        float ms = 0;
+                        cudaEventElapsedTime(&ms, pev[k], pev[k + 1]);
+                        local.ms_kernel[STEP_SEQ[k]] += ms;
+                    }
+                }
+                local.kernel_launches += STEP_LEN;
+                steps++;
+            }
+        }
+        CUDA_TRY(cudaMemcpyAsync(pl->h_pinned, w.active_groups, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        active = pl->h_pinned[0];
+    }
+    k_export<<<(B + 127) / 128, 128, 0, st>>>(w, d_status, d_ncoef, d_nswitch);
+    local.kernel_launches++;
+    CUDA_TRY(cudaEventRecord(ev1, st));
+    CUDA_TRY(cudaEventSynchronize(ev1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    local.ms_total = ms;
+    local.steps = steps;
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    for (auto &e : pev) cudaEventDestroy(e);
+    if (gexec) cudaGraphExecDestroy(gexec);
+    if (graph) cudaGraphDestroy(graph);
+    CUDA_TRY(cudaGetLastError());
+    if (stats) *stats = local;
+    return HELM_OK;
+}
+
+int helm_solve_batch_host(helm_plan *pl, int32_t B, const double *h_scale, const helm_params *prm,
+                          double *h_vout, int32_t *h_status, int32_t *h_ncoef, int32_t *h_nswitch,
+                          helm_stats *stats) {
+    if (!pl || !h_scale || !h_vout || !h_status || B <= 0) { g_err = "null/invalid argument"; return HELM_E_ARG; }
+    int rc = check_params(prm);
+    if (rc) return rc;
+    WsLayout L = layout(pl, B, prm);
+    if (!pl->stream) CUDA_TRY(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
+    if (pl->ws_bytes < L.total) {
+        if (pl->ws) cudaFree(pl->ws);
+        pl->ws = nullptr; pl->ws_bytes = 0;
+        CUDA_TRY(cudaMalloc(&pl->ws, L.total));
+        pl->ws_bytes = L.total;
+    }
+    size_t N = pl->S.N;
+    if (pl->cached_B < B) {
+        if (pl->d_scale) { cudaFree(pl->d_scale); cudaFree(pl->d_vout); cudaFree(pl->d_status); cudaFree(pl->d_ncoef); cudaFree(pl->d_nswitch); }
+        pl->d_scale = nullptr; pl->cached_B = 0;
+        CUDA_TRY(cudaMalloc((void **)&pl->d_scale, sizeof(double) * B));
+        CUDA_TRY(cudaMalloc((void **)&pl->d_vout, sizeof(double) * 2 * N * B));
+        CUDA_TRY(cudaMalloc((void **)&pl->d_status, sizeof(int) * B));
+        CUDA_TRY(cudaMalloc((void **)&pl->d_ncoef, sizeof(int) * B * HELM_MAX_PASSES));
+        CUDA_TRY(cudaMalloc((void **)&pl->d_nswitch, sizeof(int) * B));
+        pl->cached_B = B;
+    }
+    cudaStream_t st = pl->stream;
+    CUDA_TRY(cudaMemcpyAsync(pl->d_scale, h_scale, sizeof(double) * B, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(pl->d_vout, 0, sizeof(double) * 2 * N * B, st));
+    rc = helm_solve_batch_device(pl, B, pl->d_scale, prm, pl->ws, pl->ws_bytes, pl->d_vout, pl->d_status,
+                                 pl->d_ncoef, pl->d_nswitch, st, stats);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(h_vout, pl->d_vout, sizeof(double) * 2 * N * B, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(h_status, pl->d_status, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+    if (h_ncoef) CUDA_TRY(cudaMemcpyAsync(h_ncoef, pl->d_ncoef, sizeof(int) * B * HELM_MAX_PASSES, cudaMemcpyDeviceToHost, st));
+    if (h_nswitch) CUDA_TRY(cudaMemcpyAsync(h_nswitch, pl->d_nswitch, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return HELM_OK;
+}
+
+int helm_debug_factor_solve(helm_plan *pl, int32_t B, int32_t group, const uint8_t *h_bt,
+                            const double *h_rhs, double *h_x) {
+    if (!pl || !h_bt || !h_rhs || !h_x || B <= 0) { g_err = "null/invalid argument"; return HELM_E_ARG; }
+    helm_params prm;
+    memset(&prm, 0, sizeof(prm));
+    prm.mismatch = 1e-8; prm.max_coefficients = 5; prm.group = group;
+    WsLayout L = layout(pl, B, &prm);
+    void *ws = nullptr;
+    double *d_scale = nullptr;
+    CUDA_TRY(cudaMalloc(&ws, L.total));
+    CUDA_TRY(cudaMalloc((void **)&d_scale, sizeof(double) * B));
+    std::vector<double> ones(B, 1.0);
+    CUDA_TRY(cudaMemcpy(d_scale, ones.data(), sizeof(double) * B, cudaMemcpyHostToDevice));
+    WorkDev w = bind(pl, L, B, &prm, ws, nullptr);
+    const PlanDev &p = pl->d;
+    const helm::Symbolic &S = pl->S;
+    launch_setup(L.G, p, w, d_scale, 0);
+    CUDA_TRY(cudaDeviceSynchronize());
+    size_t N = S.N, per = (size_t)L.Bp * N;
+    std::vector<unsigned char> bt(per, HELM_BUS_PQ);
+    std::vector<double2> rhs(per, make_double2(0, 0));
+    for (int b = 0; b < B; ++b) {
+        int grp = b / L.G, s = b % L.G;
+        for (size_t r = 0; r < N; ++r) {
+            int o = S.perm[r];
+            size_t bi = ((size_t)grp * N + r) * L.G + s;
+            bt[bi] = h_bt[(size_t)b * N + o];
+            rhs[bi] = make_double2(h_rhs[((size_t)b * N + o) * 2], h_rhs[((size_t)b * N + o) * 2 + 1]);
+        }
+    }
+    CUDA_TRY(cudaMemcpy(w.btype, bt.data(), per, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(w.rhs, rhs.data(), per * sizeof(double2), cudaMemcpyHostToDevice));
+    launch_any(L.G, KI_ASM, p, w, 0);
+    launch_any(L.G, KI_FACTOR, p, w, 0);
+    launch_any(L.G, KI_SOLVE, p, w, 0);
+    CUDA_TRY(cudaDeviceSynchronize());
+    std::vector<double2> x(per);
+    CUDA_TRY(cudaMemcpy(x.data(), w.xb, per * sizeof(double2), cudaMemcpyDeviceToHost));
+    for (int b = 0; b < B; ++b) {
+        int grp = b / L.G, s = b % L.G;
+        for (size_t r = 0; r < N; ++r) {
+            int o = S.perm[r];
+            double2 v = x[((size_t)grp * N + r) * L.G + s];
+            h_x[((size_t)b * N + o) * 2] = v.x;
+            h_x[((size_t)b * N + o) * 2 + 1] = v.y;
+        }
+    }
+    cudaFree(ws);
+    cudaFree(d_scale);
+    return HELM_OK;
+}
+
+int helm_measure_peaks(double *dfma_tflops, double *copy_gbs) {
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    float ms = 0;
+    if (dfma_tflops) {
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        int blocks = sms * 8, threads = 256, iters = 1 << 16;
+        double *out = nullptr;
+        CUDA_TRY(cudaMalloc((void **)&out, sizeof(double) * blocks * threads));
+        k_dfma_peak<<<blocks, threads>>>(out, 1024);
+        double best = 0;
+        for (int rep = 0; rep < 3; ++rep) {
+            cudaEventRecord(e0);
+            k_dfma_peak<<<blocks, threads>>>(out, iters);
+            cudaEventRecord(e1);
+            CUDA_TRY(cudaEventSynchronize(e1));
+            cudaEventElapsedTime(&ms, e0, e1);
+            double fl = 2.0 * 8 * (double)iters * blocks * threads;
+            best = std::max(best, fl / (ms * 1e-3) / 1e12);
+        }
+        *dfma_tflops = best;
+        cudaFree(out);
+    }
+    if (copy_gbs) {
+        size_t n = (size_t)1 << 26;  // 64 Mi double2 = 1 GiB each way
+        double2 *a = nullptr, *b = nullptr;
+        CUDA_TRY(cudaMalloc((void **)&a, n * sizeof(double2)));
+        CUDA_TRY(cudaMalloc((void **)&b, n * sizeof(double2)));
+        cudaMemset(a, 0, n * sizeof(double2));
+        double best = 0;
+        for (int rep = 0; rep < 5; ++rep) {
+            cudaEventRecord(e0);
+            k_copy<<<148 * 16, 512>>>(a, b, n);
+            cudaEventRecord(e1);
+            CUDA_TRY(cudaEventSynchronize(e1));
+            cudaEventElapsedTime(&ms, e0, e1);
+            best = std::max(best, 2.0 * n * sizeof(double2) / (ms * 1e-3) / 1e9);
+        }
+        *copy_gbs = best;
+        cudaFree(a);
+        cudaFree(b);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return HELM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,274 @@
+// Host symbolic analysis: ordering, fill, level sets, schedules.
+//
+// The HELM recursion matrix (reference helm.py:30-60) is a 2N x 2N real matrix
+// made of 2x2 blocks on the pattern of the bus adjacency: block (i,j) exists iff
+// buses i and j share a branch.  Treating every block as one entry gives an
+// N x N structurally symmetric pattern that is the same for every PV/PQ
+// switching state (a PV row keeps a subset of the PQ row, helm.py:50-60), so one
+// symbolic analysis serves every Q-limit pass and every scenario.
+//
+//  1. minimum-degree ordering on the elimination graph (exact external degree,
+//     deterministic tie-break on the bus index);
+//  2. the filled graph falls out of the elimination (neighbours at elimination
+//     time = upper pattern of that pivot);
+//  3. buses are renumbered by dependency level of the forward solve (a
+//     topological reordering of the elimination tree leaves the fill unchanged),
+//     so the rows of one L-level are contiguous;
+//  4. level sets of the backward solve, slot numbering in consumption order,
+//     row-wise (up-looking) numeric factorization schedule, assembly map.
+#include "symbolic.h"
+
+#include <algorithm>
+#include <queue>
+#include <utility>
+
+namespace helm {
+
+namespace {
+
+inline bool sorted_contains(const std::vector<int> &v, int x) {
+    return std::binary_search(v.begin(), v.end(), x);
+}
+
+inline void sorted_insert(std::vector<int> &v, int x) {
+    auto it = std::lower_bound(v.begin(), v.end(), x);
+    if (it == v.end() || *it != x) v.insert(it, x);
+}
+
+inline void sorted_erase(std::vector<int> &v, int x) {
+    auto it = std::lower_bound(v.begin(), v.end(), x);
+    if (it != v.end() && *it == x) v.erase(it);
+}
+
+}  // namespace
+
+bool build_symbolic(int N, const int32_t *adj_ptr, const int32_t *adj_idx, Symbolic &S,
+                    std::string &err) {
+    if (N <= 0) {
+        err = "n_bus must be positive";
+        return false;
+    }
+    S = Symbolic();
+    S.N = N;
+    S.nnz_adj = adj_ptr[N];
+
+    // ---- elimination graph (off-diagonal, symmetrised) -------------------------
+    std::vector<std::vector<int>> g(N);
+    for (int i = 0; i < N; ++i) {
+        bool has_diag = false;
+        for (int p = adj_ptr[i]; p < adj_ptr[i + 1]; ++p) {
+            int j = adj_idx[p];
+            if (j < 0 || j >= N) {
+                err = "adjacency index out of range";
+                return false;
+            }
+            if (j == i) {
+                has_diag = true;
+                continue;
+            }
+            sorted_insert(g[i], j);
+            sorted_insert(g[j], i);
+        }
+        if (!has_diag) {
+            err = "adjacency row without its diagonal entry";
+            return false;
+        }
+    }
+
+    // ---- 1+2. minimum degree with explicit fill ---------------------------------
+    std::vector<std::vector<int>> higher(N);  // filled-graph neighbours eliminated later
+    std::vector<int> pos(N, -1), order;
+    order.reserve(N);
+    typedef std::pair<int, int> DI;
+    std::priority_queue<DI, std::vector<DI>, std::greater<DI>> heap;
+    for (int i = 0; i < N; ++i) heap.push(DI((int)g[i].size(), i));
+    while (!heap.empty()) {
+        DI top = heap.top();
+        heap.pop();
+        int v = top.second;
+        if (pos[v] >= 0 || top.first != (int)g[v].size()) continue;
+        pos[v] = (int)order.size();
+        order.push_back(v);
+        std::vector<int> nb;
+        nb.swap(g[v]);
+        for (int a : nb) sorted_erase(g[a], v);
+        for (size_t x = 0; x < nb.size(); ++x)
+            for (size_t y = x + 1; y < nb.size(); ++y) {
+                int a = nb[x], b = nb[y];
+                if (!sorted_contains(g[a], b)) {
+                    sorted_insert(g[a], b);
+                    sorted_insert(g[b], a);
+                }
+            }
+        for (int a : nb) heap.push(DI((int)g[a].size(), a));
+        higher[v].swap(nb);
+    }
+    if ((int)order.size() != N) {
+        err = "ordering did not visit every bus";
+        return false;
+    }
+
+    // ---- 3. forward-solve levels and renumbering --------------------------------
+    std::vector<int> lev(N, 0), lcount(N, 0);
+    for (int k = 0; k < N; ++k) {
+        int v = order[k];
+        for (int w : higher[v]) {
+            lev[w] = std::max(lev[w], lev[v] + 1);
+            lcount[w]++;
+        }
+    }
+    std::vector<int> byl(N);
+    for (int i = 0; i < N; ++i) byl[i] = i;
+    std::sort(byl.begin(), byl.end(), [&](int a, int b) {
+        if (lev[a] != lev[b]) return lev[a] < lev[b];
+        if (lcount[a] != lcount[b]) return lcount[a] > lcount[b];  // long rows first: balanced warps
+        return pos[a] < pos[b];
+    });
+    S.perm.assign(N, 0);
+    S.iperm.assign(N, 0);
+    for (int r = 0; r < N; ++r) {
+        S.perm[r] = byl[r];
+        S.iperm[byl[r]] = r;
+    }
+    int nLlev = lev[byl[N - 1]] + 1;
+    S.llev_ptr.assign(nLlev + 1, 0);
+    for (int r = 0; r < N; ++r) S.llev_ptr[lev[S.perm[r]] + 1]++;
+    for (int l = 0; l < nLlev; ++l) S.llev_ptr[l + 1] += S.llev_ptr[l];
+
+    // filled pattern in the new numbering
+    std::vector<std::vector<int>> Lrow(N), Urow(N);
+    for (int v = 0; v < N; ++v) {
+        int rv = S.iperm[v];
+        for (int w : higher[v]) {
+            int rw = S.iperm[w];
+            if (rw <= rv) {
+                err = "internal: level renumbering broke the elimination order";
+                return false;
+            }
+            Urow[rv].push_back(rw);
+            Lrow[rw].push_back(rv);
+        }
+    }
+    S.lptr.assign(N + 1, 0);
+    for (int r = 0; r < N; ++r) {
+        std::sort(Lrow[r].begin(), Lrow[r].end());
+        std::sort(Urow[r].begin(), Urow[r].end());
+        S.lptr[r + 1] = S.lptr[r] + (int)Lrow[r].size();
+    }
+    S.nL = S.lptr[N];
+    S.lcol.resize(S.nL);
+    for (int r = 0; r < N; ++r) std::copy(Lrow[r].begin(), Lrow[r].end(), S.lcol.begin() + S.lptr[r]);
+
+    // ---- 4a. backward-solve levels ------------------------------------------------
+    std::vector<int> ulev(N, 0);
+    int nUlev = 0;
+    for (int r = N - 1; r >= 0; --r) {
+        int l = 0;
+        for (int j : Urow[r]) l = std::max(l, ulev[j] + 1);
+        ulev[r] = l;
+        nUlev = std::max(nUlev, l + 1);
+    }
+    S.urow.resize(N);
+    for (int i = 0; i < N; ++i) S.urow[i] = i;
+    std::sort(S.urow.begin(), S.urow.end(), [&](int a, int b) {
+        if (ulev[a] != ulev[b]) return ulev[a] < ulev[b];
+        if (Urow[a].size() != Urow[b].size()) return Urow[a].size() > Urow[b].size();
+        return a < b;
+    });
+    S.qof.assign(N, 0);
+    S.ulev_ptr.assign(nUlev + 1, 0);
+    S.uptr.assign(N + 1, 0);
+    for (int q = 0; q < N; ++q) {
+        int r = S.urow[q];
+        S.qof[r] = q;
+        S.ulev_ptr[ulev[r] + 1]++;
+        S.uptr[q + 1] = S.uptr[q] + (int)Urow[r].size();
+    }
+    for (int l = 0; l < nUlev; ++l) S.ulev_ptr[l + 1] += S.ulev_ptr[l];
+    S.nU = S.uptr[N];
+    S.ucol.resize(S.nU);
+    for (int q = 0; q < N; ++q) {
+        const std::vector<int> &row = Urow[S.urow[q]];
+        std::copy(row.begin(), row.end(), S.ucol.begin() + S.uptr[q]);
+    }
+    S.nslots = S.nL + S.nU + N;
+    S.dslot.resize(N);
+    for (int r = 0; r < N; ++r) S.dslot[r] = S.slotD(S.qof[r]);
+
+    // slot lookup for block (r, c)
+    auto slot_of = [&](int r, int c) -> int {
+        if (c == r) return S.dslot[r];
+        if (c < r) {
+            auto b = S.lcol.begin() + S.lptr[r], e = S.lcol.begin() + S.lptr[r + 1];
+            auto it = std::lower_bound(b, e, c);
+            if (it == e || *it != c) return -1;
+            return (int)(it - S.lcol.begin());
+        }
+        int q = S.qof[r];
+        auto b = S.ucol.begin() + S.uptr[q], e = S.ucol.begin() + S.uptr[q + 1];
+        auto it = std::lower_bound(b, e, c);
+        if (it == e || *it != c) return -1;
+        return S.slotU(q, (int)(it - b));
+    };
+
+    // ---- 4b. row-wise numeric factorization schedule -----------------------------
+    S.fptr.assign(S.nL + 1, 0);
+    for (int r = 0; r < N; ++r)
+        for (int e = S.lptr[r]; e < S.lptr[r + 1]; ++e) {
+            int k = S.lcol[e];
+            const std::vector<int> &uk = Urow[k];
+            int qk = S.qof[k];
+            for (size_t t = 0; t < uk.size(); ++t) {
+                int j = uk[t];
+                int dst = slot_of(r, j);
+                if (dst < 0) {
+                    err = "internal: fill pattern is not closed under elimination";
+                    return false;
+                }
+                S.fsrc.push_back(S.slotU(qk, (int)t));
+                S.fdst.push_back(dst);
+            }
+            S.fptr[e + 1] = (int)S.fsrc.size();
+        }
+
+    // ---- 4c. adjacency in the new numbering + assembly map -------------------------
+    S.adj_ptr.assign(N + 1, 0);
+    for (int r = 0; r < N; ++r) {
+        int o = S.perm[r];
+        S.adj_ptr[r + 1] = S.adj_ptr[r] + (adj_ptr[o + 1] - adj_ptr[o]);
+    }
+    S.adj_idx.resize(S.nnz_adj);
+    S.adj_src.resize(S.nnz_adj);
+    S.adj_slot.resize(S.nnz_adj);
+    S.slot_src.assign(S.nslots, -1);
+    S.slot_row.assign(S.nslots, 0);
+    for (int r = 0; r < N; ++r) {
+        for (int e = S.lptr[r]; e < S.lptr[r + 1]; ++e) S.slot_row[e] = r;
+        int q = S.qof[r];
+        S.slot_row[S.slotD(q)] = r;
+        for (int t = 0; t < S.uptr[q + 1] - S.uptr[q]; ++t) S.slot_row[S.slotU(q, t)] = r;
+    }
+    for (int r = 0; r < N; ++r) {
+        int o = S.perm[r];
+        int a = S.adj_ptr[r];
+        for (int p = adj_ptr[o]; p < adj_ptr[o + 1]; ++p, ++a) {
+            int c = S.iperm[adj_idx[p]];
+            S.adj_idx[a] = c;
+            S.adj_src[a] = p;
+            int sl = slot_of(r, c);
+            if (sl < 0) {
+                err = "internal: adjacency entry missing from the filled pattern";
+                return false;
+            }
+            if (S.slot_src[sl] != -1) {
+                err = "duplicate adjacency entry";
+                return false;
+            }
+            S.adj_slot[a] = sl;
+            S.slot_src[sl] = a;
+        }
+    }
+    return true;
+}
+
+}  // namespace helm

@@ -1,0 +1,41 @@
+// Host-side symbolic analysis for the 2x2-block sparse LU used by the HELM
+// recursion matrix (replaces the symbolic half of scipy `factorized`,
+// reference helmpy/core/helm.py:106).  See DESIGN.md §3.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace helm {
+
+struct Symbolic {
+    int N = 0;
+    int nnz_adj = 0;
+    // numbering: new index r <-> original bus perm[r]; iperm[orig] = r
+    std::vector<int> perm, iperm;
+    // bus adjacency in the new numbering; entries keep the original row order
+    std::vector<int> adj_ptr, adj_idx, adj_src;  // adj_src: index into the caller's nnz arrays
+    std::vector<int> adj_slot;                   // LU slot holding block (r, adj_idx)
+    // strictly-lower pattern by row, ascending columns; slot of entry e is e
+    std::vector<int> lptr, lcol;
+    std::vector<int> llev_ptr;                   // rows of L-level l: [llev_ptr[l], llev_ptr[l+1])
+    // upper part in U-level order (roots first): position q <-> row urow[q]
+    std::vector<int> urow, qof, ulev_ptr, uptr, ucol;
+    int nL = 0, nU = 0, nslots = 0;
+    std::vector<int> dslot;                      // row -> slot of its (inverted) diagonal block
+    // numeric factorization schedule: for L entry e, updates u in [fptr[e], fptr[e+1])
+    // do  LU[fdst[u]] -= L_e * LU[fsrc[u]]
+    std::vector<int> fptr, fsrc, fdst;
+    // assembly map: slot -> adjacency entry (or -1 for fill), slot -> row
+    std::vector<int> slot_src, slot_row;
+
+    inline int slotD(int q) const { return nL + uptr[q] + q; }
+    inline int slotU(int q, int t) const { return nL + uptr[q] + q + 1 + t; }
+};
+
+// adj_ptr/adj_idx: symmetric bus adjacency with the diagonal included.
+// Returns false and sets err on malformed input.
+bool build_symbolic(int N, const int32_t *adj_ptr, const int32_t *adj_idx, Symbolic &S,
+                    std::string &err);
+
+}  // namespace helm

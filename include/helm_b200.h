@@ -1,0 +1,165 @@
+/*
+ * helm_b200.h — C ABI of the B200-native HELM + Pade hot path.
+ *
+ * The reference (HELMpy, pure Python) has no FFI; these entry points are what a
+ * binding for its hot path would call.  Each one names the reference code it
+ * replaces (paths relative to the reference repository):
+ *
+ *   helm_plan_create        helmpy/core/helm.py:30-107  modif_Ytrans  (matrix
+ *                           structure + scipy `factorized` symbolic part) and
+ *                           helmpy/core/classes.py:228-297 RunVariables (state)
+ *   helm_solve_batch_*      helmpy/core/helm.py:896-985 helm(): Q-limit pass
+ *                           loop (936-955), coefficient loop
+ *                           computing_voltages_mismatch (528-659), RHS
+ *                           evaluators (293-398), solve (602), V/W update
+ *                           (402-433), Pade + convergence (608-641,
+ *                           analytic_continuation.py:29-50), Q limits (452-490)
+ *
+ * Conventions: plain pointers and sizes only.  All functions return 0 on
+ * success or a negative HELM_E_* code; helm_last_error() gives the message.
+ * Complex numbers are interleaved (re, im) doubles.  Everything is fp64.
+ */
+#ifndef HELM_B200_H
+#define HELM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HELM_OK 0
+#define HELM_E_ARG (-1)
+#define HELM_E_CUDA (-2)
+#define HELM_E_NOMEM (-3)
+#define HELM_E_STRUCT (-4)
+
+/* per-scenario status written by the solver */
+#define HELM_ST_RUNNING 0
+#define HELM_ST_CONVERGED 2   /* helm() would return the voltage vector        */
+#define HELM_ST_DIVERGED 3    /* helm() would return None (helm.py:654-657)    */
+#define HELM_ST_SINGULAR 4    /* zero 2x2 pivot in the numeric factorization   */
+
+#define HELM_MAX_PASSES 16    /* Q-limit passes recorded in ncoef[]            */
+
+/* bus type codes (reference strings 'PQ', 'PV'/'PVLIM', 'Slack') */
+#define HELM_BUS_PQ 0
+#define HELM_BUS_PV 1
+#define HELM_BUS_SLACK 2
+
+/* Host description of one grid: the fields of the reference's CaseData that
+ * helm() consumes (classes.py:180-225), network in CSR over the sorted bus
+ * adjacency `branches_buses` (diagonal included). */
+typedef struct helm_grid_host {
+    int32_t n_bus;
+    int32_t slack;              /* bus index of the slack                       */
+    const int32_t *adj_ptr;     /* [n_bus+1]                                    */
+    const int32_t *adj_idx;     /* [nnz] ascending per row                      */
+    const double *ytrans;       /* [nnz] complex: series-admittance Laplacian   */
+    const double *yfull;        /* [nnz] complex: Ytrans + diag(Yshunt) + phase */
+    const double *yshunt;       /* [n_bus] complex                              */
+    const int32_t *phase_ptr;   /* [n_bus+1] phase-shifter corrections per bus  */
+    const int32_t *phase_idx;   /* [nph] neighbour bus                          */
+    const double *phase_val;    /* [nph] complex                                */
+    const double *vsp;          /* [n_bus] specified |V| (generator buses)      */
+    const double *pg;           /* [n_bus] p.u.                                 */
+    const double *pd;           /* [n_bus]                                      */
+    const double *qd;           /* [n_bus]                                      */
+    const double *qgmax;        /* [n_bus]                                      */
+    const double *qgmin;        /* [n_bus]                                      */
+    const uint8_t *bus_type;    /* [n_bus] HELM_BUS_*                           */
+} helm_grid_host;
+
+typedef struct helm_params {
+    double mismatch;            /* helm(mismatch=)                              */
+    int32_t max_coefficients;   /* helm(max_coefficients=)                      */
+    int32_t enforce_q_limits;   /* helm(enforce_Q_limits=)                      */
+    int32_t group;              /* scenarios per lock-step group: 1,2,4,8,16,32; 0 = auto */
+    int32_t use_graph;          /* replay the per-order step as a CUDA graph    */
+    int32_t poll_every;         /* steps between host polls of the done counter; 0 = auto */
+} helm_params;
+
+typedef struct helm_plan_info {
+    int32_t n_bus;
+    int32_t nnz_adj;
+    int32_t n_l_blocks;         /* strictly-lower 2x2 blocks of L               */
+    int32_t n_u_blocks;         /* strictly-upper 2x2 blocks of U               */
+    int32_t n_slots;            /* n_l + n_u + n_bus                            */
+    int32_t n_l_levels;
+    int32_t n_u_levels;
+    int32_t n_factor_updates;   /* 2x2 block updates per numeric factorization  */
+    int32_t n_pv;               /* generator (PV) buses in the base case        */
+    int32_t reserved;
+} helm_plan_info;
+
+typedef struct helm_plan helm_plan;
+
+/* per-solve timing/launch statistics (filled by helm_solve_batch_*) */
+typedef struct helm_stats {
+    int64_t steps;              /* per-order steps executed                     */
+    int64_t kernel_launches;    /* kernels launched (graph nodes count)         */
+    int64_t graph_launches;
+    double ms_total;            /* device time of the whole solve (CUDA events) */
+    double ms_kernel[8];        /* per-kernel accumulated ms when profile=1: assemble, factor, solve, rhs_conv, advance, qlimit, pass_end, init */
+} helm_stats;
+
+const char *helm_last_error(void);
+
+/* Host symbolic analysis: minimum-degree ordering of the bus graph, symbolic
+ * 2x2-block LU fill on the all-PQ superset pattern, level sets, factorization
+ * schedule; uploads the shared index/grid arrays to the current CUDA device. */
+int helm_plan_create(const helm_grid_host *grid, helm_plan **out);
+void helm_plan_destroy(helm_plan *plan);
+int helm_plan_get_info(const helm_plan *plan, helm_plan_info *info);
+/* elimination order: perm[new index] = original bus index; buffer of n_bus */
+int helm_plan_get_perm(const helm_plan *plan, int32_t *perm_out);
+
+/* bytes of device workspace needed for n_scen scenarios */
+size_t helm_workspace_bytes(const helm_plan *plan, int32_t n_scen, const helm_params *params);
+
+/* Solve n_scen load-scaling scenarios of the plan's grid.  Scenario b is
+ * helm(case, scale=scale[b], ...) (classes.py:215-219: Pd, Qd, Pg *= scale).
+ * Device-pointer variant: every pointer is device memory of the current
+ * device; work is enqueued on `stream` (a cudaStream_t) and the call returns
+ * after the last poll, with results complete on the stream.
+ *   d_scale    [n_scen] double
+ *   d_vout     [n_scen * n_bus] complex, scenario-major, original bus order
+ *   d_status   [n_scen] int32 HELM_ST_*
+ *   d_ncoef    [n_scen * HELM_MAX_PASSES] int32: coefficients per pass (run.list_coef), 0-padded
+ *   d_nswitch  [n_scen] int32: PV->PQ switches
+ */
+int helm_solve_batch_device(helm_plan *plan, int32_t n_scen, const double *d_scale,
+                            const helm_params *params, void *d_workspace, size_t workspace_bytes,
+                            double *d_vout, int32_t *d_status, int32_t *d_ncoef,
+                            int32_t *d_nswitch, void *stream, helm_stats *stats);
+
+/* Host-buffer variant (the drop-in call): copies scale in, results out; owns
+ * and caches its device workspace inside the plan. */
+int helm_solve_batch_host(helm_plan *plan, int32_t n_scen, const double *h_scale,
+                          const helm_params *params, double *h_vout, int32_t *h_status,
+                          int32_t *h_ncoef, int32_t *h_nswitch, helm_stats *stats);
+
+/* Debug/testing hooks: run one kernel stage in isolation on device buffers.
+ * Used by the parity tests to compare individual stages with the oracle. */
+int helm_debug_factor_solve(helm_plan *plan, int32_t n_scen, int32_t group,
+                            const uint8_t *h_bus_type /* [n_scen*n_bus] original order */,
+                            const double *h_rhs /* [n_scen*2*n_bus] original order */,
+                            double *h_x /* [n_scen*2*n_bus] */);
+
+/* Host-only view of the symbolic analysis (no CUDA): ordering, fill, level
+ * sets and schedules as int32 arrays, by name (see csrc/symbolic.h). */
+typedef struct helm_symbolic helm_symbolic;
+int helm_symbolic_create(int32_t n_bus, const int32_t *adj_ptr, const int32_t *adj_idx,
+                         helm_symbolic **out);
+void helm_symbolic_destroy(helm_symbolic *sym);
+int helm_symbolic_array(const helm_symbolic *sym, const char *name, const int32_t **data,
+                        int32_t *len);
+
+/* measured fp64 FMA throughput microbenchmark (TFLOP/s) and copy bandwidth (GB/s) */
+int helm_measure_peaks(double *dfma_tflops, double *copy_gbs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HELM_B200_H */

@@ -1,0 +1,147 @@
+"""GPU parity tests: the CUDA path (through the C ABI / helm_batch / helm) against
+the oracle, the committed reference runs and the reference's golden files.
+Tolerance: 1e-8 p.u. in |V| and 1e-8 rad in angle (BASELINE.json north star)."""
+import numpy as np
+import pytest
+
+from common import CASES, TOL_ANG, TOL_MAG, golden_results, load_case, polar_err, ref_outputs
+from oracle import helm_oracle as ho
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def hb():
+    import helmpy_b200
+    from helmpy_b200.core import _lib
+    _lib.load()
+    return helmpy_b200
+
+
+@pytest.mark.parametrize('name', ['case118', 'case2869pegase'])
+@pytest.mark.parametrize('group', [1, 8])
+def test_factor_solve_stage_matches_superlu(hb, name, group):
+    """K_asm + K2f + K2 in isolation vs SuperLU on the oracle's matrix."""
+    from scipy.sparse.linalg import splu
+    from helmpy_b200.core.helm import get_plan
+    case = load_case(name)
+    plan = get_plan(case)
+    g = ho.Grid(case)
+    rng = np.random.default_rng(1)
+    B = 11
+    bts = np.tile(g.btype0.astype(np.uint8), (B, 1))
+    pv = np.nonzero(g.btype0 == 1)[0]
+    for b in range(1, B):            # random PV->PQ switching states
+        sw = rng.choice(pv, size=rng.integers(0, max(1, len(pv) // 4)), replace=False)
+        bts[b, sw] = 0
+    rhs = rng.standard_normal((B, 2 * case.N))
+    x = plan.debug_factor_solve(bts, rhs, group=group)
+    for b in range(B):
+        A = ho.build_matrix(g, bts[b].astype(np.int8))
+        xs = splu(A).solve(rhs[b])
+        assert np.max(np.abs(x[b] - xs)) <= 1e-10 * np.max(np.abs(xs))
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_helm_matches_reference_golden_xlsx(hb, name, capsys):
+    """The reference's own end-to-end test (test/test_helmpy.py:73-92)."""
+    case = load_case(name)
+    V = hb.helm(case, mismatch=1e-8, max_coefficients=40)
+    out = capsys.readouterr().out
+    g = golden_results(name)
+    assert V is not None and V.dtype == np.complex128 and V.shape == (case.N,)
+    assert 'Convergence has been reached.' in out
+    assert np.max(np.abs(np.abs(V) - g['classic_mag'])) <= TOL_MAG
+    assert np.max(np.abs(np.angle(V) - np.deg2rad(g['classic_ang_deg']))) <= TOL_ANG
+    assert V[case.slack].imag == 0.0
+
+
+@pytest.mark.parametrize('name', CASES)
+@pytest.mark.parametrize('group', [1, 4, 8])
+def test_batch_matches_reference_runs(hb, name, group):
+    """Committed outputs of the unmodified reference at several load scales:
+    same convergence status, pass structure, switch count, voltages."""
+    case = load_case(name)
+    runs, _ = ref_outputs(name)
+    scales = [r['scale'] for r in runs]
+    res = hb.helm_batch(case, scales, mismatch=1e-8, max_coefficients=40, group=group)
+    for b, r in enumerate(runs):
+        assert bool(res.converged[b]) == r['converged'], (name, r['scale'])
+        if r['converged']:
+            assert res.list_coef(b) == r['list_coef'], (name, r['scale'])
+            assert res.nswitch[b] == len(r['switched'])
+            dmag, dang = polar_err(res.V[b], r['V'])
+            assert dmag <= TOL_MAG and dang <= TOL_ANG, (name, r['scale'], dmag, dang)
+        else:
+            assert res.status[b] == 3
+
+
+@pytest.mark.parametrize('name,nscen', [('case118', 64), ('case1354pegase', 12)])
+def test_batch_matches_oracle_random_scales(hb, name, nscen):
+    case = load_case(name)
+    rng = np.random.default_rng(0)
+    scales = rng.uniform(0.8, 1.05, nscen)
+    res = hb.helm_batch(case, scales, mismatch=1e-8, max_coefficients=40)
+    for b, s in enumerate(scales):
+        Vo, info = ho.helm_oracle(case, mismatch=1e-8, scale=s, max_coefficients=40)
+        assert bool(res.converged[b]) == (Vo is not None)
+        if Vo is not None:
+            assert res.list_coef(b) == info['list_coef']
+            dmag, dang = polar_err(res.V[b], Vo)
+            assert dmag <= TOL_MAG and dang <= TOL_ANG
+
+
+def test_no_q_limits_and_loose_mismatch(hb):
+    case = load_case('case118')
+    for kw in (dict(enforce_Q_limits=False, mismatch=1e-8), dict(mismatch=1e-4)):
+        res = hb.helm_batch(case, [1.0], max_coefficients=40, **kw)
+        Vo, info = ho.helm_oracle(case, scale=1, max_coefficients=40, **kw)
+        assert res.list_coef(0) == info['list_coef']
+        dmag, dang = polar_err(res.V[0], Vo)
+        assert dmag <= TOL_MAG and dang <= TOL_ANG
+
+
+def test_divergence_returns_none(hb, capsys):
+    case = load_case('case2869pegase')
+    V = hb.helm(case, mismatch=1e-8, scale=1.2, max_coefficients=40)
+    assert V is None
+    assert 'Maximum number of coefficients' in capsys.readouterr().out
+    assert case.scale == 1
+
+
+def test_argument_validation(hb, capsys):
+    case = load_case('case9')
+    assert hb.helm(case, mismatch=1) is None               # int mismatch: helm.py:861
+    assert 'Erroneous argument type.' in capsys.readouterr().out
+    assert hb.helm(case, max_coefficients=4) is None
+    assert hb.helm(case, pv_bus_model=3) is None
+
+
+def test_graph_and_eager_agree(hb):
+    case = load_case('case118')
+    scales = np.linspace(0.8, 1.2, 16)
+    a = hb.helm_batch(case, scales, mismatch=1e-8, max_coefficients=40, use_graph=True)
+    b = hb.helm_batch(case, scales, mismatch=1e-8, max_coefficients=40, use_graph=False)
+    assert np.array_equal(a.V, b.V) and np.array_equal(a.ncoef, b.ncoef)
+
+
+def test_full_size_properties(hb):
+    """BASELINE-size batch: properties that need no oracle — every scenario that
+    converges satisfies the power-flow equations at its own tolerance class, the
+    slack voltage is exact, PV magnitudes equal their set-points unless switched."""
+    case = load_case('case2869pegase')
+    rng = np.random.default_rng(0)
+    scales = rng.uniform(0.8, 1.05, 256)
+    res = hb.helm_batch(case, scales, mismatch=1e-8, max_coefficients=40)
+    assert res.converged.all()
+    V = res.V
+    assert np.allclose(V[:, case.slack], case.V[case.slack], atol=0, rtol=0)
+    # complex power mismatch at PQ buses of the base case
+    rows = np.repeat(np.arange(case.N), np.diff(case.adj_ptr))
+    pq = np.array([t == 'PQ' for t in case.Buses_type])
+    for b in range(0, 256, 37):
+        I = np.zeros(case.N, dtype=complex)
+        np.add.at(I, rows, case.Y_val * V[b, case.adj_idx])
+        S = V[b] * np.conj(I)
+        Ssp = -(case.Pd + 1j * case.Qd) * scales[b]
+        assert np.max(np.abs(S[pq] - Ssp[pq])) < 1e-6

@@ -1,0 +1,122 @@
+"""CPU: host logic — loader, xlsx round trip, symbolic analysis, C-ABI surface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import blocklu_emul as be
+from common import CASES, load_case, load_tables
+from helmpy_b200.core import _lib, xlsx
+from helmpy_b200.core.classes import create_case_data_object_from_xlsx
+from oracle import helm_oracle as ho
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    header = open(os.path.join(REPO, 'include', 'helm_b200.h')).read()
+    declared = set(re.findall(r'\b(helm_[a-z_]+)\s*\(', header))
+    assert declared == set(_lib.EXPORTED_SYMBOLS)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+
+
+def test_xlsx_round_trip(tmp_path):
+    b, br, g = load_tables('case118')
+    p = str(tmp_path / 'case118.xlsx')
+    xlsx.write_numeric_xlsx(p, [('Sheet1', np.zeros((0, 0))), ('Buses', b), ('Branches', br), ('Generators', g)])
+    assert xlsx.sheet_names(p) == ['Sheet1', 'Buses', 'Branches', 'Generators']
+    case = create_case_data_object_from_xlsx(p)
+    ref = load_case('case118')
+    assert case.name == 'case118' and case.N == 118
+    assert np.array_equal(case.Ytrans_val, ref.Ytrans_val)
+    assert np.array_equal(case.Y_val, ref.Y_val)
+    assert case.branches_buses == ref.branches_buses
+    assert create_case_data_object_from_xlsx(p, case_name=3) is None   # classes.py:118-120
+
+
+def test_case_scale_semantics():
+    case = load_case('case9')
+    pd0 = case.Pd.copy()
+    case.set_scale(1.1)
+    assert np.allclose(case.Pd, pd0 * 1.1) and case.scale == 1.1
+    case.reset_scale()
+    assert np.allclose(case.Pd, pd0) and case.scale == 1
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize('name', ['case9', 'case118', 'case1354pegase'])
+def test_loader_bit_identical_to_reference(name):
+    from oracle import ref_shim
+    path = '/root/reference/data/cases/%s.xlsx' % name
+    rc = ref_shim.ref_case(path)
+    c = create_case_data_object_from_xlsx(path)
+    assert np.array_equal(rc.Ytrans, c.Ytrans) and np.array_equal(rc.Y, c.Y)
+    assert np.array_equal(rc.Yshunt, c.Yshunt)
+    assert rc.branches_buses == c.branches_buses
+    assert np.array_equal(rc.list_gen, c.list_gen) and rc.Buses_type == c.Buses_type
+    for a in ('Pd', 'Qd', 'Pg'):
+        assert np.array_equal(getattr(rc, a), getattr(c, a))
+    assert set(rc.phase_dict) == set(c.phase_dict)
+    for k in rc.phase_dict:
+        assert rc.phase_dict[k][0] == c.phase_dict[k][0] and rc.phase_dict[k][1] == c.phase_dict[k][1]
+
+
+@pytest.mark.parametrize('name', ['case9', 'case118', 'case1354pegase'])
+def test_symbolic_structure(name):
+    case = load_case(name)
+    S = _lib.symbolic_arrays(case.adj_ptr, case.adj_idx)
+    N = case.N
+    assert sorted(S['perm']) == list(range(N))
+    assert np.array_equal(S['iperm'][S['perm']], np.arange(N))
+    # L rows strictly lower, ascending; rows of a level only depend on earlier levels
+    lev = np.zeros(N, dtype=int)
+    for l in range(len(S['llev_ptr']) - 1):
+        lev[S['llev_ptr'][l]:S['llev_ptr'][l + 1]] = l
+    for r in range(N):
+        cols = S['lcol'][S['lptr'][r]:S['lptr'][r + 1]]
+        assert np.all(np.diff(cols) > 0) and (len(cols) == 0 or cols[-1] < r)
+        assert np.all(lev[cols] < lev[r])
+    ulev = np.zeros(N, dtype=int)
+    for l in range(len(S['ulev_ptr']) - 1):
+        ulev[S['urow'][S['ulev_ptr'][l]:S['ulev_ptr'][l + 1]]] = l
+    for q in range(N):
+        r = S['urow'][q]
+        cols = S['ucol'][S['uptr'][q]:S['uptr'][q + 1]]
+        assert np.all(cols > r) and np.all(ulev[cols] < ulev[r])
+    # structural symmetry of the fill: nL == nU
+    assert len(S['lcol']) == len(S['ucol'])
+    # every adjacency entry has its own slot
+    assert len(set(S['adj_slot'])) == len(S['adj_slot'])
+
+
+@pytest.mark.parametrize('name', ['case118', 'case1354pegase'])
+def test_block_lu_static_pivoting_matches_superlu(name):
+    """The fixed-pattern 2x2-block LU (no value pivoting) reproduces SuperLU's
+    partial-pivoting solution on every Q-limit pass matrix of the case."""
+    from scipy.sparse.linalg import splu
+    case = load_case(name)
+    S = _lib.symbolic_arrays(case.adj_ptr, case.adj_idx)
+    g = ho.Grid(case)
+    V, info = ho.helm_oracle(case, mismatch=1e-8, max_coefficients=40, record=True)
+    bt = g.btype0.copy()
+    done = 0
+    for ps in info['passes']:
+        A = ps['A']
+        rhs = ps['rhs'][:, 3]
+        xs = splu(A).solve(rhs)
+        lu = be.factor(S, be.assemble(S, case.Ytrans_val, bt))
+        x = be.solve(S, lu, rhs)
+        assert np.max(np.abs(x - xs)) <= 1e-11 * np.max(np.abs(xs))
+        # next pass: the buses switched so far become PQ
+        nsw = len(info['switched'])
+        done += 1
+        # switched buses are recorded cumulatively; recover this pass's set from A of the next pass
+        if done < len(info['passes']):
+            An = info['passes'][done]['A'].tocsr()
+            for i in range(case.N):
+                if bt[i] == 1 and An.getrow(2 * i + 1).nnz > 1:
+                    bt[i] = 0
