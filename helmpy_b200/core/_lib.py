@@ -97,7 +97,8 @@ def load():
     lib.helm_debug_factor_solve.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                             C.c_void_p, C.c_void_p]
     lib.helm_measure_peaks.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
-    lib.helm_symbolic_create.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.helm_symbolic_create.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.POINTER(C.c_void_p)]
     lib.helm_symbolic_destroy.argtypes = [C.c_void_p]
     lib.helm_symbolic_destroy.restype = None
     lib.helm_symbolic_array.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p),
@@ -116,13 +117,15 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def symbolic_arrays(adj_ptr, adj_idx):
+def symbolic_arrays(adj_ptr, adj_idx, bus_type=None):
     """Host-only symbolic analysis -> dict of int32 numpy arrays (no CUDA)."""
     lib = load()
     adj_ptr = np.ascontiguousarray(adj_ptr, dtype=np.int32)
     adj_idx = np.ascontiguousarray(adj_idx, dtype=np.int32)
+    bt = None if bus_type is None else np.ascontiguousarray(bus_type, dtype=np.uint8)
     h = C.c_void_p()
-    rc = lib.helm_symbolic_create(len(adj_ptr) - 1, _ptr(adj_ptr), _ptr(adj_idx), C.byref(h))
+    rc = lib.helm_symbolic_create(len(adj_ptr) - 1, _ptr(adj_ptr), _ptr(adj_idx),
+                                  None if bt is None else _ptr(bt), C.byref(h))
     if rc != 0:
         raise HelmB200Error("helm_symbolic_create failed (code %d)" % rc)
     out = {}

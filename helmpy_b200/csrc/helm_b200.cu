@@ -146,14 +146,19 @@ __device__ __forceinline__ Blk bmul(Blk x, Blk y) {
 }
 
 // ---- K2f: numeric 2x2-block LU on the fixed pattern (replaces SuperLU gstrf, helm.py:106)
-// One CTA per group; rows of one L-level are independent; thread (slot, s)
-// eliminates whole rows (up-looking).  L_rk = A_rk * inv(D_k); D_r stored inverted.
-template <int G, int T>
-__global__ void __launch_bounds__(T) k_factor(PlanDev p, WorkDev w) {
-    int grp = blockIdx.x;
+// One WARP per group (no block barriers): lane = (row slot, scenario); rows of one
+// L-level are independent, levels are separated by __syncwarp().  Each lane
+// eliminates whole rows up-looking: L_rk = A_rk * inv(D_k), row_r -= L_rk * U_k.
+// D_r is stored inverted.  Many groups are resident per SM, which is what hides
+// the dependency latency of the thin levels near the root of the elimination tree.
+template <int G, int WPB>
+__global__ void __launch_bounds__(WPB * 32) k_factor(PlanDev p, WorkDev w) {
+    int grp = blockIdx.x * WPB + (threadIdx.x >> 5);
+    if (grp >= w.ngroups) return;
     if (!(w.g_flags[grp] & GF_NEEDFACTOR)) return;
-    const int R = T / G;
-    int s = threadIdx.x % G, slot = threadIdx.x / G;
+    const int R = 32 / G;
+    int lane = threadIdx.x & 31;
+    int s = lane % G, slot = lane / G;
     int sg = grp * G + s;
     bool active = w.s_status[sg] == ST_ACTIVE;
     double2 *lu = w.lu + (size_t)grp * p.nslots * G * 2;
@@ -162,13 +167,27 @@ __global__ void __launch_bounds__(T) k_factor(PlanDev p, WorkDev w) {
         int r1 = p.llev_ptr[l + 1];
         if (active) {
             for (int r = p.llev_ptr[l] + slot; r < r1; r += R) {
-                for (int e = p.lptr[r]; e < p.lptr[r + 1]; ++e) {
+                int e0 = p.lptr[r], e1 = p.lptr[r + 1];
+                for (int e = e0; e < e1; ++e) {
                     int k = p.lcol[e];
+                    int u0 = p.fptr[e], u1 = p.fptr[e + 1];
                     Blk a = ldblk(lu, (size_t)e * G + s);
                     Blk dk = ldblk(lu, (size_t)p.dslot[k] * G + s);
                     Blk m = bmul(a, dk);
                     stblk(lu, (size_t)e * G + s, m);
-                    for (int u = p.fptr[e]; u < p.fptr[e + 1]; ++u) {
+                    int u = u0;
+                    for (; u + 2 <= u1; u += 2) {      // two independent updates in flight
+                        int s0 = p.fsrc[u], s1 = p.fsrc[u + 1];
+                        size_t d0 = (size_t)p.fdst[u] * G + s, d1 = (size_t)p.fdst[u + 1] * G + s;
+                        Blk a0 = ldblk(lu, (size_t)s0 * G + s), a1 = ldblk(lu, (size_t)s1 * G + s);
+                        Blk b0 = ldblk(lu, d0), b1 = ldblk(lu, d1);
+                        Blk p0 = bmul(m, a0), p1 = bmul(m, a1);
+                        b0.a -= p0.a; b0.b -= p0.b; b0.c -= p0.c; b0.d -= p0.d;
+                        b1.a -= p1.a; b1.b -= p1.b; b1.c -= p1.c; b1.d -= p1.d;
+                        stblk(lu, d0, b0);
+                        stblk(lu, d1, b1);
+                    }
+                    if (u < u1) {
                         Blk src = ldblk(lu, (size_t)p.fsrc[u] * G + s);
                         size_t di = (size_t)p.fdst[u] * G + s;
                         Blk dst = ldblk(lu, di);
@@ -185,20 +204,48 @@ __global__ void __launch_bounds__(T) k_factor(PlanDev p, WorkDev w) {
                 stblk(lu, dd, Blk{d.d * inv, -d.b * inv, -d.c * inv, d.a * inv});
             }
         }
-        __syncthreads();
+        __syncwarp();
     }
     if (singular) w.s_status[sg] = ST_SINGULAR;
 }
 
 // ---- K2: level-scheduled block SpTRSV (replaces SuperLU gstrs, helm.py:602) -----------
-// One CTA per group.  x = U^-1 L^-1 rhs; forward phase writes y into xb, backward
-// phase works in place.  Rows of one level are independent: thread (slot, s).
-template <int G, int T>
-__global__ void __launch_bounds__(T) k_solve(PlanDev p, WorkDev w) {
-    int grp = blockIdx.x;
+// One WARP per group.  x = U^-1 L^-1 rhs; the forward phase writes y into xb, the
+// backward phase works in place.  Rows of one level are independent: lane =
+// (row slot, scenario); levels are separated by __syncwarp().  The factors are
+// consumed in storage order (slots are numbered in consumption order).
+template <int G>
+__device__ __forceinline__ void row_accumulate(const double2 *lu, const double2 *xb, const int *cols,
+                                               size_t slot0, int n, int s, double2 &acc) {
+    int t = 0;
+    for (; t + 4 <= n; t += 4) {                       // 4 entries in flight
+        int c0 = cols[t], c1 = cols[t + 1], c2 = cols[t + 2], c3 = cols[t + 3];
+        Blk m0 = ldblk(lu, (slot0 + t) * G + s), m1 = ldblk(lu, (slot0 + t + 1) * G + s);
+        Blk m2 = ldblk(lu, (slot0 + t + 2) * G + s), m3 = ldblk(lu, (slot0 + t + 3) * G + s);
+        double2 x0 = xb[(size_t)c0 * G + s], x1 = xb[(size_t)c1 * G + s];
+        double2 x2 = xb[(size_t)c2 * G + s], x3 = xb[(size_t)c3 * G + s];
+        acc.x -= m0.a * x0.x + m0.b * x0.y; acc.y -= m0.c * x0.x + m0.d * x0.y;
+        acc.x -= m1.a * x1.x + m1.b * x1.y; acc.y -= m1.c * x1.x + m1.d * x1.y;
+        acc.x -= m2.a * x2.x + m2.b * x2.y; acc.y -= m2.c * x2.x + m2.d * x2.y;
+        acc.x -= m3.a * x3.x + m3.b * x3.y; acc.y -= m3.c * x3.x + m3.d * x3.y;
+    }
+    for (; t < n; ++t) {
+        int c = cols[t];
+        Blk m = ldblk(lu, (slot0 + t) * G + s);
+        double2 xc = xb[(size_t)c * G + s];
+        acc.x -= m.a * xc.x + m.b * xc.y;
+        acc.y -= m.c * xc.x + m.d * xc.y;
+    }
+}
+
+template <int G, int WPB>
+__global__ void __launch_bounds__(WPB * 32) k_solve(PlanDev p, WorkDev w) {
+    int grp = blockIdx.x * WPB + (threadIdx.x >> 5);
+    if (grp >= w.ngroups) return;
     if (w.g_flags[grp] & GF_DONE) return;
-    const int R = T / G;
-    int s = threadIdx.x % G, slot = threadIdx.x / G;
+    const int R = 32 / G;
+    int lane = threadIdx.x & 31;
+    int s = lane % G, slot = lane / G;
     bool active = w.s_status[grp * G + s] == ST_ACTIVE;
     const double2 *lu = w.lu + (size_t)grp * p.nslots * G * 2;
     const double2 *rhs = w.rhs + (size_t)grp * p.N * G;
@@ -207,108 +254,29 @@ __global__ void __launch_bounds__(T) k_solve(PlanDev p, WorkDev w) {
         int r1 = p.llev_ptr[l + 1];
         if (active) {
             for (int r = p.llev_ptr[l] + slot; r < r1; r += R) {
+                int e0 = p.lptr[r], e1 = p.lptr[r + 1];
                 double2 acc = rhs[(size_t)r * G + s];
-                int e1 = p.lptr[r + 1];
-                for (int e = p.lptr[r]; e < e1; ++e) {
-                    int c = p.lcol[e];
-                    Blk m = ldblk(lu, (size_t)e * G + s);
-                    double2 xc = xb[(size_t)c * G + s];
-                    acc.x -= m.a * xc.x + m.b * xc.y;
-                    acc.y -= m.c * xc.x + m.d * xc.y;
-                }
+                row_accumulate<G>(lu, xb, p.lcol + e0, (size_t)e0, e1 - e0, s, acc);
                 xb[(size_t)r * G + s] = acc;
             }
         }
-        __syncthreads();
+        __syncwarp();
     }
     for (int l = 0; l < p.nUlev; ++l) {
         int q1 = p.ulev_ptr[l + 1];
         if (active) {
             for (int q = p.ulev_ptr[l] + slot; q < q1; q += R) {
                 int r = p.urow[q];
-                double2 acc = xb[(size_t)r * G + s];
                 int u0 = p.uptr[q], nu = p.uptr[q + 1] - u0;
                 size_t base = (size_t)(p.nL + u0 + q);
-                for (int t = 0; t < nu; ++t) {
-                    int c = p.ucol[u0 + t];
-                    Blk m = ldblk(lu, (base + 1 + t) * G + s);
-                    double2 xc = xb[(size_t)c * G + s];
-                    acc.x -= m.a * xc.x + m.b * xc.y;
-                    acc.y -= m.c * xc.x + m.d * xc.y;
-                }
                 Blk d = ldblk(lu, base * G + s);
+                double2 acc = xb[(size_t)r * G + s];
+                row_accumulate<G>(lu, xb, p.ucol + u0, base + 1, nu, s, acc);
                 xb[(size_t)r * G + s] = make_double2(d.a * acc.x + d.b * acc.y, d.c * acc.x + d.d * acc.y);
             }
         }
-        __syncthreads();
+        __syncwarp();
     }
-}
-
-// ---- RHS of order jn >= 2 for bus i (reference helm.py:293-398) -----------------------
-// v = V_i[jn-1] (just solved), neighbours' V_k[jn-1] are read from the solution
-// buffer xb; older orders from the history Vh.  Hh holds W (PQ) or barras_CC (PV).
-template <int G>
-__device__ __forceinline__ double2 rhs_next(const PlanDev &p, const WorkDev &w, int grp, int i, int s,
-                                            int j /* = jn-1 */, unsigned char bt, double2 v,
-                                            double2 wj /* W_i[j], PQ only */, double sc) {
-    const int N = p.N;
-    const double2 *xb = w.xb + (size_t)grp * N * G;
-    if (bt == HELM_BUS_SLACK) return make_double2(0.0, 0.0);                     // helm.py:395-397
-    if (bt == HELM_BUS_PQ) {                                                     // helm.py:367-385
-        double Pi = p.pg[i] * sc - p.pd[i] * sc;
-        double Qi = w.Qg[ix<G>(grp, N, i, s)] - p.qd[i] * sc;
-        double2 pp = make_double2(0.0, 0.0);
-        for (int a = p.ph_ptr[i]; a < p.ph_ptr[i + 1]; ++a)
-            pp = cadd(pp, cmul(p.ph_val[a], xb[(size_t)p.ph_idx[a] * G + s]));
-        double2 sconj = make_double2(Pi, -Qi);
-        double2 t = cmul(sconj, make_double2(wj.x, -wj.y));
-        double2 ysv = cmul(p.yshunt[i], v);
-        return make_double2(t.x - ysv.x - pp.x, t.y - ysv.y - pp.y);
-    }
-    // PV bus, model 2 (helm.py:293-364); n = j+1 >= 2
-    double2 PP = make_double2(0.0, 0.0);
-    for (int a = p.adj_ptr[i]; a < p.adj_ptr[i + 1]; ++a)
-        PP = cadd(PP, cmul(p.ytr[a], xb[(size_t)p.adj_idx[a] * G + s]));         // helm.py:310-312
-    w.Hh[hx<G>(w, N, grp, j, i, s)] = PP;                                        // barras_CC[i][n-1]
-    double2 ppp = make_double2(0.0, 0.0);
-    // x = 1 .. n-2 : conj(V[n-x]) * CC[x];  V[n-1] = v is the x=1 term
-    for (int x = 1; x <= j - 1; ++x) {
-        double2 vv = (x == 1) ? v : w.Vh[hx<G>(w, N, grp, j + 1 - x, i, s)];
-        double2 cc = w.Hh[hx<G>(w, N, grp, x, i, s)];
-        ppp = cadd(ppp, cmulc(cc, vv));
-    }
-    double2 v1 = (j == 1) ? v : w.Vh[hx<G>(w, N, grp, 1, i, s)];
-    ppp = cadd(ppp, cmulc(PP, v1));                                              // helm.py:314
-    double cc_ = 0.0 - ppp.x;
-    double2 ysh = p.yshunt[i];
-    size_t vvi = ix<G>(grp, N, i, s);
-    if (ysh.x != 0.0) {                                                          // conduc_buses
-        if (j >= 2) cc_ -= ysh.x * (w.VVant[vvi] + 2.0 * v.x);                   // helm.py:317-318
-        else cc_ -= ysh.x * 2.0 * v.x;                                           // helm.py:336-337
-    }
-    if (p.ph_ptr[i + 1] > p.ph_ptr[i]) {                                         // helm.py:320-327
-        double2 acc = make_double2(0.0, 0.0);
-        for (int x = 0; x <= j; ++x) {
-            double2 pp = make_double2(0.0, 0.0);
-            for (int a = p.ph_ptr[i]; a < p.ph_ptr[i + 1]; ++a) {
-                int k = p.ph_idx[a];
-                double2 vk = (x == 0) ? xb[(size_t)k * G + s] : w.Vh[hx<G>(w, N, grp, j - x, k, s)];
-                pp = cadd(pp, cmul(p.ph_val[a], vk));
-            }
-            double2 vx = (x == j) ? v : w.Vh[hx<G>(w, N, grp, x, i, s)];
-            acc = cadd(acc, cmulc(pp, vx));
-        }
-        cc_ -= acc.x;
-    }
-    // VV = sum_{k=1}^{n-1} V[k] conj(V[n-k])  (helm.py:356-361)
-    double vvre = 0.0;
-    for (int k = 1; k <= j; ++k) {
-        double2 a = (k == j) ? v : w.Vh[hx<G>(w, N, grp, k, i, s)];
-        double2 b = (j + 1 - k == j) ? v : w.Vh[hx<G>(w, N, grp, j + 1 - k, i, s)];
-        vvre += a.x * b.x + a.y * b.y;
-    }
-    w.VVant[vvi] = vvre;
-    return make_double2(cc_, -vvre * 0.5);
 }
 
 // ---- K_init: order-0 germ and RHS of order 1 (helm.py:110-139, 551-556, n == 1 branches) ---
@@ -354,9 +322,33 @@ __global__ void k_init(PlanDev p, WorkDev w) {
 // One thread per (bus, scenario).  Replaces compute_complex_voltages (helm.py:402-420),
 // calculate_inverse_voltages_w_array (423-433), the per-bus evaluators (293-398) and the
 // Pade/convergence test (608-641, analytic_continuation.py).  The Pade value is obtained
-// with Wynn's epsilon algorithm kept incrementally: each order appends one anti-diagonal.
+// with Wynn's epsilon algorithm kept incrementally: each order appends one anti-diagonal
+// (the reference states the algorithm itself in analytic_continuation.py:9-26).
+//
+// All O(j) work of one order is a single fused loop over the history index t = 1..j:
+//   PQ:  W_i[j]  = -sum_t W_i[t-1] V_i[j+1-t]
+//   PV:  PPP     =  sum_t conj(V_i[j+1-t]) CC_i[t]          (CC_i[j] = sum_k Ytrans_ik V_k[j])
+//        VV      =  sum_t V_i[t] conj(V_i[j+1-t])
+//   all: eps_t^(j-t) = eps_{t-2}^(j-t+1) + 1 / (eps_{t-1}^(j-t+1) - eps_{t-1}^(j-t))
+// The loop is blocked by KU: the loads of a block (histories are [order][bus][G], so
+// each one is a coalesced 16 B per lane) are issued together before the dependent
+// arithmetic, which is what gives the kernel its memory-level parallelism.
+constexpr int KU = 4;
+
+struct EpsState { double2 prev1, prev2, cur; };
+
+__device__ __forceinline__ void eps_step(EpsState &st, int t, int j, double2 v, double2 eold_t, double2 *Eb,
+                                         size_t plane) {
+    double2 d = (t == 1) ? v : csub(st.cur, st.prev1);
+    double2 e = cadd(st.prev2, crecip_guard(d));
+    st.prev2 = st.prev1;
+    if (t < j) st.prev1 = eold_t;
+    Eb[(size_t)t * plane] = e;
+    st.cur = e;
+}
+
 template <int G>
-__global__ void k_rhs_conv(PlanDev p, WorkDev w) {
+__global__ void __launch_bounds__(256) k_rhs_conv(PlanDev p, WorkDev w) {
     int grp = blockIdx.y;
     int gf = w.g_flags[grp];
     if (gf & (GF_DONE | GF_PASSEND)) return;
@@ -367,52 +359,125 @@ __global__ void k_rhs_conv(PlanDev p, WorkDev w) {
     if (w.s_status[sg] != ST_ACTIVE) return;
     const int N = p.N;
     const int j = w.g_n[grp] + 1;  // order just solved
-    size_t bi = ix<G>(grp, N, i, s);
-    unsigned char bt = w.btype[bi];
-    double2 v = w.xb[bi];
-    w.Vh[hx<G>(w, N, grp, j, i, s)] = v;                                          // helm.py:412-414
+    const size_t plane = (size_t)N * G;
+    const size_t bi = ix<G>(grp, N, i, s);
+    const size_t h0 = hx<G>(w, N, grp, 0, i, s);
+    double2 *Vb = w.Vh + h0, *Hb = w.Hh + h0, *Eb = w.Eh + h0;
+    const double2 *xb = w.xb + (size_t)grp * N * G;
+    const unsigned char bt = w.btype[bi];
+    const double2 v = xb[(size_t)i * G + s];
+    Vb[(size_t)j * plane] = v;                                                    // helm.py:412-414
     if (bt == HELM_BUS_SLACK) {
-        w.rhs[bi] = make_double2(0.0, 0.0);
+        w.rhs[bi] = make_double2(0.0, 0.0);                                       // helm.py:395-397
         return;
     }
-    // --- epsilon anti-diagonal of order j (Wynn; analytic_continuation.py:9-26 is the
-    //     reference's own statement of the algorithm)
-    {
-        double2 prev1 = w.Eh[hx<G>(w, N, grp, 0, i, s)];   // eps_0^(j-1) = S_{j-1}
-        double2 prev2 = make_double2(0.0, 0.0);            // eps_{-1} = 0
-        double2 cur = cadd(prev1, v);                      // S_j
-        w.Eh[hx<G>(w, N, grp, 0, i, s)] = cur;
-        for (int k = 1; k <= j; ++k) {
-            double2 d = (k == 1) ? v : csub(cur, prev1);
-            double2 e = cadd(prev2, crecip_guard(d));
-            prev2 = prev1;
-            if (k < j) prev1 = w.Eh[hx<G>(w, N, grp, k, i, s)];
-            w.Eh[hx<G>(w, N, grp, k, i, s)] = e;
-            cur = e;
-        }
-        if ((j & 1) == 0) {                                // m = j+1 odd: cur = [j/2 / j/2] Pade at s = 1
-            if (j >= 4) {                                  // helm.py:611: m > 3
-                double2 old = w.Pcur[bi];
-                double mag1 = hypot(old.x, old.y), rad1 = atan2(old.y, old.x);
-                double mag2 = hypot(cur.x, cur.y), rad2 = atan2(cur.y, cur.x);
-                bool ok = (fabs(mag1 - mag2) <= w.mismatch) && (fabs(rad1 - rad2) <= w.mismatch);  // helm.py:618
-                if (!ok) w.s_fail[sg] = 1;
+    const double2 zero = make_double2(0.0, 0.0);
+    EpsState es;
+    es.prev1 = Eb[0];                                      // eps_0^(j-1) = S_{j-1}
+    es.prev2 = zero;                                       // eps_{-1} = 0
+    es.cur = cadd(es.prev1, v);                            // S_j
+    Eb[0] = es.cur;
+    double2 out;
+    if (bt == HELM_BUS_PQ) {
+        double2 aux = zero;
+        for (int t0 = 1; t0 <= j; t0 += KU) {
+            double2 vr[KU], eo[KU], hh[KU];
+#pragma unroll
+            for (int u = 0; u < KU; ++u) {
+                int t = t0 + u;
+                if (t <= j) {
+                    vr[u] = (t == 1) ? v : Vb[(size_t)(j + 1 - t) * plane];
+                    eo[u] = (t < j) ? Eb[(size_t)t * plane] : zero;
+                    hh[u] = Hb[(size_t)(t - 1) * plane];                          // W[t-1]
+                }
             }
-            w.Pcur[bi] = cur;
+#pragma unroll
+            for (int u = 0; u < KU; ++u) {
+                int t = t0 + u;
+                if (t <= j) {
+                    eps_step(es, t, j, v, eo[u], Eb, plane);
+                    aux = cadd(aux, cmul(hh[u], vr[u]));                          // helm.py:430-432
+                }
+            }
         }
-    }
-    double2 wj = make_double2(0.0, 0.0);
-    if (bt == HELM_BUS_PQ) {                                                      // helm.py:423-433
-        double2 aux = make_double2(0.0, 0.0);
-        for (int k = 0; k < j; ++k) {
-            double2 wk = w.Hh[hx<G>(w, N, grp, k, i, s)];
-            double2 vk = (k == 0) ? v : w.Vh[hx<G>(w, N, grp, j - k, i, s)];
-            aux = cadd(aux, cmul(wk, vk));
+        double2 wj = make_double2(-aux.x, -aux.y);
+        Hb[(size_t)j * plane] = wj;                                               // W[j]
+        // RHS of order j+1 (helm.py:367-385)
+        double sc = w.scale[sg];
+        double Pi = p.pg[i] * sc - p.pd[i] * sc;
+        double Qi = w.Qg[bi] - p.qd[i] * sc;
+        double2 pp = zero;
+        for (int a = p.ph_ptr[i]; a < p.ph_ptr[i + 1]; ++a)
+            pp = cadd(pp, cmul(p.ph_val[a], xb[(size_t)p.ph_idx[a] * G + s]));
+        double2 tt = cmul(make_double2(Pi, -Qi), make_double2(wj.x, -wj.y));
+        double2 ysv = cmul(p.yshunt[i], v);
+        out = make_double2(tt.x - ysv.x - pp.x, tt.y - ysv.y - pp.y);
+    } else {
+        // PV bus, model 2 (helm.py:293-364); n = j+1 >= 2
+        double2 PP = zero;
+        for (int a = p.adj_ptr[i]; a < p.adj_ptr[i + 1]; ++a)
+            PP = cadd(PP, cmul(p.ytr[a], xb[(size_t)p.adj_idx[a] * G + s]));      // helm.py:310-312
+        Hb[(size_t)j * plane] = PP;                                               // barras_CC[i][n-1]
+        double2 ppp = zero;
+        double vvre = 0.0;
+        for (int t0 = 1; t0 <= j; t0 += KU) {
+            double2 vr[KU], eo[KU], hh[KU], vf[KU];
+#pragma unroll
+            for (int u = 0; u < KU; ++u) {
+                int t = t0 + u;
+                if (t <= j) {
+                    vr[u] = (t == 1) ? v : Vb[(size_t)(j + 1 - t) * plane];
+                    eo[u] = (t < j) ? Eb[(size_t)t * plane] : zero;
+                    hh[u] = (t < j) ? Hb[(size_t)t * plane] : PP;                 // CC[t]
+                    vf[u] = (t < j) ? Vb[(size_t)t * plane] : v;                  // V[t]
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < KU; ++u) {
+                int t = t0 + u;
+                if (t <= j) {
+                    eps_step(es, t, j, v, eo[u], Eb, plane);
+                    ppp = cadd(ppp, cmulc(hh[u], vr[u]));                         // helm.py:306-314
+                    vvre += vf[u].x * vr[u].x + vf[u].y * vr[u].y;                // helm.py:356-361
+                }
+            }
         }
-        wj = make_double2(-aux.x, -aux.y);
-        w.Hh[hx<G>(w, N, grp, j, i, s)] = wj;
+        double cc_ = 0.0 - ppp.x;
+        double2 ysh = p.yshunt[i];
+        if (ysh.x != 0.0) {                                                      // conduc_buses
+            if (j >= 2) cc_ -= ysh.x * (w.VVant[bi] + 2.0 * v.x);                // helm.py:317-318
+            else cc_ -= ysh.x * 2.0 * v.x;                                       // helm.py:336-337
+        }
+        if (p.ph_ptr[i + 1] > p.ph_ptr[i]) {                                     // helm.py:320-327
+            double2 acc = zero;
+            for (int x = 0; x <= j; ++x) {
+                double2 pp = zero;
+                for (int a = p.ph_ptr[i]; a < p.ph_ptr[i + 1]; ++a) {
+                    int k = p.ph_idx[a];
+                    double2 vk = (x == 0) ? xb[(size_t)k * G + s] : w.Vh[hx<G>(w, N, grp, j - x, k, s)];
+                    pp = cadd(pp, cmul(p.ph_val[a], vk));
+                }
+                double2 vx = (x == j) ? v : Vb[(size_t)x * plane];
+                acc = cadd(acc, cmulc(pp, vx));
+            }
+            cc_ -= acc.x;
+        }
+        w.VVant[bi] = vvre;
+        out = make_double2(cc_, -vvre * 0.5);
     }
-    w.rhs[bi] = rhs_next<G>(p, w, grp, i, s, j, bt, v, wj, w.scale[sg]);
+    w.rhs[bi] = out;
+    // --- Pade value of m = j+1 terms and the convergence test (helm.py:608-641)
+    if ((j & 1) == 0) {                                    // m odd: es.cur = [j/2 / j/2] Pade at s = 1
+        double2 cur = es.cur;
+        if (j >= 4) {                                      // helm.py:611: m > 3
+            double2 old = w.Pcur[bi];
+            double mag1 = hypot(old.x, old.y), rad1 = atan2(old.y, old.x);
+            double mag2 = hypot(cur.x, cur.y), rad2 = atan2(cur.y, cur.x);
+            bool ok = (fabs(mag1 - mag2) <= w.mismatch) && (fabs(rad1 - rad2) <= w.mismatch);  // helm.py:618
+            if (!ok) w.s_fail[sg] = 1;
+        }
+        w.Pcur[bi] = cur;
+    }
 }
 
 // ---- K_adv: per-group bookkeeping after an order (helm.py:608-657 control flow) ----------
@@ -672,7 +737,7 @@ WorkDev bind(const helm_plan *pl, const WsLayout &L, int B, const helm_params *p
 }
 
 constexpr int T_ELEM = 256;   // threads per CTA of the per-(item, scenario) kernels
-constexpr int T_SOLVE = 256;  // threads per CTA of the factor / solve kernels
+constexpr int WPB_SOLVE = 4;  // warps (= scenario groups) per CTA of the factor / solve kernels
 
 enum { KI_ASM = 0, KI_FACTOR, KI_SOLVE, KI_RHS, KI_ADV, KI_QLIM, KI_PEND, KI_INIT, KI_COUNT };
 
@@ -683,9 +748,9 @@ void launch_kernel(int which, const PlanDev &p, const WorkDev &w, cudaStream_t s
     int gridGrp = (w.ngroups + 127) / 128;
     switch (which) {
         case KI_ASM: k_assemble<G><<<gridSlot, T_ELEM, 0, st>>>(p, w); break;
-        case KI_FACTOR: k_factor<G, T_SOLVE><<<w.ngroups, T_SOLVE, 0, st>>>(p, w); break;
+        case KI_FACTOR: k_factor<G, WPB_SOLVE><<<(w.ngroups + WPB_SOLVE - 1) / WPB_SOLVE, WPB_SOLVE * 32, 0, st>>>(p, w); break;
         case KI_INIT: k_init<G><<<gridBus, T_ELEM, 0, st>>>(p, w); break;
-        case KI_SOLVE: k_solve<G, T_SOLVE><<<w.ngroups, T_SOLVE, 0, st>>>(p, w); break;
+        case KI_SOLVE: k_solve<G, WPB_SOLVE><<<(w.ngroups + WPB_SOLVE - 1) / WPB_SOLVE, WPB_SOLVE * 32, 0, st>>>(p, w); break;
         case KI_RHS: k_rhs_conv<G><<<gridBus, T_ELEM, 0, st>>>(p, w); break;
         case KI_ADV: k_advance<<<gridGrp, 128, 0, st>>>(w); break;
         case KI_QLIM: k_qlimit<G><<<gridBus, T_ELEM, 0, st>>>(p, w); break;
@@ -730,7 +795,7 @@ int helm_plan_create(const helm_grid_host *g, helm_plan **out) {
     if (!g || !out) { g_err = "null argument"; return HELM_E_ARG; }
     helm_plan *pl = new helm_plan();
     std::string err;
-    if (!helm::build_symbolic(g->n_bus, g->adj_ptr, g->adj_idx, pl->S, err)) {
+    if (!helm::build_symbolic(g->n_bus, g->adj_ptr, g->adj_idx, g->bus_type, pl->S, err)) {
         g_err = err;
         delete pl;
         return HELM_E_STRUCT;

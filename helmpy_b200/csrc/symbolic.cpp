@@ -42,8 +42,8 @@ inline void sorted_erase(std::vector<int> &v, int x) {
 
 }  // namespace
 
-bool build_symbolic(int N, const int32_t *adj_ptr, const int32_t *adj_idx, Symbolic &S,
-                    std::string &err) {
+bool build_symbolic(int N, const int32_t *adj_ptr, const int32_t *adj_idx, const uint8_t *bus_type,
+                    Symbolic &S, std::string &err) {
     if (N <= 0) {
         err = "n_bus must be positive";
         return false;
@@ -121,6 +121,7 @@ bool build_symbolic(int N, const int32_t *adj_ptr, const int32_t *adj_idx, Symbo
     for (int i = 0; i < N; ++i) byl[i] = i;
     std::sort(byl.begin(), byl.end(), [&](int a, int b) {
         if (lev[a] != lev[b]) return lev[a] < lev[b];
+        if (bus_type && bus_type[a] != bus_type[b]) return bus_type[a] < bus_type[b];  // homogeneous warps
         if (lcount[a] != lcount[b]) return lcount[a] > lcount[b];  // long rows first: balanced warps
         return pos[a] < pos[b];
     });

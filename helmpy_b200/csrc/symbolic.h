@@ -35,7 +35,9 @@ struct Symbolic {
 
 // adj_ptr/adj_idx: symmetric bus adjacency with the diagonal included.
 // Returns false and sets err on malformed input.
-bool build_symbolic(int N, const int32_t *adj_ptr, const int32_t *adj_idx, Symbolic &S,
-                    std::string &err);
+// bus_type (may be null): HELM_BUS_* of the base case; buses of one forward level are grouped
+// by type so that warps of the per-bus kernels are homogeneous.
+bool build_symbolic(int N, const int32_t *adj_ptr, const int32_t *adj_idx, const uint8_t *bus_type,
+                    Symbolic &S, std::string &err);
 
 }  // namespace helm

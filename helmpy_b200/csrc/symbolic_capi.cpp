@@ -14,10 +14,10 @@ struct helm_symbolic {
 extern "C" {
 
 int helm_symbolic_create(int32_t n_bus, const int32_t *adj_ptr, const int32_t *adj_idx,
-                         helm_symbolic **out) {
+                         const uint8_t *bus_type, helm_symbolic **out) {
     if (!adj_ptr || !adj_idx || !out) return HELM_E_ARG;
     helm_symbolic *h = new helm_symbolic();
-    if (!helm::build_symbolic(n_bus, adj_ptr, adj_idx, h->S, h->err)) {
+    if (!helm::build_symbolic(n_bus, adj_ptr, adj_idx, bus_type, h->S, h->err)) {
         delete h;
         return HELM_E_STRUCT;
     }

@@ -151,7 +151,7 @@ int helm_debug_factor_solve(helm_plan *plan, int32_t n_scen, int32_t group,
  * sets and schedules as int32 arrays, by name (see csrc/symbolic.h). */
 typedef struct helm_symbolic helm_symbolic;
 int helm_symbolic_create(int32_t n_bus, const int32_t *adj_ptr, const int32_t *adj_idx,
-                         helm_symbolic **out);
+                         const uint8_t *bus_type /* may be NULL */, helm_symbolic **out);
 void helm_symbolic_destroy(helm_symbolic *sym);
 int helm_symbolic_array(const helm_symbolic *sym, const char *name, const int32_t **data,
                         int32_t *len);
