@@ -40,7 +40,9 @@ thread_local std::string g_err;
 // internal per-scenario status (superset of the public codes)
 enum : int { ST_ACTIVE = 0, ST_FROZEN = 1, ST_CONVERGED = 2, ST_DIVERGED = 3, ST_SINGULAR = 4, ST_PAD = 5 };
 // group flags
-enum : int { GF_NEEDFACTOR = 1, GF_PASSEND = 2, GF_DONE = 4 };
+// PENDING: the group needs a (re)factorization; FACTORING: it is being factorized in the
+// side branch of the current step and sits this order out (see the step graph below).
+enum : int { GF_PENDING = 1, GF_PASSEND = 2, GF_DONE = 4, GF_FACTORING = 8 };
 
 // ---- device-side views ------------------------------------------------------------
 struct PlanDev {
@@ -107,29 +109,29 @@ __device__ __forceinline__ size_t hx(const WorkDev &w, int N, int grp, int k, in
 // ---- K_asm: scatter A into the LU slots (reference helm.py:46-60) -------------------
 // One thread per (slot, scenario).  Fill slots get zero blocks.
 template <int G>
-__global__ void k_assemble(PlanDev p, WorkDev w) {
-    int grp = blockIdx.y;
-    if (!(w.g_flags[grp] & GF_NEEDFACTOR)) return;
-    int flat = blockIdx.x * blockDim.x + threadIdx.x;
-    int slot = flat / G, s = flat % G;
-    if (slot >= p.nslots) return;
-    if (w.s_status[grp * G + s] != ST_ACTIVE) return;
-    int r = p.slot_row[slot];
-    int a = p.slot_src[slot];
-    unsigned char bt = w.btype[ix<G>(grp, p.N, r, s)];
-    bool diag = (p.dslot[r] == slot);
-    double2 r0 = make_double2(0.0, 0.0), r1 = make_double2(0.0, 0.0);
-    if (bt == HELM_BUS_SLACK) {
-        if (diag) { r0.x = 1.0; r1.y = 1.0; }                         // helm.py:47-49
-    } else if (a >= 0) {
-        double2 y = p.ytr[a];
-        r0 = make_double2(y.x, -y.y);                                 // helm.py:52-53 / 59-60
-        if (bt == HELM_BUS_PQ) r1 = make_double2(y.y, y.x);           // helm.py:54-55
-        else if (diag) r1 = make_double2(1.0, 0.0);                   // helm.py:57
+__global__ void __launch_bounds__(256) k_assemble(PlanDev p, WorkDev w) {
+    int grp = blockIdx.x;
+    if (!(w.g_flags[grp] & GF_FACTORING)) return;
+    for (int flat = threadIdx.x; flat < p.nslots * G; flat += blockDim.x) {
+        int slot = flat / G, s = flat % G;
+        if (w.s_status[grp * G + s] != ST_ACTIVE) continue;
+        int r = p.slot_row[slot];
+        int a = p.slot_src[slot];
+        unsigned char bt = w.btype[ix<G>(grp, p.N, r, s)];
+        bool diag = (p.dslot[r] == slot);
+        double2 r0 = make_double2(0.0, 0.0), r1 = make_double2(0.0, 0.0);
+        if (bt == HELM_BUS_SLACK) {
+            if (diag) { r0.x = 1.0; r1.y = 1.0; }                         // helm.py:47-49
+        } else if (a >= 0) {
+            double2 y = p.ytr[a];
+            r0 = make_double2(y.x, -y.y);                                 // helm.py:52-53 / 59-60
+            if (bt == HELM_BUS_PQ) r1 = make_double2(y.y, y.x);           // helm.py:54-55
+            else if (diag) r1 = make_double2(1.0, 0.0);                   // helm.py:57
+        }
+        double2 *dst = w.lu + ix<G>(grp, p.nslots, slot, s) * 2;
+        dst[0] = r0;
+        dst[1] = r1;
     }
-    double2 *dst = w.lu + ix<G>(grp, p.nslots, slot, s) * 2;
-    dst[0] = r0;
-    dst[1] = r1;
 }
 
 struct Blk { double a, b, c, d; };  // [[a b][c d]]
@@ -155,7 +157,7 @@ template <int G, int WPB>
 __global__ void __launch_bounds__(WPB * 32) k_factor(PlanDev p, WorkDev w) {
     int grp = blockIdx.x * WPB + (threadIdx.x >> 5);
     if (grp >= w.ngroups) return;
-    if (!(w.g_flags[grp] & GF_NEEDFACTOR)) return;
+    if (!(w.g_flags[grp] & GF_FACTORING)) return;
     const int R = 32 / G;
     int lane = threadIdx.x & 31;
     int s = lane % G, slot = lane / G;
@@ -214,35 +216,61 @@ __global__ void __launch_bounds__(WPB * 32) k_factor(PlanDev p, WorkDev w) {
 // backward phase works in place.  Rows of one level are independent: lane =
 // (row slot, scenario); levels are separated by __syncwarp().  The factors are
 // consumed in storage order (slots are numbered in consumption order).
+__device__ __forceinline__ Blk ldblk_stream(const double2 *lu, size_t e) {
+    // factors are read exactly once per solve: stream them past L1/L2 residency (ld.global.cs)
+    double2 r0 = __ldcs(lu + e * 2), r1 = __ldcs(lu + e * 2 + 1);
+    return Blk{r0.x, r0.y, r1.x, r1.y};
+}
+__device__ __forceinline__ void bfma(double2 &acc, const Blk &m, const double2 &x) {
+    acc.x -= m.a * x.x + m.b * x.y;
+    acc.y -= m.c * x.x + m.d * x.y;
+}
+
+// acc -= sum_t LU[slot0+t] * x[cols[t]] for one row
 template <int G>
 __device__ __forceinline__ void row_accumulate(const double2 *lu, const double2 *xb, const int *cols,
                                                size_t slot0, int n, int s, double2 &acc) {
     int t = 0;
     for (; t + 4 <= n; t += 4) {                       // 4 entries in flight
-        int c0 = cols[t], c1 = cols[t + 1], c2 = cols[t + 2], c3 = cols[t + 3];
-        Blk m0 = ldblk(lu, (slot0 + t) * G + s), m1 = ldblk(lu, (slot0 + t + 1) * G + s);
-        Blk m2 = ldblk(lu, (slot0 + t + 2) * G + s), m3 = ldblk(lu, (slot0 + t + 3) * G + s);
+        int c0 = __ldg(cols + t), c1 = __ldg(cols + t + 1), c2 = __ldg(cols + t + 2), c3 = __ldg(cols + t + 3);
+        Blk m0 = ldblk_stream(lu, (slot0 + t) * G + s), m1 = ldblk_stream(lu, (slot0 + t + 1) * G + s);
+        Blk m2 = ldblk_stream(lu, (slot0 + t + 2) * G + s), m3 = ldblk_stream(lu, (slot0 + t + 3) * G + s);
         double2 x0 = xb[(size_t)c0 * G + s], x1 = xb[(size_t)c1 * G + s];
         double2 x2 = xb[(size_t)c2 * G + s], x3 = xb[(size_t)c3 * G + s];
-        acc.x -= m0.a * x0.x + m0.b * x0.y; acc.y -= m0.c * x0.x + m0.d * x0.y;
-        acc.x -= m1.a * x1.x + m1.b * x1.y; acc.y -= m1.c * x1.x + m1.d * x1.y;
-        acc.x -= m2.a * x2.x + m2.b * x2.y; acc.y -= m2.c * x2.x + m2.d * x2.y;
-        acc.x -= m3.a * x3.x + m3.b * x3.y; acc.y -= m3.c * x3.x + m3.d * x3.y;
+        bfma(acc, m0, x0); bfma(acc, m1, x1); bfma(acc, m2, x2); bfma(acc, m3, x3);
     }
     for (; t < n; ++t) {
-        int c = cols[t];
-        Blk m = ldblk(lu, (slot0 + t) * G + s);
-        double2 xc = xb[(size_t)c * G + s];
-        acc.x -= m.a * xc.x + m.b * xc.y;
-        acc.y -= m.c * xc.x + m.d * xc.y;
+        int c = __ldg(cols + t);
+        Blk m = ldblk_stream(lu, (slot0 + t) * G + s);
+        bfma(acc, m, xb[(size_t)c * G + s]);
     }
+}
+
+// the same for two independent rows at once (wide levels: twice the loads in flight per lane)
+template <int G>
+__device__ __forceinline__ void row_accumulate2(const double2 *lu, const double2 *xb,
+                                                const int *ca, size_t sa, int na, double2 &acc_a,
+                                                const int *cb, size_t sb, int nb, double2 &acc_b, int s) {
+    int t = 0;
+    int nmin = na < nb ? na : nb;
+    for (; t + 2 <= nmin; t += 2) {
+        int a0 = __ldg(ca + t), a1 = __ldg(ca + t + 1), b0 = __ldg(cb + t), b1 = __ldg(cb + t + 1);
+        Blk ma0 = ldblk_stream(lu, (sa + t) * G + s), ma1 = ldblk_stream(lu, (sa + t + 1) * G + s);
+        Blk mb0 = ldblk_stream(lu, (sb + t) * G + s), mb1 = ldblk_stream(lu, (sb + t + 1) * G + s);
+        double2 xa0 = xb[(size_t)a0 * G + s], xa1 = xb[(size_t)a1 * G + s];
+        double2 xb0 = xb[(size_t)b0 * G + s], xb1 = xb[(size_t)b1 * G + s];
+        bfma(acc_a, ma0, xa0); bfma(acc_a, ma1, xa1);
+        bfma(acc_b, mb0, xb0); bfma(acc_b, mb1, xb1);
+    }
+    row_accumulate<G>(lu, xb, ca + t, sa + t, na - t, s, acc_a);
+    row_accumulate<G>(lu, xb, cb + t, sb + t, nb - t, s, acc_b);
 }
 
 template <int G, int WPB>
 __global__ void __launch_bounds__(WPB * 32) k_solve(PlanDev p, WorkDev w) {
     int grp = blockIdx.x * WPB + (threadIdx.x >> 5);
     if (grp >= w.ngroups) return;
-    if (w.g_flags[grp] & GF_DONE) return;
+    if (w.g_flags[grp] & (GF_DONE | GF_FACTORING)) return;
     const int R = 32 / G;
     int lane = threadIdx.x & 31;
     int s = lane % G, slot = lane / G;
@@ -251,10 +279,21 @@ __global__ void __launch_bounds__(WPB * 32) k_solve(PlanDev p, WorkDev w) {
     const double2 *rhs = w.rhs + (size_t)grp * p.N * G;
     double2 *xb = w.xb + (size_t)grp * p.N * G;
     for (int l = 0; l < p.nLlev; ++l) {
-        int r1 = p.llev_ptr[l + 1];
+        int r1 = __ldg(p.llev_ptr + l + 1);
         if (active) {
-            for (int r = p.llev_ptr[l] + slot; r < r1; r += R) {
-                int e0 = p.lptr[r], e1 = p.lptr[r + 1];
+            int r = __ldg(p.llev_ptr + l) + slot;
+            for (; r + R < r1; r += 2 * R) {           // two rows per lane in flight
+                int rb = r + R;
+                int e0a = __ldg(p.lptr + r), e1a = __ldg(p.lptr + r + 1);
+                int e0b = __ldg(p.lptr + rb), e1b = __ldg(p.lptr + rb + 1);
+                double2 acc_a = rhs[(size_t)r * G + s], acc_b = rhs[(size_t)rb * G + s];
+                row_accumulate2<G>(lu, xb, p.lcol + e0a, (size_t)e0a, e1a - e0a, acc_a,
+                                   p.lcol + e0b, (size_t)e0b, e1b - e0b, acc_b, s);
+                xb[(size_t)r * G + s] = acc_a;
+                xb[(size_t)rb * G + s] = acc_b;
+            }
+            if (r < r1) {
+                int e0 = __ldg(p.lptr + r), e1 = __ldg(p.lptr + r + 1);
                 double2 acc = rhs[(size_t)r * G + s];
                 row_accumulate<G>(lu, xb, p.lcol + e0, (size_t)e0, e1 - e0, s, acc);
                 xb[(size_t)r * G + s] = acc;
@@ -263,13 +302,27 @@ __global__ void __launch_bounds__(WPB * 32) k_solve(PlanDev p, WorkDev w) {
         __syncwarp();
     }
     for (int l = 0; l < p.nUlev; ++l) {
-        int q1 = p.ulev_ptr[l + 1];
+        int q1 = __ldg(p.ulev_ptr + l + 1);
         if (active) {
-            for (int q = p.ulev_ptr[l] + slot; q < q1; q += R) {
-                int r = p.urow[q];
-                int u0 = p.uptr[q], nu = p.uptr[q + 1] - u0;
+            int q = __ldg(p.ulev_ptr + l) + slot;
+            for (; q + R < q1; q += 2 * R) {
+                int qb = q + R;
+                int ra = __ldg(p.urow + q), rb = __ldg(p.urow + qb);
+                int u0a = __ldg(p.uptr + q), nua = __ldg(p.uptr + q + 1) - u0a;
+                int u0b = __ldg(p.uptr + qb), nub = __ldg(p.uptr + qb + 1) - u0b;
+                size_t base_a = (size_t)(p.nL + u0a + q), base_b = (size_t)(p.nL + u0b + qb);
+                Blk da = ldblk_stream(lu, base_a * G + s), db = ldblk_stream(lu, base_b * G + s);
+                double2 acc_a = xb[(size_t)ra * G + s], acc_b = xb[(size_t)rb * G + s];
+                row_accumulate2<G>(lu, xb, p.ucol + u0a, base_a + 1, nua, acc_a,
+                                   p.ucol + u0b, base_b + 1, nub, acc_b, s);
+                xb[(size_t)ra * G + s] = make_double2(da.a * acc_a.x + da.b * acc_a.y, da.c * acc_a.x + da.d * acc_a.y);
+                xb[(size_t)rb * G + s] = make_double2(db.a * acc_b.x + db.b * acc_b.y, db.c * acc_b.x + db.d * acc_b.y);
+            }
+            if (q < q1) {
+                int r = __ldg(p.urow + q);
+                int u0 = __ldg(p.uptr + q), nu = __ldg(p.uptr + q + 1) - u0;
                 size_t base = (size_t)(p.nL + u0 + q);
-                Blk d = ldblk(lu, base * G + s);
+                Blk d = ldblk_stream(lu, base * G + s);
                 double2 acc = xb[(size_t)r * G + s];
                 row_accumulate<G>(lu, xb, p.ucol + u0, base + 1, nu, s, acc);
                 xb[(size_t)r * G + s] = make_double2(d.a * acc.x + d.b * acc.y, d.c * acc.x + d.d * acc.y);
@@ -283,7 +336,7 @@ __global__ void __launch_bounds__(WPB * 32) k_solve(PlanDev p, WorkDev w) {
 template <int G>
 __global__ void k_init(PlanDev p, WorkDev w) {
     int grp = blockIdx.y;
-    if (!(w.g_flags[grp] & GF_NEEDFACTOR)) return;
+    if (!(w.g_flags[grp] & GF_FACTORING)) return;
     int flat = blockIdx.x * blockDim.x + threadIdx.x;
     int i = flat / G, s = flat % G;
     if (i >= p.N) return;
@@ -351,7 +404,7 @@ template <int G>
 __global__ void __launch_bounds__(256) k_rhs_conv(PlanDev p, WorkDev w) {
     int grp = blockIdx.y;
     int gf = w.g_flags[grp];
-    if (gf & (GF_DONE | GF_PASSEND)) return;
+    if (gf & (GF_DONE | GF_PASSEND | GF_FACTORING)) return;
     int flat = blockIdx.x * blockDim.x + threadIdx.x;
     int i = flat / G, s = flat % G;
     if (i >= p.N) return;
@@ -485,7 +538,7 @@ __global__ void k_advance(WorkDev w) {
     int grp = blockIdx.x * blockDim.x + threadIdx.x;
     if (grp >= w.ngroups) return;
     int gf = w.g_flags[grp];
-    if (gf & (GF_DONE | GF_PASSEND)) return;
+    if (gf & (GF_DONE | GF_PASSEND | GF_FACTORING)) return;
     int j = w.g_n[grp] + 1, m = j + 1;
     bool checked = ((j & 1) == 0) && j >= 4;
     int nact = 0;
@@ -504,7 +557,6 @@ __global__ void k_advance(WorkDev w) {
         w.s_fail[sg] = 0;
     }
     w.g_n[grp] = j;
-    gf &= ~GF_NEEDFACTOR;
     if (nact == 0) gf |= GF_PASSEND;
     w.g_flags[grp] = gf;
 }
@@ -567,12 +619,23 @@ __global__ void k_pass_end(WorkDev w) {
     }
     gf &= ~GF_PASSEND;
     if (any) {
-        gf |= GF_NEEDFACTOR;
+        gf |= GF_PENDING;
         w.g_n[grp] = 0;
     } else {
         gf |= GF_DONE;
         atomicSub(w.active_groups, 1);
     }
+    w.g_flags[grp] = gf;
+}
+
+// ---- K_begin: start of a step.  Groups factorized during the previous step rejoin the main
+// branch; groups whose pass ended in the previous step move to the factorization branch.
+__global__ void k_step_begin(WorkDev w) {
+    int grp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (grp >= w.ngroups) return;
+    int gf = w.g_flags[grp];
+    if (gf & GF_FACTORING) gf &= ~GF_FACTORING;
+    else if (gf & GF_PENDING) gf = (gf & ~GF_PENDING) | GF_FACTORING;
     w.g_flags[grp] = gf;
 }
 
@@ -599,7 +662,7 @@ __global__ void k_setup(PlanDev p, WorkDev w, const double *scale_in) {
     }
     if (flat == 0) {
         w.g_n[grp] = 0;
-        w.g_flags[grp] = GF_NEEDFACTOR;
+        w.g_flags[grp] = GF_PENDING;
         if (grp == 0) *w.active_groups = w.ngroups;
     }
 }
@@ -653,6 +716,8 @@ struct helm_plan {
     double *h_vout_pinned = nullptr;
     size_t h_vout_bytes = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 namespace {
@@ -739,15 +804,15 @@ WorkDev bind(const helm_plan *pl, const WsLayout &L, int B, const helm_params *p
 constexpr int T_ELEM = 256;   // threads per CTA of the per-(item, scenario) kernels
 constexpr int WPB_SOLVE = 4;  // warps (= scenario groups) per CTA of the factor / solve kernels
 
-enum { KI_ASM = 0, KI_FACTOR, KI_SOLVE, KI_RHS, KI_ADV, KI_QLIM, KI_PEND, KI_INIT, KI_COUNT };
+enum { KI_ASM = 0, KI_FACTOR, KI_SOLVE, KI_RHS, KI_ADV, KI_QLIM, KI_PEND, KI_INIT, KI_BEGIN, KI_COUNT };
 
 template <int G>
 void launch_kernel(int which, const PlanDev &p, const WorkDev &w, cudaStream_t st) {
     dim3 gridBus((p.N * G + T_ELEM - 1) / T_ELEM, w.ngroups);
-    dim3 gridSlot((p.nslots * G + T_ELEM - 1) / T_ELEM, w.ngroups);
     int gridGrp = (w.ngroups + 127) / 128;
     switch (which) {
-        case KI_ASM: k_assemble<G><<<gridSlot, T_ELEM, 0, st>>>(p, w); break;
+        case KI_ASM: k_assemble<G><<<w.ngroups, 256, 0, st>>>(p, w); break;
+        case KI_BEGIN: k_step_begin<<<gridGrp, 128, 0, st>>>(w); break;
         case KI_FACTOR: k_factor<G, WPB_SOLVE><<<(w.ngroups + WPB_SOLVE - 1) / WPB_SOLVE, WPB_SOLVE * 32, 0, st>>>(p, w); break;
         case KI_INIT: k_init<G><<<gridBus, T_ELEM, 0, st>>>(p, w); break;
         case KI_SOLVE: k_solve<G, WPB_SOLVE><<<(w.ngroups + WPB_SOLVE - 1) / WPB_SOLVE, WPB_SOLVE * 32, 0, st>>>(p, w); break;
@@ -781,9 +846,57 @@ void launch_setup(int G, const PlanDev &p, const WorkDev &w, const double *d_sca
     }
 }
 
-// kernels of one per-order step, in order
-const int STEP_SEQ[] = {KI_ASM, KI_FACTOR, KI_INIT, KI_SOLVE, KI_RHS, KI_ADV, KI_QLIM, KI_PEND};
-constexpr int STEP_LEN = sizeof(STEP_SEQ) / sizeof(int);
+// One per-order step is a fork/join:
+//
+//   k_step_begin ──┬── main branch : solve -> rhs_conv -> advance -> qlimit -> pass_end   (stream st)
+//                  └── side branch : assemble -> factor -> init                            (stream side)
+//
+// Groups that start a Q-limit pass are (re)factorized in the side branch while every other
+// group advances one order in the main branch, so the latency of a numeric factorization is
+// hidden behind the solves of the rest of the batch; the factorized groups rejoin at the
+// next k_step_begin.  Both in eager mode and under stream capture the fork/join is expressed
+// with events, so the captured CUDA graph has the two branches as parallel paths.
+const int MAIN_SEQ[] = {KI_SOLVE, KI_RHS, KI_ADV, KI_QLIM, KI_PEND};
+const int SIDE_SEQ[] = {KI_ASM, KI_FACTOR, KI_INIT};
+constexpr int MAIN_LEN = sizeof(MAIN_SEQ) / sizeof(int);
+constexpr int SIDE_LEN = sizeof(SIDE_SEQ) / sizeof(int);
+constexpr int STEP_LEN = 1 + MAIN_LEN + SIDE_LEN;
+
+struct StepCtx {
+    cudaStream_t st, side;
+    cudaEvent_t fork, join;
+};
+
+void launch_step(int G, const PlanDev &p, const WorkDev &w, const StepCtx &c) {
+    launch_any(G, KI_BEGIN, p, w, c.st);
+    cudaEventRecord(c.fork, c.st);
+    cudaStreamWaitEvent(c.side, c.fork, 0);
+    for (int k = 0; k < SIDE_LEN; ++k) launch_any(G, SIDE_SEQ[k], p, w, c.side);
+    cudaEventRecord(c.join, c.side);
+    for (int k = 0; k < MAIN_LEN; ++k) launch_any(G, MAIN_SEQ[k], p, w, c.st);
+    cudaStreamWaitEvent(c.st, c.join, 0);
+}
+
+// serial variant with an event around every kernel (profile mode)
+void launch_step_profiled(int G, const PlanDev &p, const WorkDev &w, cudaStream_t st,
+                          std::vector<cudaEvent_t> &ev, helm_stats &acc) {
+    int seq[STEP_LEN];
+    int n = 0;
+    seq[n++] = KI_BEGIN;
+    for (int k = 0; k < SIDE_LEN; ++k) seq[n++] = SIDE_SEQ[k];
+    for (int k = 0; k < MAIN_LEN; ++k) seq[n++] = MAIN_SEQ[k];
+    for (int k = 0; k < n; ++k) {
+        cudaEventRecord(ev[k], st);
+        launch_any(G, seq[k], p, w, st);
+    }
+    cudaEventRecord(ev[n], st);
+    cudaEventSynchronize(ev[n]);
+    for (int k = 0; k < n; ++k) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev[k], ev[k + 1]);
+        if (seq[k] < 8) acc.ms_kernel[seq[k]] += ms;
+    }
+}
 
 }  // namespace
 
@@ -856,6 +969,9 @@ void helm_plan_destroy(helm_plan *pl) {
     if (pl->h_pinned) cudaFreeHost(pl->h_pinned);
     if (pl->h_vout_pinned) cudaFreeHost(pl->h_vout_pinned);
     if (pl->stream) cudaStreamDestroy(pl->stream);
+    if (pl->side) cudaStreamDestroy(pl->side);
+    if (pl->ev_fork) cudaEventDestroy(pl->ev_fork);
+    if (pl->ev_join) cudaEventDestroy(pl->ev_join);
     delete pl;
 }
 
@@ -912,12 +1028,17 @@ int helm_solve_batch_device(helm_plan *pl, int32_t B, const double *d_scale, con
     memset(&local, 0, sizeof(local));
     local.kernel_launches = 1;
 
+    if (!pl->side) CUDA_TRY(cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking));
+    if (!pl->ev_fork) {
+        CUDA_TRY(cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&pl->ev_join, cudaEventDisableTiming));
+    }
+    StepCtx ctx{st, pl->side, pl->ev_fork, pl->ev_join};
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t gexec = nullptr;
     if (use_graph) {
         CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        for (int rep = 0; rep < poll_every; ++rep)
-            for (int k = 0; k < STEP_LEN; ++k) launch_any(L.G, STEP_SEQ[k], p, w, st);
+        for (int rep = 0; rep < poll_every; ++rep) launch_step(L.G, p, w, ctx);
         CUDA_TRY(cudaStreamEndCapture(st, &graph));
         CUDA_TRY(cudaGraphInstantiate(&gexec, graph, 0));
     }
@@ -937,19 +1058,8 @@ int helm_solve_batch_device(helm_plan *pl, int32_t B, const double *d_scale, con
             steps += poll_every;
         } else {
             for (int rep = 0; rep < poll_every; ++rep) {
-                for (int k = 0; k < STEP_LEN; ++k) {
-                    if (profile) cudaEventRecord(pev[k], st);
-                    launch_any(L.G, STEP_SEQ[k], p, w, st);
-                }
-                if (profile) {
-                    cudaEventRecord(pev[STEP_LEN], st);
-                    cudaEventSynchronize(pev[STEP_LEN]);
-                    for (int k = 0; k < STEP_LEN; ++k) {
-                        float ms = 0;
-                        cudaEventElapsedTime(&ms, pev[k], pev[k + 1]);
-                        local.ms_kernel[STEP_SEQ[k]] += ms;
-                    }
-                }
+                if (profile) launch_step_profiled(L.G, p, w, st, pev, local);
+                else launch_step(L.G, p, w, ctx);
                 local.kernel_launches += STEP_LEN;
                 steps++;
             }
@@ -1047,8 +1157,10 @@ int helm_debug_factor_solve(helm_plan *pl, int32_t B, int32_t group, const uint8
     }
     CUDA_TRY(cudaMemcpy(w.btype, bt.data(), per, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(w.rhs, rhs.data(), per * sizeof(double2), cudaMemcpyHostToDevice));
+    launch_any(L.G, KI_BEGIN, p, w, 0);   // PENDING -> FACTORING
     launch_any(L.G, KI_ASM, p, w, 0);
     launch_any(L.G, KI_FACTOR, p, w, 0);
+    launch_any(L.G, KI_BEGIN, p, w, 0);   // FACTORING -> main branch
     launch_any(L.G, KI_SOLVE, p, w, 0);
     CUDA_TRY(cudaDeviceSynchronize());
     std::vector<double2> x(per);
