@@ -13,8 +13,8 @@ import numpy as np
 HELM_MAX_PASSES = 16
 ST_RUNNING, ST_CONVERGED, ST_DIVERGED, ST_SINGULAR = 0, 2, 3, 4
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
-                         "libhelm_b200.so")
+_LIB_PATH = os.environ.get("HELM_B200_LIB") or os.path.join(
+    os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "libhelm_b200.so")
 
 
 class HelmB200Error(RuntimeError):
@@ -58,7 +58,7 @@ KERNEL_NAMES = ("assemble", "factor", "solve", "rhs_conv", "advance", "qlimit", 
 EXPORTED_SYMBOLS = (
     "helm_last_error", "helm_plan_create", "helm_plan_destroy", "helm_plan_get_info",
     "helm_plan_get_perm", "helm_workspace_bytes", "helm_solve_batch_device",
-    "helm_solve_batch_host", "helm_debug_factor_solve", "helm_measure_peaks",
+    "helm_solve_batch_host", "helm_debug_factor_solve", "helm_debug_timeline", "helm_measure_peaks",
     "helm_symbolic_create", "helm_symbolic_destroy", "helm_symbolic_array",
 )
 
@@ -96,6 +96,7 @@ def load():
         C.c_void_p, C.c_void_p, C.POINTER(Stats)]
     lib.helm_debug_factor_solve.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                             C.c_void_p, C.c_void_p]
+    lib.helm_debug_timeline.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
     lib.helm_measure_peaks.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.helm_symbolic_create.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.POINTER(C.c_void_p)]
@@ -132,7 +133,8 @@ def symbolic_arrays(adj_ptr, adj_idx, bus_type=None):
     try:
         for name in ("perm", "iperm", "adj_ptr", "adj_idx", "adj_src", "adj_slot", "lptr", "lcol",
                      "llev_ptr", "urow", "qof", "ulev_ptr", "uptr", "ucol", "dslot", "fptr",
-                     "fsrc", "fdst", "slot_src", "slot_row"):
+                     "fsrc", "fdst", "fdst_local", "fchunk_row", "fchunk_lpr", "frow_off",
+                     "slot_src", "slot_row"):
             data = C.c_void_p()
             n = C.c_int32()
             rc = lib.helm_symbolic_array(h, name.encode(), C.byref(data), C.byref(n))

@@ -57,7 +57,9 @@ struct PlanDev {
     const int *lptr, *lcol, *llev_ptr;
     const int *urow, *ulev_ptr, *uptr, *ucol, *dslot;
     const int *slot_src, *slot_row;
-    const int *fptr, *fsrc, *fdst;
+    const int *fptr, *fsrc, *fdst, *fdstl, *qof;
+    const int *fchunk_row, *fchunk_lpr, *frow_off;
+    int max_row_blocks, nfchunks, cap_upd, cap_ent, cap_rowblk;
 };
 
 struct WorkDev {
@@ -75,7 +77,39 @@ struct WorkDev {
     double2 *lu;                      // [group][nslots][G][2]
     double2 *Vh, *Hh, *Eh;            // [group][K][N][G]
     double2 *vout;                    // [B][N] original order
+    unsigned long long *tl;           // timeline buffer (HELM_TIMELINE builds only), else null
 };
+
+// Optional kernel timeline (compile with -DHELM_TIMELINE): per step and kernel, the first CTA
+// start and the last CTA end on the global timer; tl[0] is the step counter.
+#ifdef HELM_TIMELINE
+#define TL_MAXSTEPS 512
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+struct TlScope {
+    unsigned long long *slot;
+    __device__ __forceinline__ TlScope(const unsigned long long *tl_, int kid) {
+        unsigned long long *tl = const_cast<unsigned long long *>(tl_);
+        slot = nullptr;
+        if (tl && threadIdx.x == 0) {
+            unsigned long long step = tl[0];
+            if (step < TL_MAXSTEPS) {
+                slot = tl + 8 + (step * 16 + kid) * 2;
+                atomicMin(slot, gtime());
+            }
+        }
+    }
+    __device__ __forceinline__ ~TlScope() {
+        if (slot) atomicMax(slot + 1, gtime());
+    }
+};
+#define TL_SCOPE(w, kid) TlScope _tl((w).tl, kid)
+#else
+#define TL_SCOPE(w, kid)
+#endif
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
     return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -110,6 +144,7 @@ __device__ __forceinline__ size_t hx(const WorkDev &w, int N, int grp, int k, in
 // One thread per (slot, scenario).  Fill slots get zero blocks.
 template <int G>
 __global__ void __launch_bounds__(256) k_assemble(PlanDev p, WorkDev w) {
+    TL_SCOPE(w, 0);
     int grp = blockIdx.x;
     if (!(w.g_flags[grp] & GF_FACTORING)) return;
     for (int flat = threadIdx.x; flat < p.nslots * G; flat += blockDim.x) {
@@ -211,6 +246,142 @@ __global__ void __launch_bounds__(WPB * 32) k_factor(PlanDev p, WorkDev w) {
     if (singular) w.s_status[sg] = ST_SINGULAR;
 }
 
+// ---- K2f (G = 1): cooperative variant.  Near the root of the elimination tree the levels hold
+// one to eight long rows whose eliminations are inherently sequential per row; there a
+// sub-warp of 4/8/16 lanes works on one row: the row's blocks are staged in shared memory,
+// the updates of one L entry (distinct destinations) are spread over the lanes, and only
+// the multiplier chain stays serial.  Wide levels keep one lane per row.
+__device__ __forceinline__ Blk ldsm(const double2 *b, int i) {
+    double2 r0 = b[2 * i], r1 = b[2 * i + 1];
+    return Blk{r0.x, r0.y, r1.x, r1.y};
+}
+__device__ __forceinline__ void stsm(double2 *b, int i, Blk m) {
+    b[2 * i] = make_double2(m.a, m.b);
+    b[2 * i + 1] = make_double2(m.c, m.d);
+}
+
+constexpr int WPB_FACTOR = 2;   // warps (= scenarios) per CTA of the staged factorization
+
+// Shared-memory plan of one warp:
+// [src blocks cap_upd][Dk blocks cap_ent][row blocks cap_rowblk][dst idx cap_upd][update ptr cap_ent+1]
+__host__ __device__ inline size_t factor_smem_per_warp(int cap_upd, int cap_ent, int cap_rowblk) {
+    return (size_t)(cap_upd + cap_ent + cap_rowblk) * 32 +
+           (size_t)((cap_upd + 3) / 4 * 4 + (cap_ent + 1 + 3) / 4 * 4) * sizeof(int);
+}
+
+// One warp factorizes one scenario chunk by chunk (csrc/symbolic.cpp §4b'): a chunk is a run of
+// consecutive rows of one L-level.  Phase 1: all 32 lanes stage every operand of the chunk in
+// shared memory with independent loads (source U blocks, inverted pivots, destination indices,
+// the rows themselves) — this is where the HBM/L2 latency is paid, once per chunk and with full
+// memory-level parallelism.  Phase 2: each row is eliminated by a sub-warp of `lpr` lanes from
+// shared memory only; the updates of one L entry have distinct destinations and are spread over
+// the lanes, only the multiplier chain is serial.  Phase 3: rows are written back.
+template <int WPB>
+__global__ void __launch_bounds__(WPB * 32) k_factor_coop(PlanDev p, WorkDev w) {
+    TL_SCOPE(w, 1);
+    extern __shared__ double2 smem_f[];
+    int wib = threadIdx.x >> 5;
+    int grp = blockIdx.x * WPB + wib;
+    if (grp >= w.ngroups) return;
+    if (!(w.g_flags[grp] & GF_FACTORING)) return;
+    int lane = threadIdx.x & 31;
+    if (w.s_status[grp] != ST_ACTIVE) return;               // G = 1: warp-uniform
+    double2 *lu = w.lu + (size_t)grp * p.nslots * 2;
+    char *base = (char *)smem_f + (size_t)wib * factor_smem_per_warp(p.cap_upd, p.cap_ent, p.cap_rowblk);
+    double2 *sSrc = (double2 *)base;
+    double2 *sDk = sSrc + (size_t)p.cap_upd * 2;
+    double2 *sRow = sDk + (size_t)p.cap_ent * 2;
+    int *sDl = (int *)(sRow + (size_t)p.cap_rowblk * 2);
+    int *sUp = sDl + (p.cap_upd + 3) / 4 * 4;
+    bool singular = false;
+    for (int c = 0; c < p.nfchunks; ++c) {
+        const int r0 = __ldg(p.fchunk_row + c), r1 = __ldg(p.fchunk_row + c + 1);
+        const int lpr = __ldg(p.fchunk_lpr + c);
+        if (lpr == 0) {                                     // rows without L entries: invert the pivot
+            for (int r = r0 + lane; r < r1; r += 32) {
+                size_t dd = (size_t)__ldg(p.dslot + r);
+                Blk d = ldblk(lu, dd);
+                double det = d.a * d.d - d.b * d.c;
+                if (det == 0.0 || !(det == det)) { singular = true; det = 1.0; }
+                double inv = 1.0 / det;
+                stblk(lu, dd, Blk{d.d * inv, -d.b * inv, -d.c * inv, d.a * inv});
+            }
+            __syncwarp();
+            continue;
+        }
+        const int e_base = __ldg(p.lptr + r0), e_end = __ldg(p.lptr + r1);
+        const int u_base = __ldg(p.fptr + e_base), u_end = __ldg(p.fptr + e_end);
+        // ---- phase 1: stage
+        for (int u = u_base + lane; u < u_end; u += 32) {
+            size_t src = (size_t)__ldg(p.fsrc + u);
+            sSrc[2 * (u - u_base)] = lu[src * 2];
+            sSrc[2 * (u - u_base) + 1] = lu[src * 2 + 1];
+            sDl[u - u_base] = __ldg(p.fdstl + u);
+        }
+        for (int e = e_base + lane; e <= e_end; e += 32) {
+            sUp[e - e_base] = __ldg(p.fptr + e) - u_base;
+            if (e < e_end) {
+                size_t dk = (size_t)__ldg(p.dslot + __ldg(p.lcol + e));
+                sDk[2 * (e - e_base)] = lu[dk * 2];
+                sDk[2 * (e - e_base) + 1] = lu[dk * 2 + 1];
+            }
+        }
+        const int rs = lane / lpr, sl = lane % lpr;
+        const int r = r0 + rs;
+        const bool have = r < r1;
+        int e0 = 0, nl = 0, rowlen = 0, dbase = 0;
+        double2 *buf = sRow;
+        if (have) {
+            e0 = __ldg(p.lptr + r);
+            nl = __ldg(p.lptr + r + 1) - e0;
+            int q = __ldg(p.qof + r);
+            rowlen = nl + 1 + (__ldg(p.uptr + q + 1) - __ldg(p.uptr + q));
+            dbase = __ldg(p.dslot + r);
+            buf = sRow + (size_t)__ldg(p.frow_off + r) * 2;
+            for (int b = sl; b < rowlen; b += lpr) {
+                size_t slot = (b < nl) ? (size_t)(e0 + b) : (size_t)(dbase + (b - nl));
+                buf[2 * b] = lu[slot * 2];
+                buf[2 * b + 1] = lu[slot * 2 + 1];
+            }
+        }
+        __syncwarp();
+        // ---- phase 2: eliminate from shared memory
+        if (have) {
+            const unsigned mask = (lpr >= 32) ? 0xFFFFFFFFu : (((1u << lpr) - 1u) << (rs * lpr));
+            for (int e = 0; e < nl; ++e) {
+                Blk m = bmul(ldsm(buf, e), ldsm(sDk, e0 + e - e_base));
+                int u0 = sUp[e0 + e - e_base], u1 = sUp[e0 + e + 1 - e_base];
+                for (int u = u0 + sl; u < u1; u += lpr) {
+                    Blk src = ldsm(sSrc, u);
+                    int dl = sDl[u];
+                    Blk dst = ldsm(buf, dl);
+                    Blk pr = bmul(m, src);
+                    dst.a -= pr.a; dst.b -= pr.b; dst.c -= pr.c; dst.d -= pr.d;
+                    stsm(buf, dl, dst);
+                }
+                __syncwarp(mask);
+                if (sl == 0) stsm(buf, e, m);
+            }
+            if (sl == 0) {
+                Blk d = ldsm(buf, nl);
+                double det = d.a * d.d - d.b * d.c;
+                if (det == 0.0 || !(det == det)) { singular = true; det = 1.0; }
+                double inv = 1.0 / det;
+                stsm(buf, nl, Blk{d.d * inv, -d.b * inv, -d.c * inv, d.a * inv});
+            }
+            __syncwarp(mask);
+            // ---- phase 3: write back
+            for (int b = sl; b < rowlen; b += lpr) {
+                size_t slot = (b < nl) ? (size_t)(e0 + b) : (size_t)(dbase + (b - nl));
+                lu[slot * 2] = buf[2 * b];
+                lu[slot * 2 + 1] = buf[2 * b + 1];
+            }
+        }
+        __syncwarp();
+    }
+    if (__any_sync(0xFFFFFFFFu, singular) && lane == 0) w.s_status[grp] = ST_SINGULAR;
+}
+
 // ---- K2: level-scheduled block SpTRSV (replaces SuperLU gstrs, helm.py:602) -----------
 // One WARP per group.  x = U^-1 L^-1 rhs; the forward phase writes y into xb, the
 // backward phase works in place.  Rows of one level are independent: lane =
@@ -268,6 +439,7 @@ __device__ __forceinline__ void row_accumulate2(const double2 *lu, const double2
 
 template <int G, int WPB>
 __global__ void __launch_bounds__(WPB * 32) k_solve(PlanDev p, WorkDev w) {
+    TL_SCOPE(w, 2);
     int grp = blockIdx.x * WPB + (threadIdx.x >> 5);
     if (grp >= w.ngroups) return;
     if (w.g_flags[grp] & (GF_DONE | GF_FACTORING)) return;
@@ -335,6 +507,7 @@ __global__ void __launch_bounds__(WPB * 32) k_solve(PlanDev p, WorkDev w) {
 // ---- K_init: order-0 germ and RHS of order 1 (helm.py:110-139, 551-556, n == 1 branches) ---
 template <int G>
 __global__ void k_init(PlanDev p, WorkDev w) {
+    TL_SCOPE(w, 7);
     int grp = blockIdx.y;
     if (!(w.g_flags[grp] & GF_FACTORING)) return;
     int flat = blockIdx.x * blockDim.x + threadIdx.x;
@@ -402,6 +575,7 @@ __device__ __forceinline__ void eps_step(EpsState &st, int t, int j, double2 v, 
 
 template <int G>
 __global__ void __launch_bounds__(256) k_rhs_conv(PlanDev p, WorkDev w) {
+    TL_SCOPE(w, 3);
     int grp = blockIdx.y;
     int gf = w.g_flags[grp];
     if (gf & (GF_DONE | GF_PASSEND | GF_FACTORING)) return;
@@ -535,6 +709,7 @@ __global__ void __launch_bounds__(256) k_rhs_conv(PlanDev p, WorkDev w) {
 
 // ---- K_adv: per-group bookkeeping after an order (helm.py:608-657 control flow) ----------
 __global__ void k_advance(WorkDev w) {
+    TL_SCOPE(w, 4);
     int grp = blockIdx.x * blockDim.x + threadIdx.x;
     if (grp >= w.ngroups) return;
     int gf = w.g_flags[grp];
@@ -564,6 +739,7 @@ __global__ void k_advance(WorkDev w) {
 // ---- K4: Q-limit check on the Pade voltages, result write-out (helm.py:452-490, 985) -----
 template <int G>
 __global__ void k_qlimit(PlanDev p, WorkDev w) {
+    TL_SCOPE(w, 5);
     int grp = blockIdx.y;
     if (!(w.g_flags[grp] & GF_PASSEND)) return;
     int flat = blockIdx.x * blockDim.x + threadIdx.x;
@@ -597,6 +773,7 @@ __global__ void k_qlimit(PlanDev p, WorkDev w) {
 
 // ---- K_pend: pass bookkeeping (helm.py:936-955, 644-653) ----------------------------------
 __global__ void k_pass_end(WorkDev w) {
+    TL_SCOPE(w, 6);
     int grp = blockIdx.x * blockDim.x + threadIdx.x;
     if (grp >= w.ngroups) return;
     int gf = w.g_flags[grp];
@@ -631,6 +808,9 @@ __global__ void k_pass_end(WorkDev w) {
 // ---- K_begin: start of a step.  Groups factorized during the previous step rejoin the main
 // branch; groups whose pass ended in the previous step move to the factorization branch.
 __global__ void k_step_begin(WorkDev w) {
+#ifdef HELM_TIMELINE
+    if (w.tl && blockIdx.x == 0 && threadIdx.x == 0) w.tl[0] += 1;
+#endif
     int grp = blockIdx.x * blockDim.x + threadIdx.x;
     if (grp >= w.ngroups) return;
     int gf = w.g_flags[grp];
@@ -718,6 +898,7 @@ struct helm_plan {
     cudaStream_t stream = nullptr;
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    unsigned long long *tl = nullptr;
 };
 
 namespace {
@@ -798,6 +979,7 @@ WorkDev bind(const helm_plan *pl, const WsLayout &L, int B, const helm_params *p
     w.Hh = (double2 *)(b + L.off_Hh);
     w.Eh = (double2 *)(b + L.off_Eh);
     w.vout = (double2 *)vout;
+    w.tl = pl->tl;
     return w;
 }
 
@@ -813,7 +995,14 @@ void launch_kernel(int which, const PlanDev &p, const WorkDev &w, cudaStream_t s
     switch (which) {
         case KI_ASM: k_assemble<G><<<w.ngroups, 256, 0, st>>>(p, w); break;
         case KI_BEGIN: k_step_begin<<<gridGrp, 128, 0, st>>>(w); break;
-        case KI_FACTOR: k_factor<G, WPB_SOLVE><<<(w.ngroups + WPB_SOLVE - 1) / WPB_SOLVE, WPB_SOLVE * 32, 0, st>>>(p, w); break;
+        case KI_FACTOR:
+            if (G == 1) {
+                size_t smem = WPB_FACTOR * factor_smem_per_warp(p.cap_upd, p.cap_ent, p.cap_rowblk);
+                k_factor_coop<WPB_FACTOR><<<(w.ngroups + WPB_FACTOR - 1) / WPB_FACTOR, WPB_FACTOR * 32, smem, st>>>(p, w);
+            } else {
+                k_factor<G, WPB_SOLVE><<<(w.ngroups + WPB_SOLVE - 1) / WPB_SOLVE, WPB_SOLVE * 32, 0, st>>>(p, w);
+            }
+            break;
         case KI_INIT: k_init<G><<<gridBus, T_ELEM, 0, st>>>(p, w); break;
         case KI_SOLVE: k_solve<G, WPB_SOLVE><<<(w.ngroups + WPB_SOLVE - 1) / WPB_SOLVE, WPB_SOLVE * 32, 0, st>>>(p, w); break;
         case KI_RHS: k_rhs_conv<G><<<gridBus, T_ELEM, 0, st>>>(p, w); break;
@@ -868,6 +1057,13 @@ struct StepCtx {
 };
 
 void launch_step(int G, const PlanDev &p, const WorkDev &w, const StepCtx &c) {
+    static const bool nofork = getenv("HELM_B200_NOFORK") != nullptr;   // A/B switch: serial step
+    if (nofork) {
+        launch_any(G, KI_BEGIN, p, w, c.st);
+        for (int k = 0; k < SIDE_LEN; ++k) launch_any(G, SIDE_SEQ[k], p, w, c.st);
+        for (int k = 0; k < MAIN_LEN; ++k) launch_any(G, MAIN_SEQ[k], p, w, c.st);
+        return;
+    }
     launch_any(G, KI_BEGIN, p, w, c.st);
     cudaEventRecord(c.fork, c.st);
     cudaStreamWaitEvent(c.side, c.fork, 0);
@@ -951,8 +1147,22 @@ int helm_plan_create(const helm_grid_host *g, helm_plan **out) {
     UP(S.perm, perm) UP(S.lptr, lptr) UP(S.lcol, lcol) UP(S.llev_ptr, llev_ptr)
     UP(S.urow, urow) UP(S.ulev_ptr, ulev_ptr) UP(S.uptr, uptr) UP(S.ucol, ucol) UP(S.dslot, dslot)
     UP(S.slot_src, slot_src) UP(S.slot_row, slot_row)
-    UP(S.fptr, fptr) UP(S.fsrc, fsrc) UP(S.fdst, fdst)
+    UP(S.fptr, fptr) UP(S.fsrc, fsrc) UP(S.fdst, fdst) UP(S.fdst_local, fdstl) UP(S.qof, qof)
+    UP(S.fchunk_row, fchunk_row) UP(S.fchunk_lpr, fchunk_lpr) UP(S.frow_off, frow_off)
+    d.max_row_blocks = S.max_row_blocks;
+    d.nfchunks = (int)S.fchunk_lpr.size(); d.cap_upd = S.cap_upd; d.cap_ent = S.cap_ent; d.cap_rowblk = S.cap_rowblk;
 #undef UP
+    {
+        size_t smem = WPB_FACTOR * factor_smem_per_warp(pl->d.cap_upd, pl->d.cap_ent, pl->d.cap_rowblk);
+        if (smem > 200 * 1024) { g_err = "row too long for the staged factorization buffer"; helm_plan_destroy(pl); return HELM_E_STRUCT; }
+        // the attribute is per function, not per plan: only ever raise it
+        static size_t smem_set = 48 * 1024;
+        if (smem > smem_set) {
+            CUDA_TRY(cudaFuncSetAttribute(k_factor_coop<WPB_FACTOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CUDA_TRY(cudaFuncSetAttribute(k_factor_coop<WPB_FACTOR>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            smem_set = smem;
+        }
+    }
     *out = pl;
     return HELM_OK;
 }
@@ -1018,6 +1228,16 @@ int helm_solve_batch_device(helm_plan *pl, int32_t B, const double *d_scale, con
     int poll_every = prm->poll_every > 0 ? prm->poll_every : 4;
     if (!pl->h_pinned) CUDA_TRY(cudaMallocHost((void **)&pl->h_pinned, 64));
 
+#ifdef HELM_TIMELINE
+    {
+        size_t n = 8 + (size_t)TL_MAXSTEPS * 16 * 2;
+        if (!pl->tl) CUDA_TRY(cudaMalloc((void **)&pl->tl, n * sizeof(unsigned long long)));
+        std::vector<unsigned long long> init(n, 0);
+        for (size_t i = 8; i < n; i += 2) init[i] = ~0ull;
+        CUDA_TRY(cudaMemcpy(pl->tl, init.data(), n * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+        w.tl = pl->tl;
+    }
+#endif
     cudaEvent_t ev0, ev1;
     CUDA_TRY(cudaEventCreate(&ev0));
     CUDA_TRY(cudaEventCreate(&ev1));
@@ -1028,7 +1248,13 @@ int helm_solve_batch_device(helm_plan *pl, int32_t B, const double *d_scale, con
     memset(&local, 0, sizeof(local));
     local.kernel_launches = 1;
 
-    if (!pl->side) CUDA_TRY(cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking));
+    if (!pl->side) {
+        // the factorization branch is short and latency-bound: give it scheduling priority so its
+        // few CTAs are not queued behind the large grids of the main branch
+        int lo = 0, hi = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&pl->side, cudaStreamNonBlocking, hi));
+    }
     if (!pl->ev_fork) {
         CUDA_TRY(cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&pl->ev_join, cudaEventDisableTiming));
@@ -1177,6 +1403,19 @@ int helm_debug_factor_solve(helm_plan *pl, int32_t B, int32_t group, const uint8
     cudaFree(ws);
     cudaFree(d_scale);
     return HELM_OK;
+}
+
+int helm_debug_timeline(helm_plan *pl, uint64_t *out, int32_t max_steps) {
+#ifdef HELM_TIMELINE
+    if (!pl || !pl->tl || !out) { g_err = "no timeline"; return HELM_E_ARG; }
+    int n = std::min<int>(max_steps, TL_MAXSTEPS);
+    CUDA_TRY(cudaMemcpy(out, pl->tl + 8, (size_t)n * 16 * 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return HELM_OK;
+#else
+    (void)pl; (void)out; (void)max_steps;
+    g_err = "library built without -DHELM_TIMELINE";
+    return HELM_E_ARG;
+#endif
 }
 
 int helm_measure_peaks(double *dfma_tflops, double *copy_gbs) {

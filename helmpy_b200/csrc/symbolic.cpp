@@ -228,9 +228,56 @@ bool build_symbolic(int N, const int32_t *adj_ptr, const int32_t *adj_idx, const
                 }
                 S.fsrc.push_back(S.slotU(qk, (int)t));
                 S.fdst.push_back(dst);
+                int nl = S.lptr[r + 1] - S.lptr[r];
+                S.fdst_local.push_back(dst < S.nL ? dst - S.lptr[r] : nl + (dst - S.dslot[r]));
             }
             S.fptr[e + 1] = (int)S.fsrc.size();
         }
+
+    for (int r = 0; r < N; ++r) {
+        int q = S.qof[r];
+        S.max_row_blocks = std::max(S.max_row_blocks, (S.lptr[r + 1] - S.lptr[r]) + 1 + (S.uptr[q + 1] - S.uptr[q]));
+    }
+
+    // ---- 4b'. factorization chunks -----------------------------------------------------------
+    {
+        const int CAPU_LIMIT = 640;   // staged 2x2 source blocks per chunk (20 KB)
+        S.frow_off.assign(N, 0);
+        S.fchunk_row.clear();
+        S.fchunk_lpr.clear();
+        for (int l = 0; l < nLlev; ++l) {
+            int r0 = S.llev_ptr[l], r1 = S.llev_ptr[l + 1];
+            bool diag_only = true;
+            for (int r = r0; r < r1; ++r) diag_only = diag_only && (S.lptr[r + 1] == S.lptr[r]);
+            if (diag_only) {
+                S.fchunk_row.push_back(r0);
+                S.fchunk_lpr.push_back(0);
+                continue;
+            }
+            int r = r0;
+            while (r < r1) {
+                int start = r, upd = 0, ent = 0, blk = 0;
+                while (r < r1 && r - start < 32) {
+                    int u = S.fptr[S.lptr[r + 1]] - S.fptr[S.lptr[r]];
+                    if (r > start && upd + u > CAPU_LIMIT) break;
+                    int q = S.qof[r];
+                    S.frow_off[r] = blk;
+                    blk += (S.lptr[r + 1] - S.lptr[r]) + 1 + (S.uptr[q + 1] - S.uptr[q]);
+                    upd += u;
+                    ent += S.lptr[r + 1] - S.lptr[r];
+                    ++r;
+                }
+                int nrows = r - start, p2 = 1;
+                while (p2 < nrows) p2 <<= 1;
+                S.fchunk_row.push_back(start);
+                S.fchunk_lpr.push_back(std::max(1, std::min(16, 32 / p2)));
+                S.cap_upd = std::max(S.cap_upd, upd);
+                S.cap_ent = std::max(S.cap_ent, ent);
+                S.cap_rowblk = std::max(S.cap_rowblk, blk);
+            }
+        }
+        S.fchunk_row.push_back(N);
+    }
 
     // ---- 4c. adjacency in the new numbering + assembly map -------------------------
     S.adj_ptr.assign(N + 1, 0);

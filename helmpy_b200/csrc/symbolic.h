@@ -26,6 +26,15 @@ struct Symbolic {
     // numeric factorization schedule: for L entry e, updates u in [fptr[e], fptr[e+1])
     // do  LU[fdst[u]] -= L_e * LU[fsrc[u]]
     std::vector<int> fptr, fsrc, fdst;
+    // fdst_local[u]: position of fdst[u] inside its row's buffer [L entries | D | U entries]
+    std::vector<int> fdst_local;
+    int max_row_blocks = 0;                      // max over rows of nL(r) + 1 + nU(r)
+    // factorization chunks: consecutive rows of one L-level that one warp factorizes together
+    // with all their operands staged in shared memory.  Chunk c covers rows
+    // [fchunk_row[c], fchunk_row[c+1]); fchunk_lpr[c] = lanes per row (0: diagonal-only rows).
+    std::vector<int> fchunk_row, fchunk_lpr;
+    std::vector<int> frow_off;                   // row -> block offset of its buffer inside its chunk
+    int cap_upd = 0, cap_ent = 0, cap_rowblk = 0;  // staging capacities (max over chunks)
     // assembly map: slot -> adjacency entry (or -1 for fill), slot -> row
     std::vector<int> slot_src, slot_row;
 

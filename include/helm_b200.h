@@ -147,6 +147,11 @@ int helm_debug_factor_solve(helm_plan *plan, int32_t n_scen, int32_t group,
                             const double *h_rhs /* [n_scen*2*n_bus] original order */,
                             double *h_x /* [n_scen*2*n_bus] */);
 
+/* Kernel timeline of the last solve (only in builds with -DHELM_TIMELINE): for step s and kernel
+ * k (index as in helm_stats.ms_kernel), out[(s*16+k)*2+{0,1}] = first-CTA start / last-CTA end
+ * on the GPU global timer (ns); untouched entries are {~0, 0}. */
+int helm_debug_timeline(helm_plan *plan, uint64_t *out, int32_t max_steps);
+
 /* Host-only view of the symbolic analysis (no CUDA): ordering, fill, level
  * sets and schedules as int32 arrays, by name (see csrc/symbolic.h). */
 typedef struct helm_symbolic helm_symbolic;

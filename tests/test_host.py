@@ -120,3 +120,22 @@ def test_block_lu_static_pivoting_matches_superlu(name):
             for i in range(case.N):
                 if bt[i] == 1 and An.getrow(2 * i + 1).nnz > 1:
                     bt[i] = 0
+
+
+@pytest.mark.parametrize('name', ['case118', 'case1354pegase'])
+def test_factor_schedule_local_indices(name):
+    """fdst_local addresses the same block as fdst inside the row buffer [L | D | U]."""
+    case = load_case(name)
+    S = _lib.symbolic_arrays(case.adj_ptr, case.adj_idx, case.bus_types_code())
+    N = case.N
+    nL = len(S['lcol'])
+    for r in range(N):
+        e0, e1 = S['lptr'][r], S['lptr'][r + 1]
+        nl = e1 - e0
+        base = S['dslot'][r]
+        for e in range(e0, e1):
+            for u in range(S['fptr'][e], S['fptr'][e + 1]):
+                dl = S['fdst_local'][u]
+                slot = e0 + dl if dl < nl else base + (dl - nl)
+                assert slot == S['fdst'][u]
+                assert S['fsrc'][u] >= nL          # sources are U blocks of an earlier row
