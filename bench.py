@@ -359,7 +359,7 @@ def main():
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='cuda', choices=['cuda', 'reference'])
-    ap.add_argument('--batch', type=int, default=int(os.environ.get('HELM_BENCH_BATCH', '2048')),
+    ap.add_argument('--batch', type=int, default=int(os.environ.get('HELM_BENCH_BATCH', '4096')),
                     help='scenarios per GPU per step')
     ap.add_argument('--group', type=int, default=int(os.environ.get('HELM_BENCH_GROUP', '1')))
     ap.add_argument('--no-cpu-baseline', action='store_true')

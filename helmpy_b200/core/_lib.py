@@ -134,6 +134,7 @@ def symbolic_arrays(adj_ptr, adj_idx, bus_type=None):
         for name in ("perm", "iperm", "adj_ptr", "adj_idx", "adj_src", "adj_slot", "lptr", "lcol",
                      "llev_ptr", "urow", "qof", "ulev_ptr", "uptr", "ucol", "dslot", "fptr",
                      "fsrc", "fdst", "fdst_local", "fchunk_row", "fchunk_lpr", "frow_off",
+                     "sstep_kind", "sstep_a", "sstep_b", "sring_desc",
                      "slot_src", "slot_row"):
             data = C.c_void_p()
             n = C.c_int32()

@@ -59,6 +59,8 @@ struct PlanDev {
     const int *slot_src, *slot_row;
     const int *fptr, *fsrc, *fdst, *fdstl, *qof;
     const int *fchunk_row, *fchunk_lpr, *frow_off;
+    const int *sstep_kind, *sstep_a, *sstep_b, *sring_desc;
+    int nsteps, nring, use_smem_solve, smem_solve_max_groups;
     int max_row_blocks, nfchunks, cap_upd, cap_ent, cap_rowblk;
 };
 
@@ -107,8 +109,12 @@ struct TlScope {
     }
 };
 #define TL_SCOPE(w, kid) TlScope _tl((w).tl, kid)
+#define TL_CLK_DECL long long _c0 = clock64(), _c1
+#define TL_CLK_ADD(w, idx) do { _c1 = clock64(); if ((w).tl && threadIdx.x == 0) atomicAdd((w).tl + (idx), (unsigned long long)(_c1 - _c0)); _c0 = _c1; } while (0)
 #else
 #define TL_SCOPE(w, kid)
+#define TL_CLK_DECL
+#define TL_CLK_ADD(w, idx)
 #endif
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
@@ -502,6 +508,312 @@ __global__ void __launch_bounds__(WPB * 32) k_solve(PlanDev p, WorkDev w) {
         }
         __syncwarp();
     }
+}
+
+// ---- K2 (G = 1), warp per scenario with cooperative thin levels ---------------------------------
+// Same data flow as k_solve<1>, but levels with fewer than 16 rows (the long tail near the root of
+// the elimination tree: 1-8 rows of 20-60 entries each) give each row to a sub-warp whose lanes
+// split the row's entries and combine with shuffles, instead of leaving 31 lanes idle while one
+// lane walks a 57-entry row.  Cuts the executed warp instructions per solve ~4x (ncu, profiles/).
+template <int WPB>
+__global__ void __launch_bounds__(WPB * 32) k_solve_warp(PlanDev p, WorkDev w) {
+    TL_SCOPE(w, 2);
+    int grp = blockIdx.x * WPB + (threadIdx.x >> 5);
+    if (grp >= w.ngroups) return;
+    if (w.g_flags[grp] & (GF_DONE | GF_FACTORING)) return;
+    if (w.s_status[grp] != ST_ACTIVE) return;
+    const int lane = threadIdx.x & 31;
+    const double2 *lu = w.lu + (size_t)grp * p.nslots * 2;
+    const double2 *rhs = w.rhs + (size_t)grp * p.N;
+    double2 *xb = w.xb + (size_t)grp * p.N;
+    for (int l = 0; l < p.nLlev; ++l) {
+        const int r0 = __ldg(p.llev_ptr + l), r1 = __ldg(p.llev_ptr + l + 1);
+        const int width = r1 - r0;
+        if (width >= 16) {
+            int r = r0 + lane;
+            for (; r + 32 < r1; r += 64) {
+                int rb = r + 32;
+                int e0a = __ldg(p.lptr + r), e1a = __ldg(p.lptr + r + 1);
+                int e0b = __ldg(p.lptr + rb), e1b = __ldg(p.lptr + rb + 1);
+                double2 acc_a = rhs[r], acc_b = rhs[rb];
+                row_accumulate2<1>(lu, xb, p.lcol + e0a, (size_t)e0a, e1a - e0a, acc_a,
+                                   p.lcol + e0b, (size_t)e0b, e1b - e0b, acc_b, 0);
+                xb[r] = acc_a;
+                xb[rb] = acc_b;
+            }
+            if (r < r1) {
+                int e0 = __ldg(p.lptr + r), e1 = __ldg(p.lptr + r + 1);
+                double2 acc = rhs[r];
+                row_accumulate<1>(lu, xb, p.lcol + e0, (size_t)e0, e1 - e0, 0, acc);
+                xb[r] = acc;
+            }
+        } else {
+            const int lpr = (width <= 1) ? 32 : (width <= 2) ? 16 : (width <= 4) ? 8 : (width <= 8) ? 4 : 2;
+            const int rs = lane / lpr, sl = lane % lpr;
+            const int r = r0 + rs;
+            double2 sum = make_double2(0.0, 0.0);
+            if (r < r1) {
+                int e0 = __ldg(p.lptr + r), e1 = __ldg(p.lptr + r + 1);
+                for (int e = e0 + sl; e < e1; e += lpr) {
+                    int c = __ldg(p.lcol + e);
+                    Blk m = ldblk_stream(lu, (size_t)e);
+                    double2 x = xb[c];
+                    sum.x += m.a * x.x + m.b * x.y;
+                    sum.y += m.c * x.x + m.d * x.y;
+                }
+            }
+            for (int o = lpr >> 1; o > 0; o >>= 1) {
+                sum.x += __shfl_xor_sync(0xFFFFFFFFu, sum.x, o);
+                sum.y += __shfl_xor_sync(0xFFFFFFFFu, sum.y, o);
+            }
+            if (r < r1 && sl == 0) {
+                double2 b = rhs[r];
+                xb[r] = make_double2(b.x - sum.x, b.y - sum.y);
+            }
+        }
+        __syncwarp();
+    }
+    for (int l = 0; l < p.nUlev; ++l) {
+        const int q0 = __ldg(p.ulev_ptr + l), q1 = __ldg(p.ulev_ptr + l + 1);
+        const int width = q1 - q0;
+        if (width >= 16) {
+            int q = q0 + lane;
+            for (; q + 32 < q1; q += 64) {
+                int qb = q + 32;
+                int ra = __ldg(p.urow + q), rb = __ldg(p.urow + qb);
+                int u0a = __ldg(p.uptr + q), nua = __ldg(p.uptr + q + 1) - u0a;
+                int u0b = __ldg(p.uptr + qb), nub = __ldg(p.uptr + qb + 1) - u0b;
+                size_t base_a = (size_t)(p.nL + u0a + q), base_b = (size_t)(p.nL + u0b + qb);
+                Blk da = ldblk_stream(lu, base_a), db = ldblk_stream(lu, base_b);
+                double2 acc_a = xb[ra], acc_b = xb[rb];
+                row_accumulate2<1>(lu, xb, p.ucol + u0a, base_a + 1, nua, acc_a,
+                                   p.ucol + u0b, base_b + 1, nub, acc_b, 0);
+                xb[ra] = make_double2(da.a * acc_a.x + da.b * acc_a.y, da.c * acc_a.x + da.d * acc_a.y);
+                xb[rb] = make_double2(db.a * acc_b.x + db.b * acc_b.y, db.c * acc_b.x + db.d * acc_b.y);
+            }
+            if (q < q1) {
+                int r = __ldg(p.urow + q);
+                int u0 = __ldg(p.uptr + q), nu = __ldg(p.uptr + q + 1) - u0;
+                size_t base = (size_t)(p.nL + u0 + q);
+                Blk d = ldblk_stream(lu, base);
+                double2 acc = xb[r];
+                row_accumulate<1>(lu, xb, p.ucol + u0, base + 1, nu, 0, acc);
+                xb[r] = make_double2(d.a * acc.x + d.b * acc.y, d.c * acc.x + d.d * acc.y);
+            }
+        } else {
+            const int lpr = (width <= 1) ? 32 : (width <= 2) ? 16 : (width <= 4) ? 8 : (width <= 8) ? 4 : 2;
+            const int rs = lane / lpr, sl = lane % lpr;
+            const int q = q0 + rs;
+            double2 sum = make_double2(0.0, 0.0);
+            size_t base = 0;
+            int r = 0;
+            if (q < q1) {
+                r = __ldg(p.urow + q);
+                int u0 = __ldg(p.uptr + q), nu = __ldg(p.uptr + q + 1) - u0;
+                base = (size_t)(p.nL + u0 + q);
+                for (int t = sl; t < nu; t += lpr) {
+                    int c = __ldg(p.ucol + u0 + t);
+                    Blk m = ldblk_stream(lu, base + 1 + t);
+                    double2 x = xb[c];
+                    sum.x += m.a * x.x + m.b * x.y;
+                    sum.y += m.c * x.x + m.d * x.y;
+                }
+            }
+            for (int o = lpr >> 1; o > 0; o >>= 1) {
+                sum.x += __shfl_xor_sync(0xFFFFFFFFu, sum.x, o);
+                sum.y += __shfl_xor_sync(0xFFFFFFFFu, sum.y, o);
+            }
+            if (q < q1 && sl == 0) {
+                Blk d = ldblk_stream(lu, base);
+                double2 cur = xb[r];
+                double ax = cur.x - sum.x, ay = cur.y - sum.y;
+                xb[r] = make_double2(d.a * ax + d.b * ay, d.c * ax + d.d * ay);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---- K2 (G = 1, N*16 B fits in shared memory): shared-memory solve ------------------------------
+// One CTA per scenario.  The solution vector lives in shared memory, so a dependent level costs a
+// barrier and a shared-memory round trip instead of an L2 one.  The levels near the root of the
+// elimination tree (few, long rows — they make up most of the 172-step dependency chain) are
+// "ring" steps: their factor blocks, column indices and row pointers are contiguous in storage, and
+// are prefetched RING_D steps ahead into a shared-memory ring with cp.async (LDGSTS), so the chain
+// never waits for HBM; there one warp takes one row and its lanes split the row's entries.  The
+// wide levels near the leaves have thousands of independent rows and read their factors straight
+// from global memory, one row per thread.
+constexpr int SM_T = 256;                      // threads per CTA
+constexpr int SM_NW = SM_T / 32;
+constexpr int RING_D = 4;                      // prefetch distance (ring slots)
+constexpr int RING_BLK = helm::Symbolic::RING_BLOCKS;
+constexpr int RING_ROWS = helm::Symbolic::RING_ROWS;
+// slot layout (bytes): [vals RING_BLK*32][cols RING_BLK*4][rowptr (RING_ROWS+4)*4][rows (RING_ROWS+4)*4]
+constexpr int RING_SLOT_BYTES = RING_BLK * 32 + RING_BLK * 4 + 2 * (RING_ROWS + 4) * 4;
+
+// shared memory: [x: N double2][ring: RING_D slots][ring descriptors: nring*8 ints][steps: nsteps*3 ints]
+__host__ __device__ inline size_t solve_smem_bytes(int N, int nring, int nsteps) {
+    return (size_t)N * sizeof(double2) + (size_t)RING_D * RING_SLOT_BYTES +
+           (size_t)((nring * 8 + nsteps * 3 + 3) / 4 * 4) * sizeof(int);
+}
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int NPEND>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NPEND) : "memory"); }
+
+// issue the copies of ring step kk (descriptor in shared memory) into its slot; every thread
+// commits one group
+__device__ __forceinline__ void ring_issue(const PlanDev &p, const double2 *lu, char *ring, const int *sdesc,
+                                           int kk, int tid) {
+    if (kk < p.nring) {
+        const int *d = sdesc + kk * 8;
+        int kind = d[0], row0 = d[1], nrows = d[2], slot0 = d[3];
+        int nblk = d[4], col0 = d[5], ncol = d[6];
+        char *slot = ring + (size_t)(kk % RING_D) * RING_SLOT_BYTES;
+        const char *gv = (const char *)(lu + (size_t)slot0 * 2);
+        for (int i = tid; i < nblk * 2; i += SM_T) cp_async16(slot + (size_t)i * 16, gv + (size_t)i * 16);
+        int *sc = (int *)(slot + RING_BLK * 32);
+        const int *gc = (kind == 1 ? p.lcol : p.ucol) + col0;
+        for (int i = tid; i < ncol; i += SM_T) cp_async4(sc + i, gc + i);
+        int *sp = sc + RING_BLK;
+        const int *gp = (kind == 1 ? p.lptr : p.uptr) + row0;
+        for (int i = tid; i <= nrows; i += SM_T) cp_async4(sp + i, gp + i);
+        if (kind == 3) {
+            int *sr = sp + RING_ROWS + 4;
+            for (int i = tid; i < nrows; i += SM_T) cp_async4(sr + i, p.urow + row0 + i);
+        }
+    }
+    cp_async_commit();
+}
+
+__device__ __forceinline__ double2 warp_sum2(double2 v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        v.x += __shfl_xor_sync(0xFFFFFFFFu, v.x, o);
+        v.y += __shfl_xor_sync(0xFFFFFFFFu, v.y, o);
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(SM_T) k_solve_smem(PlanDev p, WorkDev w) {
+    TL_SCOPE(w, 2);
+    extern __shared__ double2 smem_s[];
+    const int grp = blockIdx.x;                              // G = 1: one scenario per CTA
+    if (w.g_flags[grp] & (GF_DONE | GF_FACTORING)) return;
+    if (w.s_status[grp] != ST_ACTIVE) return;
+    const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+    const int N = p.N;
+    double2 *xs = smem_s;
+    char *ring = (char *)(smem_s + N);
+    const double2 *lu = w.lu + (size_t)grp * p.nslots * 2;
+    const double2 *rhs = w.rhs + (size_t)grp * N;
+    double2 *xb = w.xb + (size_t)grp * N;
+    int *sdesc = (int *)(ring + (size_t)RING_D * RING_SLOT_BYTES);
+    int *ssteps = sdesc + p.nring * 8;
+    for (int i = tid; i < p.nring * 8; i += SM_T) sdesc[i] = __ldg(p.sring_desc + i);
+    for (int i = tid; i < p.nsteps; i += SM_T) {
+        ssteps[3 * i] = __ldg(p.sstep_kind + i);
+        ssteps[3 * i + 1] = __ldg(p.sstep_a + i);
+        ssteps[3 * i + 2] = __ldg(p.sstep_b + i);
+    }
+    TL_CLK_DECL;
+    for (int i = tid; i < N; i += SM_T) xs[i] = rhs[i];
+    __syncthreads();
+    TL_CLK_ADD(w, 1);
+    // prologue: first RING_D-1 ring steps in flight
+    for (int kk = 0; kk < RING_D - 1; ++kk) ring_issue(p, lu, ring, sdesc, kk, tid);
+    int k = 0;                                               // ring steps consumed so far
+    for (int st = 0; st < p.nsteps; ++st) {
+        const int kind = ssteps[3 * st];
+        const int a = ssteps[3 * st + 1], b = ssteps[3 * st + 2];
+        if (kind == 4) continue;
+        if (kind == 1 || kind == 3) {
+            TL_CLK_ADD(w, 7);
+            cp_async_wait<RING_D - 2>();                     // this step's group has landed (this thread)
+            __syncthreads();                                 // ... for every thread; previous step's x visible
+            TL_CLK_ADD(w, 2);
+            ring_issue(p, lu, ring, sdesc, k + RING_D - 1, tid);   // refill the slot the previous ring step used
+            const char *slot = ring + (size_t)(k % RING_D) * RING_SLOT_BYTES;
+            const double2 *V = (const double2 *)slot;
+            const int *C = (const int *)(slot + RING_BLK * 32);
+            const int *P = C + RING_BLK;
+            const int *R = P + RING_ROWS + 4;
+            const int nrows = b - a;
+            const int p0 = P[0];
+            if (kind == 1) {
+                for (int rr = wp; rr < nrows; rr += SM_NW) {
+                    int ea = P[rr] - p0, eb = P[rr + 1] - p0;
+                    double2 sum = make_double2(0.0, 0.0);
+                    for (int t = ea + lane; t < eb; t += 32) {
+                        double2 r0 = V[2 * t], r1 = V[2 * t + 1];
+                        double2 x = xs[C[t]];
+                        sum.x += r0.x * x.x + r0.y * x.y;
+                        sum.y += r1.x * x.x + r1.y * x.y;
+                    }
+                    sum = warp_sum2(sum);
+                    if (lane == 0) {
+                        double2 cur = xs[a + rr];
+                        xs[a + rr] = make_double2(cur.x - sum.x, cur.y - sum.y);
+                    }
+                }
+            } else {
+                for (int rr = wp; rr < nrows; rr += SM_NW) {
+                    int ua = P[rr] - p0, ub = P[rr + 1] - p0;
+                    int bi = ua + rr;                        // the row's inverted pivot block
+                    double2 sum = make_double2(0.0, 0.0);
+                    for (int t = lane; t < ub - ua; t += 32) {
+                        double2 r0 = V[2 * (bi + 1 + t)], r1 = V[2 * (bi + 1 + t) + 1];
+                        double2 x = xs[C[ua + t]];
+                        sum.x += r0.x * x.x + r0.y * x.y;
+                        sum.y += r1.x * x.x + r1.y * x.y;
+                    }
+                    sum = warp_sum2(sum);
+                    if (lane == 0) {
+                        int r = R[rr];
+                        double2 cur = xs[r];
+                        double ax = cur.x - sum.x, ay = cur.y - sum.y;
+                        double2 d0 = V[2 * bi], d1 = V[2 * bi + 1];
+                        xs[r] = make_double2(d0.x * ax + d0.y * ay, d1.x * ax + d1.y * ay);
+                    }
+                }
+            }
+            ++k;
+            TL_CLK_ADD(w, 3);
+        } else if (kind == 0) {
+            __syncthreads();
+            for (int r = a + tid; r < b; r += SM_T) {
+                int e0 = __ldg(p.lptr + r), e1 = __ldg(p.lptr + r + 1);
+                double2 acc = xs[r];
+                row_accumulate<1>(lu, xs, p.lcol + e0, (size_t)e0, e1 - e0, 0, acc);
+                xs[r] = acc;
+            }
+            TL_CLK_ADD(w, 4);
+        } else {  // kind == 2
+            __syncthreads();
+            for (int q = a + tid; q < b; q += SM_T) {
+                int r = __ldg(p.urow + q);
+                int u0 = __ldg(p.uptr + q), nu = __ldg(p.uptr + q + 1) - u0;
+                size_t base = (size_t)(p.nL + u0 + q);
+                Blk d = ldblk_stream(lu, base);
+                double2 acc = xs[r];
+                row_accumulate<1>(lu, xs, p.ucol + u0, base + 1, nu, 0, acc);
+                xs[r] = make_double2(d.a * acc.x + d.b * acc.y, d.c * acc.x + d.d * acc.y);
+            }
+            TL_CLK_ADD(w, 5);
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    for (int i = tid; i < N; i += SM_T) xb[i] = xs[i];
+    TL_CLK_ADD(w, 6);
 }
 
 // ---- K_init: order-0 germ and RHS of order 1 (helm.py:110-139, 551-556, n == 1 branches) ---
@@ -1004,7 +1316,17 @@ void launch_kernel(int which, const PlanDev &p, const WorkDev &w, cudaStream_t s
             }
             break;
         case KI_INIT: k_init<G><<<gridBus, T_ELEM, 0, st>>>(p, w); break;
-        case KI_SOLVE: k_solve<G, WPB_SOLVE><<<(w.ngroups + WPB_SOLVE - 1) / WPB_SOLVE, WPB_SOLVE * 32, 0, st>>>(p, w); break;
+        case KI_SOLVE:
+            // shared-memory solve for small batches (<= ~3 CTAs per SM of concurrency is enough);
+            // large batches keep more scenarios in flight with the warp-per-scenario kernel
+            if (G == 1 && p.use_smem_solve && w.ngroups <= p.smem_solve_max_groups) {
+                k_solve_smem<<<w.ngroups, SM_T, solve_smem_bytes(p.N, p.nring, p.nsteps), st>>>(p, w);
+            } else if (G == 1) {
+                k_solve_warp<WPB_SOLVE><<<(w.ngroups + WPB_SOLVE - 1) / WPB_SOLVE, WPB_SOLVE * 32, 0, st>>>(p, w);
+            } else {
+                k_solve<G, WPB_SOLVE><<<(w.ngroups + WPB_SOLVE - 1) / WPB_SOLVE, WPB_SOLVE * 32, 0, st>>>(p, w);
+            }
+            break;
         case KI_RHS: k_rhs_conv<G><<<gridBus, T_ELEM, 0, st>>>(p, w); break;
         case KI_ADV: k_advance<<<gridGrp, 128, 0, st>>>(w); break;
         case KI_QLIM: k_qlimit<G><<<gridBus, T_ELEM, 0, st>>>(p, w); break;
@@ -1149,12 +1471,23 @@ int helm_plan_create(const helm_grid_host *g, helm_plan **out) {
     UP(S.slot_src, slot_src) UP(S.slot_row, slot_row)
     UP(S.fptr, fptr) UP(S.fsrc, fsrc) UP(S.fdst, fdst) UP(S.fdst_local, fdstl) UP(S.qof, qof)
     UP(S.fchunk_row, fchunk_row) UP(S.fchunk_lpr, fchunk_lpr) UP(S.frow_off, frow_off)
+    UP(S.sstep_kind, sstep_kind) UP(S.sstep_a, sstep_a) UP(S.sstep_b, sstep_b) UP(S.sring_desc, sring_desc)
+    d.nsteps = (int)S.sstep_kind.size(); d.nring = (int)S.sring_desc.size() / 8;
     d.max_row_blocks = S.max_row_blocks;
     d.nfchunks = (int)S.fchunk_lpr.size(); d.cap_upd = S.cap_upd; d.cap_ent = S.cap_ent; d.cap_rowblk = S.cap_rowblk;
 #undef UP
     {
         size_t smem = WPB_FACTOR * factor_smem_per_warp(pl->d.cap_upd, pl->d.cap_ent, pl->d.cap_rowblk);
         if (smem > 200 * 1024) { g_err = "row too long for the staged factorization buffer"; helm_plan_destroy(pl); return HELM_E_STRUCT; }
+        // shared-memory solve: usable when x (16 B per bus) plus the ring leaves room for >= 2 CTAs per SM
+        size_t ssm = solve_smem_bytes(pl->d.N, pl->d.nring, pl->d.nsteps);
+        static size_t ssm_set = 48 * 1024;
+        pl->d.use_smem_solve = (ssm <= 110 * 1024) && getenv("HELM_B200_NO_SMEM_SOLVE") == nullptr;
+        pl->d.smem_solve_max_groups = getenv("HELM_B200_SMEM_SOLVE_MAX") ? atoi(getenv("HELM_B200_SMEM_SOLVE_MAX")) : 1024;
+        if (pl->d.use_smem_solve && ssm > ssm_set) {
+            CUDA_TRY(cudaFuncSetAttribute(k_solve_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
+            ssm_set = ssm;
+        }
         // the attribute is per function, not per plan: only ever raise it
         static size_t smem_set = 48 * 1024;
         if (smem > smem_set) {
@@ -1249,11 +1582,9 @@ int helm_solve_batch_device(helm_plan *pl, int32_t B, const double *d_scale, con
     local.kernel_launches = 1;
 
     if (!pl->side) {
-        // the factorization branch is short and latency-bound: give it scheduling priority so its
-        // few CTAs are not queued behind the large grids of the main branch
-        int lo = 0, hi = 0;
-        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        CUDA_TRY(cudaStreamCreateWithPriority(&pl->side, cudaStreamNonBlocking, hi));
+        // No stream priority for the side branch: measured (profiles/, timeline r1) that pending
+        // high-priority CTAs that do not fit (shared-memory limit) block the main branch's CTAs.
+        CUDA_TRY(cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking));
     }
     if (!pl->ev_fork) {
         CUDA_TRY(cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming));
@@ -1410,6 +1741,11 @@ int helm_debug_timeline(helm_plan *pl, uint64_t *out, int32_t max_steps) {
     if (!pl || !pl->tl || !out) { g_err = "no timeline"; return HELM_E_ARG; }
     int n = std::min<int>(max_steps, TL_MAXSTEPS);
     CUDA_TRY(cudaMemcpy(out, pl->tl + 8, (size_t)n * 16 * 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    {   // cycle counters tl[1..7] are returned in the (unused) kernel slots 8..14 of step 0
+        unsigned long long c[8];
+        CUDA_TRY(cudaMemcpy(c, pl->tl, sizeof(c), cudaMemcpyDeviceToHost));
+        for (int i = 1; i < 8; ++i) out[(0 * 16 + 7 + i) * 2] = c[i];
+    }
     return HELM_OK;
 #else
     (void)pl; (void)out; (void)max_steps;

@@ -19,6 +19,7 @@
 #include "symbolic.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <queue>
 #include <utility>
 
@@ -117,13 +118,51 @@ bool build_symbolic(int N, const int32_t *adj_ptr, const int32_t *adj_idx, const
             lcount[w]++;
         }
     }
+    // post-order of the elimination tree: rows of one subtree get neighbouring numbers, so the
+    // x-gathers of neighbouring rows (lanes) in the triangular solves touch neighbouring addresses
+    std::vector<int> dfs(N, 0);
+    {
+        std::vector<int> parent(N, -1);
+        std::vector<std::vector<int>> kids(N);
+        std::vector<int> roots;
+        for (int v = 0; v < N; ++v) {
+            int best = -1;
+            for (int w : higher[v])
+                if (best < 0 || pos[w] < pos[best]) best = w;
+            parent[v] = best;
+        }
+        for (int k = 0; k < N; ++k) {            // children in elimination order
+            int v = order[k];
+            if (parent[v] >= 0) kids[parent[v]].push_back(v);
+            else roots.push_back(v);
+        }
+        int counter = 0;
+        std::vector<std::pair<int, size_t>> stack;
+        for (int r : roots) {
+            stack.push_back(std::make_pair(r, (size_t)0));
+            while (!stack.empty()) {
+                int v = stack.back().first;
+                size_t &ci = stack.back().second;
+                if (ci < kids[v].size()) {
+                    int c = kids[v][ci++];
+                    stack.push_back(std::make_pair(c, (size_t)0));
+                } else {
+                    dfs[v] = counter++;
+                    stack.pop_back();
+                }
+            }
+        }
+    }
+    // within a level and bus type: long rows first (balanced lanes) — measured slightly faster in the
+    // solve than pure post-order (HELM_B200_SORT_DFS=1 switches to post-order for A/B runs)
+    const bool sort_len = getenv("HELM_B200_SORT_DFS") == nullptr;
     std::vector<int> byl(N);
     for (int i = 0; i < N; ++i) byl[i] = i;
     std::sort(byl.begin(), byl.end(), [&](int a, int b) {
         if (lev[a] != lev[b]) return lev[a] < lev[b];
         if (bus_type && bus_type[a] != bus_type[b]) return bus_type[a] < bus_type[b];  // homogeneous warps
-        if (lcount[a] != lcount[b]) return lcount[a] > lcount[b];  // long rows first: balanced warps
-        return pos[a] < pos[b];
+        if (sort_len && lcount[a] != lcount[b]) return lcount[a] > lcount[b];
+        return dfs[a] < dfs[b];
     });
     S.perm.assign(N, 0);
     S.iperm.assign(N, 0);
@@ -173,7 +212,7 @@ bool build_symbolic(int N, const int32_t *adj_ptr, const int32_t *adj_idx, const
     for (int i = 0; i < N; ++i) S.urow[i] = i;
     std::sort(S.urow.begin(), S.urow.end(), [&](int a, int b) {
         if (ulev[a] != ulev[b]) return ulev[a] < ulev[b];
-        if (Urow[a].size() != Urow[b].size()) return Urow[a].size() > Urow[b].size();
+        if (sort_len && Urow[a].size() != Urow[b].size()) return Urow[a].size() > Urow[b].size();
         return a < b;
     });
     S.qof.assign(N, 0);
@@ -277,6 +316,38 @@ bool build_symbolic(int N, const int32_t *adj_ptr, const int32_t *adj_idx, const
             }
         }
         S.fchunk_row.push_back(N);
+    }
+
+    // ---- 4b''. solve schedule ----------------------------------------------------------------
+    {
+        for (int l = 0; l < nLlev; ++l) {
+            int r0 = S.llev_ptr[l], r1 = S.llev_ptr[l + 1];
+            int ent = S.lptr[r1] - S.lptr[r0];
+            int kind = 0;
+            if (ent == 0) kind = 4;
+            else if (ent <= Symbolic::RING_BLOCKS && r1 - r0 <= Symbolic::RING_ROWS) kind = 1;
+            S.sstep_kind.push_back(kind);
+            S.sstep_a.push_back(r0);
+            S.sstep_b.push_back(r1);
+            if (kind == 1) {
+                int d[8] = {1, r0, r1 - r0, S.lptr[r0], ent, S.lptr[r0], ent, 0};
+                S.sring_desc.insert(S.sring_desc.end(), d, d + 8);
+            }
+        }
+        for (int l = 0; l < nUlev; ++l) {
+            int q0 = S.ulev_ptr[l], q1 = S.ulev_ptr[l + 1];
+            int ncol = S.uptr[q1] - S.uptr[q0];
+            int nblk = ncol + (q1 - q0);
+            int kind = 2;
+            if (nblk <= Symbolic::RING_BLOCKS && q1 - q0 <= Symbolic::RING_ROWS) kind = 3;
+            S.sstep_kind.push_back(kind);
+            S.sstep_a.push_back(q0);
+            S.sstep_b.push_back(q1);
+            if (kind == 3) {
+                int d[8] = {3, q0, q1 - q0, S.nL + S.uptr[q0] + q0, nblk, S.uptr[q0], ncol, 0};
+                S.sring_desc.insert(S.sring_desc.end(), d, d + 8);
+            }
+        }
     }
 
     // ---- 4c. adjacency in the new numbering + assembly map -------------------------

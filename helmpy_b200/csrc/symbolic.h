@@ -38,6 +38,17 @@ struct Symbolic {
     // assembly map: slot -> adjacency entry (or -1 for fill), slot -> row
     std::vector<int> slot_src, slot_row;
 
+    // triangular-solve schedule for the shared-memory solve kernel: steps in execution order
+    // (forward levels, then backward levels).  kind: 0 = forward level, rows from global memory;
+    // 1 = forward level prefetched through the shared-memory ring; 2 / 3 = same for backward
+    // levels; 4 = nothing to do.  a, b = row range [a, b) (forward) or position range (backward).
+    std::vector<int> sstep_kind, sstep_a, sstep_b;
+    // ring descriptors, 8 ints per ring step in execution order:
+    // {kind, row0, nrows, slot0, nblk, col0, ncol, 0}
+    std::vector<int> sring_desc;
+    static constexpr int RING_BLOCKS = 128;      // 2x2 blocks per ring slot
+    static constexpr int RING_ROWS = 32;         // rows per ring slot
+
     inline int slotD(int q) const { return nL + uptr[q] + q; }
     inline int slotU(int q, int t) const { return nL + uptr[q] + q + 1 + t; }
 };

@@ -20,6 +20,7 @@ n = 400
 buf = np.zeros((n, 16, 2), dtype=np.uint64)
 _lib.check(_lib.load().helm_debug_timeline(plan.handle, buf.ctypes.data_as(C.c_void_p), n), 'timeline')
 names = _lib.KERNEL_NAMES
+print('solve cycle counters (thread 0 of every CTA, summed): load_rhs, ring_wait+barrier, ring_compute, wideL, wideU, store_x, between', [int(buf[0, 7 + i, 0]) for i in range(1, 8)])
 for s in steps:
     row = buf[s]
     valid = row[:, 1] > 0
