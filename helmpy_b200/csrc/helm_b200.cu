@@ -888,23 +888,34 @@ __device__ __forceinline__ void eps_step(EpsState &st, int t, int j, double2 v, 
 template <int G>
 __global__ void __launch_bounds__(256) k_rhs_conv(PlanDev p, WorkDev w) {
     TL_SCOPE(w, 3);
-    int grp = blockIdx.y;
-    int gf = w.g_flags[grp];
-    if (gf & (GF_DONE | GF_PASSEND | GF_FACTORING)) return;
-    int flat = blockIdx.x * blockDim.x + threadIdx.x;
-    int i = flat / G, s = flat % G;
+    const int grp = blockIdx.y;
+    const int flat = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = flat / G, s = flat % G;
     if (i >= p.N) return;
-    int sg = grp * G + s;
-    if (w.s_status[sg] != ST_ACTIVE) return;
     const int N = p.N;
-    const int j = w.g_n[grp] + 1;  // order just solved
+    const int sg = grp * G + s;
     const size_t plane = (size_t)N * G;
     const size_t bi = ix<G>(grp, N, i, s);
     const size_t h0 = hx<G>(w, N, grp, 0, i, s);
     double2 *Vb = w.Vh + h0, *Hb = w.Hh + h0, *Eb = w.Eh + h0;
     const double2 *xb = w.xb + (size_t)grp * N * G;
+    // Every operand of the prologue is loaded before the first branch: the addresses are valid for
+    // any (bus, scenario), and issuing them together costs one memory round trip instead of six
+    // dependent ones (ncu r1_c: the early-exit chain was the top stall at small orders).
+    const int gf = w.g_flags[grp];
+    const int status = w.s_status[sg];
+    const int j = w.g_n[grp] + 1;  // order just solved
     const unsigned char bt = w.btype[bi];
     const double2 v = xb[(size_t)i * G + s];
+    const double2 e_prev0 = Eb[0];
+    const double sc = w.scale[sg];
+    const double qg = w.Qg[bi];
+    const double pgi = p.pg[i], pdi = p.pd[i], qdi = p.qd[i];
+    const double2 ysh = p.yshunt[i];
+    const int ph0 = p.ph_ptr[i], ph1 = p.ph_ptr[i + 1];
+    const int a0 = p.adj_ptr[i], a1 = p.adj_ptr[i + 1];
+    if (gf & (GF_DONE | GF_PASSEND | GF_FACTORING)) return;
+    if (status != ST_ACTIVE) return;
     Vb[(size_t)j * plane] = v;                                                    // helm.py:412-414
     if (bt == HELM_BUS_SLACK) {
         w.rhs[bi] = make_double2(0.0, 0.0);                                       // helm.py:395-397
@@ -912,7 +923,7 @@ __global__ void __launch_bounds__(256) k_rhs_conv(PlanDev p, WorkDev w) {
     }
     const double2 zero = make_double2(0.0, 0.0);
     EpsState es;
-    es.prev1 = Eb[0];                                      // eps_0^(j-1) = S_{j-1}
+    es.prev1 = e_prev0;                                    // eps_0^(j-1) = S_{j-1}
     es.prev2 = zero;                                       // eps_{-1} = 0
     es.cur = cadd(es.prev1, v);                            // S_j
     Eb[0] = es.cur;
@@ -942,19 +953,18 @@ __global__ void __launch_bounds__(256) k_rhs_conv(PlanDev p, WorkDev w) {
         double2 wj = make_double2(-aux.x, -aux.y);
         Hb[(size_t)j * plane] = wj;                                               // W[j]
         // RHS of order j+1 (helm.py:367-385)
-        double sc = w.scale[sg];
-        double Pi = p.pg[i] * sc - p.pd[i] * sc;
-        double Qi = w.Qg[bi] - p.qd[i] * sc;
+        double Pi = pgi * sc - pdi * sc;
+        double Qi = qg - qdi * sc;
         double2 pp = zero;
-        for (int a = p.ph_ptr[i]; a < p.ph_ptr[i + 1]; ++a)
+        for (int a = ph0; a < ph1; ++a)
             pp = cadd(pp, cmul(p.ph_val[a], xb[(size_t)p.ph_idx[a] * G + s]));
         double2 tt = cmul(make_double2(Pi, -Qi), make_double2(wj.x, -wj.y));
-        double2 ysv = cmul(p.yshunt[i], v);
+        double2 ysv = cmul(ysh, v);
         out = make_double2(tt.x - ysv.x - pp.x, tt.y - ysv.y - pp.y);
     } else {
         // PV bus, model 2 (helm.py:293-364); n = j+1 >= 2
         double2 PP = zero;
-        for (int a = p.adj_ptr[i]; a < p.adj_ptr[i + 1]; ++a)
+        for (int a = a0; a < a1; ++a)
             PP = cadd(PP, cmul(p.ytr[a], xb[(size_t)p.adj_idx[a] * G + s]));      // helm.py:310-312
         Hb[(size_t)j * plane] = PP;                                               // barras_CC[i][n-1]
         double2 ppp = zero;
@@ -982,16 +992,15 @@ __global__ void __launch_bounds__(256) k_rhs_conv(PlanDev p, WorkDev w) {
             }
         }
         double cc_ = 0.0 - ppp.x;
-        double2 ysh = p.yshunt[i];
         if (ysh.x != 0.0) {                                                      // conduc_buses
             if (j >= 2) cc_ -= ysh.x * (w.VVant[bi] + 2.0 * v.x);                // helm.py:317-318
             else cc_ -= ysh.x * 2.0 * v.x;                                       // helm.py:336-337
         }
-        if (p.ph_ptr[i + 1] > p.ph_ptr[i]) {                                     // helm.py:320-327
+        if (ph1 > ph0) {                                                         // helm.py:320-327
             double2 acc = zero;
             for (int x = 0; x <= j; ++x) {
                 double2 pp = zero;
-                for (int a = p.ph_ptr[i]; a < p.ph_ptr[i + 1]; ++a) {
+                for (int a = ph0; a < ph1; ++a) {
                     int k = p.ph_idx[a];
                     double2 vk = (x == 0) ? xb[(size_t)k * G + s] : w.Vh[hx<G>(w, N, grp, j - x, k, s)];
                     pp = cadd(pp, cmul(p.ph_val[a], vk));

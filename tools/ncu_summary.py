@@ -24,7 +24,7 @@ for wn in want:
     idx = [i for i, h in enumerate(hdr) if h == wn]
     if idx:
         print('%-85s %s' % (wn, [r[idx[0]] for r in rows[1:]]))
-src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'cuda,sass'], capture_output=True, text=True).stdout
+src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 h = None
 data = []
@@ -34,7 +34,7 @@ for r in rows:
             break
         h = r
         continue
-    if h is not None and len(r) >= len(h) - 2:
+    if h is not None and len(r) >= 8 and r[0].startswith('0x'):
         data.append(r)
 if h:
     isamp = h.index('# Samples'); isrc = h.index('Source'); iex = h.index('Instructions Executed')
