@@ -60,7 +60,7 @@ struct PlanDev {
     const int *fptr, *fsrc, *fdst, *fdstl, *qof;
     const int *fchunk_row, *fchunk_lpr, *frow_off;
     const int *sstep_kind, *sstep_a, *sstep_b, *sring_desc;
-    int nsteps, nring, use_smem_solve, smem_solve_max_groups;
+    int nsteps, nring, use_smem_solve, smem_solve_max_groups, use_coop_factor;
     int max_row_blocks, nfchunks, cap_upd, cap_ent, cap_rowblk;
 };
 
@@ -1317,7 +1317,7 @@ void launch_kernel(int which, const PlanDev &p, const WorkDev &w, cudaStream_t s
         case KI_ASM: k_assemble<G><<<w.ngroups, 256, 0, st>>>(p, w); break;
         case KI_BEGIN: k_step_begin<<<gridGrp, 128, 0, st>>>(w); break;
         case KI_FACTOR:
-            if (G == 1) {
+            if (G == 1 && p.use_coop_factor) {
                 size_t smem = WPB_FACTOR * factor_smem_per_warp(p.cap_upd, p.cap_ent, p.cap_rowblk);
                 k_factor_coop<WPB_FACTOR><<<(w.ngroups + WPB_FACTOR - 1) / WPB_FACTOR, WPB_FACTOR * 32, smem, st>>>(p, w);
             } else {
@@ -1487,7 +1487,10 @@ int helm_plan_create(const helm_grid_host *g, helm_plan **out) {
 #undef UP
     {
         size_t smem = WPB_FACTOR * factor_smem_per_warp(pl->d.cap_upd, pl->d.cap_ent, pl->d.cap_rowblk);
-        if (smem > 200 * 1024) { g_err = "row too long for the staged factorization buffer"; helm_plan_destroy(pl); return HELM_E_STRUCT; }
+        // staged factorization needs its chunk operands in shared memory; grids whose longest row
+        // does not fit fall back to the unstaged warp-per-group kernel
+        pl->d.use_coop_factor = (smem <= 200 * 1024) && getenv("HELM_B200_NO_COOP_FACTOR") == nullptr;
+        if (!pl->d.use_coop_factor) smem = 0;
         // shared-memory solve: usable when x (16 B per bus) plus the ring leaves room for >= 2 CTAs per SM
         size_t ssm = solve_smem_bytes(pl->d.N, pl->d.nring, pl->d.nsteps);
         static size_t ssm_set = 48 * 1024;
