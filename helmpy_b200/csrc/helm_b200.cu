@@ -516,7 +516,7 @@ __global__ void __launch_bounds__(WPB * 32) k_solve(PlanDev p, WorkDev w) {
 // split the row's entries and combine with shuffles, instead of leaving 31 lanes idle while one
 // lane walks a 57-entry row.  Cuts the executed warp instructions per solve ~4x (ncu, profiles/).
 template <int WPB>
-__global__ void __launch_bounds__(WPB * 32) k_solve_warp(PlanDev p, WorkDev w) {
+__global__ void __launch_bounds__(WPB * 32, 8) k_solve_warp(PlanDev p, WorkDev w) {
     TL_SCOPE(w, 2);
     int grp = blockIdx.x * WPB + (threadIdx.x >> 5);
     if (grp >= w.ngroups) return;
