@@ -266,6 +266,18 @@ __device__ __forceinline__ void stsm(double2 *b, int i, Blk m) {
     b[2 * i + 1] = make_double2(m.c, m.d);
 }
 
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int NPEND>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NPEND) : "memory"); }
+
 constexpr int WPB_FACTOR = 2;   // warps (= scenarios) per CTA of the staged factorization
 
 // Shared-memory plan of one warp:
@@ -317,19 +329,29 @@ __global__ void __launch_bounds__(WPB * 32) k_factor_coop(PlanDev p, WorkDev w) 
         }
         const int e_base = __ldg(p.lptr + r0), e_end = __ldg(p.lptr + r1);
         const int u_base = __ldg(p.fptr + e_base), u_end = __ldg(p.fptr + e_end);
-        // ---- phase 1: stage
-        for (int u = u_base + lane; u < u_end; u += 32) {
-            size_t src = (size_t)__ldg(p.fsrc + u);
-            sSrc[2 * (u - u_base)] = lu[src * 2];
-            sSrc[2 * (u - u_base) + 1] = lu[src * 2 + 1];
-            sDl[u - u_base] = __ldg(p.fdstl + u);
+        // ---- phase 1: stage with cp.async (LDGSTS): every copy of the chunk is in flight at once
+        for (int u = u_base + lane; u < u_end; u += 128) {
+            int uu[4];
+            size_t src[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uu[k] = u + 32 * k;
+                src[k] = (uu[k] < u_end) ? (size_t)__ldg(p.fsrc + uu[k]) : 0;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (uu[k] < u_end) {
+                    cp_async16(sSrc + 2 * (uu[k] - u_base), lu + src[k] * 2);
+                    cp_async16(sSrc + 2 * (uu[k] - u_base) + 1, lu + src[k] * 2 + 1);
+                    cp_async4(sDl + (uu[k] - u_base), p.fdstl + uu[k]);
+                }
         }
         for (int e = e_base + lane; e <= e_end; e += 32) {
             sUp[e - e_base] = __ldg(p.fptr + e) - u_base;
             if (e < e_end) {
                 size_t dk = (size_t)__ldg(p.dslot + __ldg(p.lcol + e));
-                sDk[2 * (e - e_base)] = lu[dk * 2];
-                sDk[2 * (e - e_base) + 1] = lu[dk * 2 + 1];
+                cp_async16(sDk + 2 * (e - e_base), lu + dk * 2);
+                cp_async16(sDk + 2 * (e - e_base) + 1, lu + dk * 2 + 1);
             }
         }
         const int rs = lane / lpr, sl = lane % lpr;
@@ -346,10 +368,12 @@ __global__ void __launch_bounds__(WPB * 32) k_factor_coop(PlanDev p, WorkDev w) 
             buf = sRow + (size_t)__ldg(p.frow_off + r) * 2;
             for (int b = sl; b < rowlen; b += lpr) {
                 size_t slot = (b < nl) ? (size_t)(e0 + b) : (size_t)(dbase + (b - nl));
-                buf[2 * b] = lu[slot * 2];
-                buf[2 * b + 1] = lu[slot * 2 + 1];
+                cp_async16(buf + 2 * b, lu + slot * 2);
+                cp_async16(buf + 2 * b + 1, lu + slot * 2 + 1);
             }
         }
+        cp_async_commit();
+        cp_async_wait<0>();
         __syncwarp();
         // ---- phase 2: eliminate from shared memory
         if (have) {
@@ -656,18 +680,6 @@ __host__ __device__ inline size_t solve_smem_bytes(int N, int nring, int nsteps)
     return (size_t)N * sizeof(double2) + (size_t)RING_D * RING_SLOT_BYTES +
            (size_t)((nring * 8 + nsteps * 3 + 3) / 4 * 4) * sizeof(int);
 }
-
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
-    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc) {
-    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int NPEND>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NPEND) : "memory"); }
 
 // issue the copies of ring step kk (descriptor in shared memory) into its slot; every thread
 // commits one group

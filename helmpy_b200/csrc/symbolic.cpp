@@ -280,7 +280,9 @@ bool build_symbolic(int N, const int32_t *adj_ptr, const int32_t *adj_idx, const
 
     // ---- 4b'. factorization chunks -----------------------------------------------------------
     {
-        const int CAPU_LIMIT = 640;   // staged 2x2 source blocks per chunk (20 KB)
+        // staged 2x2 source blocks per chunk and rows per chunk (tunable for A/B runs)
+        const int CAPU_LIMIT = getenv("HELM_B200_CAPU") ? atoi(getenv("HELM_B200_CAPU")) : 512;
+        const int ROWS_LIMIT = getenv("HELM_B200_CHUNK_ROWS") ? atoi(getenv("HELM_B200_CHUNK_ROWS")) : 32;
         S.frow_off.assign(N, 0);
         S.fchunk_row.clear();
         S.fchunk_lpr.clear();
@@ -296,7 +298,7 @@ bool build_symbolic(int N, const int32_t *adj_ptr, const int32_t *adj_idx, const
             int r = r0;
             while (r < r1) {
                 int start = r, upd = 0, ent = 0, blk = 0;
-                while (r < r1 && r - start < 32) {
+                while (r < r1 && r - start < ROWS_LIMIT) {
                     int u = S.fptr[S.lptr[r + 1]] - S.fptr[S.lptr[r]];
                     if (r > start && upd + u > CAPU_LIMIT) break;
                     int q = S.qof[r];
