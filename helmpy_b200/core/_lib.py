@@ -58,7 +58,7 @@ KERNEL_NAMES = ("assemble", "factor", "solve", "rhs_conv", "advance", "qlimit", 
 EXPORTED_SYMBOLS = (
     "helm_last_error", "helm_plan_create", "helm_plan_destroy", "helm_plan_get_info",
     "helm_plan_get_perm", "helm_workspace_bytes", "helm_solve_batch_device",
-    "helm_solve_batch_host", "helm_debug_factor_solve", "helm_debug_timeline", "helm_measure_peaks",
+    "helm_solve_batch_host", "helm_last_state_host", "helm_debug_factor_solve", "helm_debug_timeline", "helm_measure_peaks",
     "helm_symbolic_create", "helm_symbolic_destroy", "helm_symbolic_array",
 )
 
@@ -94,6 +94,7 @@ def load():
     lib.helm_solve_batch_host.argtypes = [
         C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p,
         C.c_void_p, C.c_void_p, C.POINTER(Stats)]
+    lib.helm_last_state_host.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     lib.helm_debug_factor_solve.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                             C.c_void_p, C.c_void_p]
     lib.helm_debug_timeline.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
@@ -236,6 +237,13 @@ class Plan:
             d_vout.data_ptr(), d_status.data_ptr(), d_ncoef.data_ptr(), d_nswitch.data_ptr(),
             stream_ptr, C.byref(stats)), "helm_solve_batch_device")
         return stats_dict(stats)
+
+    def last_state(self, n_scen):
+        """(Qg [B, N], bus types [B, N]) at the end of the last ``solve_host`` of n_scen scenarios."""
+        qg = np.zeros((n_scen, self.N), dtype=np.float64)
+        bt = np.zeros((n_scen, self.N), dtype=np.uint8)
+        check(load().helm_last_state_host(self.handle, n_scen, _ptr(qg), _ptr(bt)), "helm_last_state_host")
+        return qg, bt
 
     def debug_factor_solve(self, bus_types, rhs, group=1):
         bus_types = np.ascontiguousarray(bus_types, dtype=np.uint8)

@@ -131,7 +131,8 @@ def helm(case, detailed_run_print=False, mismatch=1e-4, scale=1, max_coefficient
     V = res.V[0].copy()
     if detailed_run_print or save_results:
         from . import reporting
-        reporting.report(case, V, scale=scale, mismatch=mismatch, list_coef=coefs,
+        Qg, bus_types = get_plan(case).last_state(1)
+        reporting.report(case, V, Qg[0], bus_types[0], scale=scale, mismatch=mismatch, list_coef=coefs,
                          algorithm='HELM PV2', enforce_Q_limits=enforce_Q_limits,
                          detailed_run_print=detailed_run_print, save_results=save_results,
                          results_file_name=results_file_name)

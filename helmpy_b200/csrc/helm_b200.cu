@@ -1232,6 +1232,7 @@ struct helm_plan {
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     unsigned long long *tl = nullptr;
+    int last_B = 0, last_G = 0, last_maxcoef = 0;   // layout of the last host-buffer solve
 };
 
 namespace {
@@ -1698,11 +1699,35 @@ int helm_solve_batch_host(helm_plan *pl, int32_t B, const double *h_scale, const
     rc = helm_solve_batch_device(pl, B, pl->d_scale, prm, pl->ws, pl->ws_bytes, pl->d_vout, pl->d_status,
                                  pl->d_ncoef, pl->d_nswitch, st, stats);
     if (rc) return rc;
+    pl->last_B = B; pl->last_G = L.G; pl->last_maxcoef = prm->max_coefficients;
     CUDA_TRY(cudaMemcpyAsync(h_vout, pl->d_vout, sizeof(double) * 2 * N * B, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(h_status, pl->d_status, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
     if (h_ncoef) CUDA_TRY(cudaMemcpyAsync(h_ncoef, pl->d_ncoef, sizeof(int) * B * HELM_MAX_PASSES, cudaMemcpyDeviceToHost, st));
     if (h_nswitch) CUDA_TRY(cudaMemcpyAsync(h_nswitch, pl->d_nswitch, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    return HELM_OK;
+}
+
+int helm_last_state_host(helm_plan *pl, int32_t B, double *h_qg, uint8_t *h_bus_type) {
+    if (!pl || B <= 0 || B != pl->last_B || !pl->ws) { g_err = "no matching host solve to read state from"; return HELM_E_ARG; }
+    helm_params prm;
+    memset(&prm, 0, sizeof(prm));
+    prm.mismatch = 1.0; prm.max_coefficients = pl->last_maxcoef; prm.group = pl->last_G;
+    WsLayout L = layout(pl, B, &prm);
+    const size_t N = pl->S.N, per = (size_t)L.Bp * N;
+    std::vector<double> qg(per);
+    std::vector<unsigned char> bt(per);
+    CUDA_TRY(cudaMemcpy(qg.data(), (char *)pl->ws + L.off_Qg, per * sizeof(double), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(bt.data(), (char *)pl->ws + L.off_btype, per, cudaMemcpyDeviceToHost));
+    for (int b = 0; b < B; ++b) {
+        int grp = b / L.G, s = b % L.G;
+        for (size_t r = 0; r < N; ++r) {
+            int o = pl->S.perm[r];
+            size_t bi = ((size_t)grp * N + r) * L.G + s;
+            if (h_qg) h_qg[(size_t)b * N + o] = qg[bi];
+            if (h_bus_type) h_bus_type[(size_t)b * N + o] = bt[bi];
+        }
+    }
     return HELM_OK;
 }
 

@@ -140,6 +140,12 @@ int helm_solve_batch_host(helm_plan *plan, int32_t n_scen, const double *h_scale
                           const helm_params *params, double *h_vout, int32_t *h_status,
                           int32_t *h_ncoef, int32_t *h_nswitch, helm_stats *stats);
 
+/* Per-bus state at the end of the last helm_solve_batch_host call with the same n_scen
+ * (reference run.Qg and run.Buses_type, classes.py:239, 252; needed by the result report,
+ * helm.py:670-759).  h_qg [n_scen*n_bus] p.u., h_bus_type [n_scen*n_bus] HELM_BUS_*;
+ * original bus order; either pointer may be NULL. */
+int helm_last_state_host(helm_plan *plan, int32_t n_scen, double *h_qg, uint8_t *h_bus_type);
+
 /* Debug/testing hooks: run one kernel stage in isolation on device buffers.
  * Used by the parity tests to compare individual stages with the oracle. */
 int helm_debug_factor_solve(helm_plan *plan, int32_t n_scen, int32_t group,

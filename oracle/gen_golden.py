@@ -28,6 +28,9 @@ from oracle import ref_shim  # noqa: E402
 from helmpy_b200.core import xlsx  # noqa: E402
 
 CASES = ['case9', 'case118', 'case1354pegase', 'case2869pegase']
+BRANCH_HEADERS = ['From Bus', 'To Bus', 'From-To P injection (MW)', 'From-To Q injection (MVAR)',
+                  'To-From P injection (MW)', 'To-From Q injection (MVAR)',
+                  'P flow through branch and elements (MW)', 'Q flow through branch and elements (MVAR)']
 SCALES = {
     'case9': [1, 0.8, 0.9, 1.05, 1.2, 1.5],
     'case118': [1, 0.8, 0.95, 1.05, 1.2, 1.5],
@@ -51,11 +54,15 @@ def main():
             cols = xlsx.read_table_with_header(os.path.join(ref, 'data', 'results', fname), 'Buses')
             res[key + '_mag'] = np.array(cols['Voltages Magnitude'], dtype=float)
             res[key + '_ang_deg'] = np.array(cols['Voltages Phase Angle'], dtype=float)
+            br = xlsx.read_table_with_header(os.path.join(ref, 'data', 'results', fname), 'Branches')
+            res[key + '_branches'] = np.array([br[h] for h in BRANCH_HEADERS], dtype=float).T
         mp = xlsx.read_numeric_sheet(os.path.join(ref, 'data', 'results', 'Results MATPOWER %s.xlsx' % name), 'Buses')
         res['matpower_mag'] = mp[:, 7]
         res['matpower_ang_deg'] = mp[:, 8]
         np.savez_compressed(os.path.join(out, 'results_%s.npz' % name), **res)
 
+        if os.environ.get('GOLDEN_RESULTS_ONLY'):
+            continue
         case = ref_shim.ref_case(path)
         d = {'scales': np.array(SCALES[name], dtype=float)}
         for k, s in enumerate(SCALES[name]):
@@ -71,6 +78,15 @@ def main():
                 d['last_pass_W'] = run.W[:, :m].copy()
             print(name, s, 'conv' if V is not None else 'None', info['list_coef'], len(info['switched']))
         np.savez_compressed(os.path.join(out, 'ref_%s.npz' % name), **d)
+        if case.N < 200:      # the reference's own report text (helm.py:762-807), scale 1 and 1.05
+            h = ref_shim.load_reference()
+            import contextlib, io
+            for sc in (1, 1.05):
+                buf = io.StringIO()
+                with contextlib.redirect_stdout(buf):
+                    h.helm(case, detailed_run_print=True, mismatch=1e-8, scale=sc, max_coefficients=40)
+                with open(os.path.join(out, 'ref_stdout_%s_%s.txt' % (name, sc)), 'w') as f:
+                    f.write(buf.getvalue())
 
 
 if __name__ == '__main__':

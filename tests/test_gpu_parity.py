@@ -194,3 +194,54 @@ def test_unstaged_kernels_agree(hb, monkeypatch):
     assert a[2] == b[2]
     assert np.max(np.abs(np.array(a[0]) - np.array(b[0]))) < 1e-11
     assert np.max(np.abs(np.array(a[1]) - np.array(b[1]))) < 1e-11
+
+
+def _numbers(text):
+    import re
+    return [float(x) for x in re.findall(r'[-+]?\d+\.\d+(?:[eE][-+]?\d+)?', text.replace('+   ', '+').replace('-   ', '-'))]
+
+
+@pytest.mark.parametrize('name,scale', [('case9', 1), ('case9', 1.05), ('case118', 1), ('case118', 1.05)])
+def test_detailed_print_matches_reference_stdout(hb, name, scale, capsys):
+    """helm(detailed_run_print=True): same report text as the unmodified reference
+    (tests/golden/ref_stdout_*.txt), numbers to 1e-7 (MVA, degrees)."""
+    import os
+    from common import GOLDEN
+    case = load_case(name)
+    hb.helm(case, detailed_run_print=True, mismatch=1e-8, scale=scale, max_coefficients=40)
+    out = capsys.readouterr().out
+    ref = open(os.path.join(GOLDEN, 'ref_stdout_%s_%s.txt' % (name, scale))).read()
+    ours = out[out.index('\tVoltage profile:'):]
+    theirs = ref[ref.index('\tVoltage profile:'):]
+    strip = lambda t: [' '.join(l.split()) for l in t.strip().splitlines()]
+    lo, lt = strip(ours), strip(theirs)
+    assert len(lo) == len(lt)
+    import re
+    for a, b in zip(lo, lt):
+        assert re.sub(r'[-+]?\d+\.\d+', '#', a) == re.sub(r'[-+]?\d+\.\d+', '#', b)
+        na, nb = _numbers(a), _numbers(b)
+        assert len(na) == len(nb)
+        for x, y in zip(na, nb):
+            assert abs(x - y) <= 1e-7 + 1e-9 * abs(y), (a, b)
+    assert 'Convergence has been reached.' in out
+
+
+def test_save_results_files(hb, tmp_path, monkeypatch):
+    """save_results=True writes 'Results HELM PV2 <name> <scale> <mismatch>.xlsx/.txt' with the
+    reference's sheet layout (helm.py:810-850); contents match the golden result file."""
+    from helmpy_b200.core import xlsx
+    monkeypatch.chdir(tmp_path)
+    case = load_case('case118')
+    V = hb.helm(case, mismatch=1e-8, max_coefficients=40, save_results=True)
+    base = 'Results HELM PV2 case118 1 1e-08'
+    assert (tmp_path / (base + '.xlsx')).exists() and (tmp_path / (base + '.txt')).exists()
+    assert xlsx.sheet_names(str(tmp_path / (base + '.xlsx'))) == ['Buses', 'Branches']
+    cols = xlsx.read_table_with_header(str(tmp_path / (base + '.xlsx')), 'Buses')
+    g = golden_results('case118')
+    assert np.max(np.abs(np.array(cols['Voltages Magnitude']) - g['classic_mag'])) <= 1e-8
+    assert np.max(np.abs(np.array(cols['Voltages Phase Angle']) - g['classic_ang_deg'])) <= 1e-6
+    assert complex(cols['Complex Voltages'][3]) == V[3]
+    br = xlsx.read_table_with_header(str(tmp_path / (base + '.xlsx')), 'Branches')
+    assert np.max(np.abs(np.array(br['From-To P injection (MW)']) - g['classic_branches'][:, 2])) <= 1e-5
+    txt = open(tmp_path / (base + '.txt')).read()
+    assert txt.startswith('Scale: 1   Mismatch: 1e-08   Coefficients per PVLIM-PQ switches: [15, 15]')

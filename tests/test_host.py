@@ -139,3 +139,19 @@ def test_factor_schedule_local_indices(name):
                 slot = e0 + dl if dl < nl else base + (dl - nl)
                 assert slot == S['fdst'][u]
                 assert S['fsrc'][u] >= nL          # sources are U blocks of an earlier row
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_branch_flows_match_golden_results(name):
+    """reporting.branch_flows on the golden voltages reproduces the 'Branches'
+    sheet of the reference's result files (helm.py:685-712)."""
+    from common import golden_results
+    from helmpy_b200.core import reporting
+    case = load_case(name)
+    g = golden_results(name)
+    V = g['classic_mag'] * np.exp(1j * np.deg2rad(g['classic_ang_deg']))
+    P = reporting.branch_flows(case, V)
+    ref = g['classic_branches']
+    assert P.shape == ref.shape
+    assert np.array_equal(P[:, :2], ref[:, :2])
+    assert np.max(np.abs(P[:, 2:] - ref[:, 2:])) < 1e-6      # MW / MVAr
