@@ -245,3 +245,21 @@ def test_save_results_files(hb, tmp_path, monkeypatch):
     assert np.max(np.abs(np.array(br['From-To P injection (MW)']) - g['classic_branches'][:, 2])) <= 1e-5
     txt = open(tmp_path / (base + '.txt')).read()
     assert txt.startswith('Scale: 1   Mismatch: 1e-08   Coefficients per PVLIM-PQ switches: [15, 15]')
+
+
+def test_helm_vs_nr_cross_check_large_grid(hb):
+    """BASELINE config 4 shape: Q-limit switching on a ~10k-bus grid, HELM (GPU) against the
+    Newton-Raphson cross-check on sampled scenarios (tolerance 1e-6 p.u. / 1e-5 rad: NR stops on
+    a 1e-8 power mismatch)."""
+    import contextlib, io
+    import synth
+    from helmpy_b200.core.nr import nr
+    case = synth.tiled_case(['case2869pegase'] * 3 + ['case1354pegase'])
+    scales = [0.92, 1.0]
+    res = hb.helm_batch(case, scales, mismatch=1e-8, max_coefficients=60)
+    for b, s in enumerate(scales):
+        with contextlib.redirect_stdout(io.StringIO()):
+            Vn = nr(case, Mismatch=1e-8, Scale=float(s))
+        assert res.converged[b] and Vn is not None
+        dmag, dang = polar_err(res.V[b], Vn)
+        assert dmag <= 1e-6 and dang <= 1e-5, (dmag, dang)
