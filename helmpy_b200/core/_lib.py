@@ -36,7 +36,7 @@ class Params(C.Structure):
     _fields_ = [
         ("mismatch", C.c_double), ("max_coefficients", C.c_int32),
         ("enforce_q_limits", C.c_int32), ("group", C.c_int32),
-        ("use_graph", C.c_int32), ("poll_every", C.c_int32),
+        ("use_graph", C.c_int32), ("poll_every", C.c_int32), ("max_resident", C.c_int32),
     ]
 
 
@@ -198,7 +198,7 @@ class Plan:
 
     @staticmethod
     def make_params(mismatch, max_coefficients, enforce_q_limits, group=0, use_graph=True,
-                    poll_every=0):
+                    poll_every=0, max_resident=0):
         p = Params()
         p.mismatch = float(mismatch)
         p.max_coefficients = int(max_coefficients)
@@ -206,6 +206,7 @@ class Plan:
         p.group = int(group)
         p.use_graph = int(bool(use_graph))
         p.poll_every = int(poll_every)
+        p.max_resident = int(max_resident)
         return p
 
     def workspace_bytes(self, n_scen, params):

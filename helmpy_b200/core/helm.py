@@ -86,16 +86,18 @@ class BatchResult:
 
 
 def helm_batch(case, scales, mismatch=1e-4, max_coefficients=100, enforce_Q_limits=True,
-               group=0, use_graph=True, poll_every=0):
+               group=0, use_graph=True, poll_every=0, max_resident=0):
     """Solve ``len(scales)`` load-scaling scenarios of ``case`` on the current GPU.
 
     Scenario b equals ``helm(case, scale=scales[b], mismatch=..., ...)``
     (set_scale semantics of reference classes.py:215-219).  ``case`` is not
-    mutated.  Host buffers in, host buffers out.
+    mutated.  Host buffers in, host buffers out.  At most ``max_resident`` scenarios
+    (default 4096) hold GPU state at a time; the rest of the batch queues and takes
+    over slots as scenarios finish, so device memory does not grow with the batch.
     """
     plan = get_plan(case)
     prm = _lib.Plan.make_params(mismatch, max_coefficients, enforce_Q_limits, group, use_graph,
-                                poll_every)
+                                poll_every, max_resident)
     V, status, ncoef, nswitch, stats = plan.solve_host(np.asarray(scales, dtype=np.float64), prm)
     return BatchResult(V, status, ncoef, nswitch, stats)
 

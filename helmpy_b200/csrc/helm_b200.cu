@@ -42,7 +42,8 @@ enum : int { ST_ACTIVE = 0, ST_FROZEN = 1, ST_CONVERGED = 2, ST_DIVERGED = 3, ST
 // group flags
 // PENDING: the group needs a (re)factorization; FACTORING: it is being factorized in the
 // side branch of the current step and sits this order out (see the step graph below).
-enum : int { GF_PENDING = 1, GF_PASSEND = 2, GF_DONE = 4, GF_FACTORING = 8 };
+// NEWSCEN: the group's slots were just refilled with fresh scenarios from the queue.
+enum : int { GF_PENDING = 1, GF_PASSEND = 2, GF_DONE = 4, GF_FACTORING = 8, GF_NEWSCEN = 16 };
 
 // ---- device-side views ------------------------------------------------------------
 struct PlanDev {
@@ -65,13 +66,17 @@ struct PlanDev {
 };
 
 struct WorkDev {
-    int B, G, ngroups, K;  // K = history planes = max_coef + 1
+    int B, G, ngroups, K;  // B = scenarios in the queue; K = history planes = max_coef + 1
     double mismatch;
     int max_coef, enforce_q;
     double *scale;                    // [Bp]
     int *s_status, *s_mconv, *s_fail, *s_viol, *s_npass, *s_nswitch, *s_ncoef;  // [Bp], ncoef [Bp*MAXP]
     int *g_n, *g_flags;               // [ngroups]
     int *active_groups;               // [1]
+    int *queue_next;                  // [1] next scenario of the queue to be given a slot
+    int *slot_scen;                   // [Bp] scenario currently held by a slot (-1: none)
+    const double *scale_in;           // [B] scenario scales (queue)
+    int *out_status, *out_ncoef, *out_nswitch;   // per-scenario outputs, written when a scenario ends
     unsigned char *btype;             // [group][N][G]
     double *Qg, *VVant;               // [group][N][G]
     double2 *Pcur;                    // [group][N][G]
@@ -152,7 +157,20 @@ template <int G>
 __global__ void __launch_bounds__(256) k_assemble(PlanDev p, WorkDev w) {
     TL_SCOPE(w, 0);
     int grp = blockIdx.x;
-    if (!(w.g_flags[grp] & GF_FACTORING)) return;
+    const int gflags = w.g_flags[grp];
+    if (!(gflags & GF_FACTORING)) return;
+    if (gflags & GF_NEWSCEN) {      // slots refilled from the queue: fresh per-bus state (classes.py:230-297)
+        for (int flat = threadIdx.x; flat < p.N * G; flat += blockDim.x) {
+            int i = flat / G, s = flat % G;
+            if (w.s_status[grp * G + s] != ST_ACTIVE) continue;
+            size_t bi = ix<G>(grp, p.N, i, s);
+            w.btype[bi] = p.btype0[i];
+            w.Qg[bi] = 0.0;
+            w.VVant[bi] = 0.0;
+            w.Pcur[bi] = make_double2(0.0, 0.0);
+        }
+        __syncthreads();
+    }
     for (int flat = threadIdx.x; flat < p.nslots * G; flat += blockDim.x) {
         int slot = flat / G, s = flat % G;
         if (w.s_status[grp * G + s] != ST_ACTIVE) continue;
@@ -1083,7 +1101,8 @@ __global__ void k_qlimit(PlanDev p, WorkDev w) {
     const int N = p.N;
     size_t bi = ix<G>(grp, N, i, s);
     double2 vi = w.Pcur[bi];
-    if (sg < w.B) w.vout[(size_t)sg * N + p.perm[i]] = vi;
+    const int scen = w.slot_scen[sg];
+    if (scen >= 0) w.vout[(size_t)scen * N + p.perm[i]] = vi;
     if (!w.enforce_q) return;
     if (w.btype[bi] != HELM_BUS_PV) return;
     const double2 *pc = w.Pcur + (size_t)grp * N * G;
@@ -1132,8 +1151,42 @@ __global__ void k_pass_end(WorkDev w) {
         gf |= GF_PENDING;
         w.g_n[grp] = 0;
     } else {
-        gf |= GF_DONE;
-        atomicSub(w.active_groups, 1);
+        // every scenario of the group has ended: publish its results, then refill the slots from
+        // the scenario queue (continuous batching) or retire the group
+        int refilled = 0;
+        for (int s = 0; s < w.G; ++s) {
+            int sg = grp * w.G + s;
+            int scen = w.slot_scen[sg];
+            if (scen >= 0) {
+                int st = w.s_status[sg];
+                w.out_status[scen] = (st == ST_CONVERGED) ? HELM_ST_CONVERGED
+                                   : (st == ST_DIVERGED)  ? HELM_ST_DIVERGED
+                                   : (st == ST_SINGULAR)  ? HELM_ST_SINGULAR : HELM_ST_RUNNING;
+                if (w.out_nswitch) w.out_nswitch[scen] = w.s_nswitch[sg];
+                if (w.out_ncoef)
+                    for (int k = 0; k < HELM_MAX_PASSES; ++k)
+                        w.out_ncoef[scen * HELM_MAX_PASSES + k] = w.s_ncoef[sg * HELM_MAX_PASSES + k];
+            }
+            int next = atomicAdd(w.queue_next, 1);
+            if (next < w.B) {
+                w.slot_scen[sg] = next;
+                w.scale[sg] = w.scale_in[next];
+                w.s_status[sg] = ST_ACTIVE;
+                w.s_mconv[sg] = 0; w.s_fail[sg] = 0; w.s_viol[sg] = 0; w.s_npass[sg] = 0; w.s_nswitch[sg] = 0;
+                for (int k = 0; k < HELM_MAX_PASSES; ++k) w.s_ncoef[sg * HELM_MAX_PASSES + k] = 0;
+                refilled = 1;
+            } else {
+                w.slot_scen[sg] = -1;
+                w.s_status[sg] = ST_PAD;
+            }
+        }
+        if (refilled) {
+            gf |= GF_PENDING | GF_NEWSCEN;
+            w.g_n[grp] = 0;
+        } else {
+            gf |= GF_DONE;
+            atomicSub(w.active_groups, 1);
+        }
     }
     w.g_flags[grp] = gf;
 }
@@ -1147,7 +1200,7 @@ __global__ void k_step_begin(WorkDev w) {
     int grp = blockIdx.x * blockDim.x + threadIdx.x;
     if (grp >= w.ngroups) return;
     int gf = w.g_flags[grp];
-    if (gf & GF_FACTORING) gf &= ~GF_FACTORING;
+    if (gf & GF_FACTORING) gf &= ~(GF_FACTORING | GF_NEWSCEN);
     else if (gf & GF_PENDING) gf = (gf & ~GF_PENDING) | GF_FACTORING;
     w.g_flags[grp] = gf;
 }
@@ -1169,6 +1222,7 @@ __global__ void k_setup(PlanDev p, WorkDev w, const double *scale_in) {
     if (flat < G) {
         bool real = sg < w.B;
         w.scale[sg] = real ? scale_in[sg] : 1.0;
+        w.slot_scen[sg] = real ? sg : -1;
         w.s_status[sg] = real ? ST_ACTIVE : ST_PAD;
         w.s_mconv[sg] = 0; w.s_fail[sg] = 0; w.s_viol[sg] = 0; w.s_npass[sg] = 0; w.s_nswitch[sg] = 0;
         for (int k = 0; k < HELM_MAX_PASSES; ++k) w.s_ncoef[sg * HELM_MAX_PASSES + k] = 0;
@@ -1176,20 +1230,11 @@ __global__ void k_setup(PlanDev p, WorkDev w, const double *scale_in) {
     if (flat == 0) {
         w.g_n[grp] = 0;
         w.g_flags[grp] = GF_PENDING;
-        if (grp == 0) *w.active_groups = w.ngroups;
+        if (grp == 0) {
+            *w.active_groups = w.ngroups;
+            *w.queue_next = w.ngroups * G;      // slots 0..Bp-1 start with scenarios 0..Bp-1
+        }
     }
-}
-
-__global__ void k_export(WorkDev w, int *status, int *ncoef, int *nswitch) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= w.B) return;
-    int st = w.s_status[b];
-    status[b] = (st == ST_CONVERGED) ? HELM_ST_CONVERGED
-              : (st == ST_DIVERGED)  ? HELM_ST_DIVERGED
-              : (st == ST_SINGULAR)  ? HELM_ST_SINGULAR : HELM_ST_RUNNING;
-    if (nswitch) nswitch[b] = w.s_nswitch[b];
-    if (ncoef)
-        for (int k = 0; k < HELM_MAX_PASSES; ++k) ncoef[b * HELM_MAX_PASSES + k] = w.s_ncoef[b * HELM_MAX_PASSES + k];
 }
 
 // ---- microbenchmarks for the roofline denominators ------------------------------------------
@@ -1232,7 +1277,7 @@ struct helm_plan {
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     unsigned long long *tl = nullptr;
-    int last_B = 0, last_G = 0, last_maxcoef = 0;   // layout of the last host-buffer solve
+    int last_B = 0, last_G = 0, last_maxcoef = 0, last_resident = 0;   // layout of the last host-buffer solve
 };
 
 namespace {
@@ -1253,10 +1298,8 @@ inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 int pick_group(int n_scen, int requested) {
     if (requested == 1 || requested == 2 || requested == 4 || requested == 8 || requested == 16 || requested == 32)
         return requested;
-    if (n_scen >= 2048) return 8;
-    if (n_scen >= 512) return 4;
-    if (n_scen >= 64) return 2;
-    return 1;
+    (void)n_scen;
+    return 1;   // measured fastest at every batch size (profiles/README.md): no lock-step waiting
 }
 
 struct WsLayout {
@@ -1268,14 +1311,18 @@ struct WsLayout {
 WsLayout layout(const helm_plan *pl, int B, const helm_params *prm) {
     WsLayout L;
     L.G = pick_group(B, prm->group);
-    L.ngroups = (B + L.G - 1) / L.G;
+    // resident scenarios (slots): the rest of the batch waits in the queue and takes over slots as
+    // scenarios finish (continuous batching)
+    int resident = prm->max_resident > 0 ? prm->max_resident : 4096;
+    if (resident > B) resident = B;
+    L.ngroups = (resident + L.G - 1) / L.G;
     L.Bp = L.ngroups * L.G;
     L.K = prm->max_coefficients + 1;
     size_t N = pl->S.N, per = (size_t)L.Bp * N;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes); return r; };
     L.off_scale = take(sizeof(double) * L.Bp);
-    L.off_sint = take(sizeof(int) * L.Bp * (6 + HELM_MAX_PASSES));
+    L.off_sint = take(sizeof(int) * L.Bp * (7 + HELM_MAX_PASSES));
     L.off_gint = take(sizeof(int) * (2 * L.ngroups + 4));
     L.off_btype = take(per);
     L.off_Qg = take(per * sizeof(double));
@@ -1299,9 +1346,10 @@ WorkDev bind(const helm_plan *pl, const WsLayout &L, int B, const helm_params *p
     w.scale = (double *)(b + L.off_scale);
     int *si = (int *)(b + L.off_sint);
     w.s_status = si; w.s_mconv = si + L.Bp; w.s_fail = si + 2 * L.Bp; w.s_viol = si + 3 * L.Bp;
-    w.s_npass = si + 4 * L.Bp; w.s_nswitch = si + 5 * L.Bp; w.s_ncoef = si + 6 * L.Bp;
+    w.s_npass = si + 4 * L.Bp; w.s_nswitch = si + 5 * L.Bp; w.slot_scen = si + 6 * L.Bp; w.s_ncoef = si + 7 * L.Bp;
     int *gi = (int *)(b + L.off_gint);
-    w.g_n = gi; w.g_flags = gi + L.ngroups; w.active_groups = gi + 2 * L.ngroups;
+    w.g_n = gi; w.g_flags = gi + L.ngroups; w.active_groups = gi + 2 * L.ngroups; w.queue_next = gi + 2 * L.ngroups + 1;
+    w.scale_in = nullptr; w.out_status = nullptr; w.out_ncoef = nullptr; w.out_nswitch = nullptr;
     w.btype = (unsigned char *)(b + L.off_btype);
     w.Qg = (double *)(b + L.off_Qg);
     w.VVant = (double *)(b + L.off_VVant);
@@ -1580,6 +1628,7 @@ int helm_solve_batch_device(helm_plan *pl, int32_t B, const double *d_scale, con
     if (ws_bytes < L.total) { g_err = "workspace too small"; return HELM_E_NOMEM; }
     cudaStream_t st = (cudaStream_t)stream_;
     WorkDev w = bind(pl, L, B, prm, d_ws, d_vout);
+    w.scale_in = d_scale; w.out_status = d_status; w.out_ncoef = d_ncoef; w.out_nswitch = d_nswitch;
     const PlanDev &p = pl->d;
     const bool profile = getenv("HELM_B200_PROFILE") != nullptr;
     const bool use_graph = prm->use_graph && !profile;
@@ -1600,6 +1649,9 @@ int helm_solve_batch_device(helm_plan *pl, int32_t B, const double *d_scale, con
     CUDA_TRY(cudaEventCreate(&ev0));
     CUDA_TRY(cudaEventCreate(&ev1));
     CUDA_TRY(cudaEventRecord(ev0, st));
+    CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int) * B, st));           // HELM_ST_RUNNING until a scenario ends
+    if (d_ncoef) CUDA_TRY(cudaMemsetAsync(d_ncoef, 0, sizeof(int) * B * HELM_MAX_PASSES, st));
+    if (d_nswitch) CUDA_TRY(cudaMemsetAsync(d_nswitch, 0, sizeof(int) * B, st));
     launch_setup(L.G, p, w, d_scale, st);
 
     helm_stats local;
@@ -1629,7 +1681,7 @@ int helm_solve_batch_device(helm_plan *pl, int32_t B, const double *d_scale, con
         pev.resize(STEP_LEN + 1);
         for (auto &e : pev) cudaEventCreate(&e);
     }
-    const long max_steps = (long)(prm->max_coefficients + 2) * 4 * HELM_MAX_PASSES;
+    const long max_steps = (long)(prm->max_coefficients + 2) * 4 * HELM_MAX_PASSES * ((B + L.Bp - 1) / L.Bp);
     long steps = 0;
     int active = 1;
     while (active > 0 && steps < max_steps) {
@@ -1650,8 +1702,6 @@ int helm_solve_batch_device(helm_plan *pl, int32_t B, const double *d_scale, con
         CUDA_TRY(cudaStreamSynchronize(st));
         active = pl->h_pinned[0];
     }
-    k_export<<<(B + 127) / 128, 128, 0, st>>>(w, d_status, d_ncoef, d_nswitch);
-    local.kernel_launches++;
     CUDA_TRY(cudaEventRecord(ev1, st));
     CUDA_TRY(cudaEventSynchronize(ev1));
     float ms = 0;
@@ -1699,7 +1749,7 @@ int helm_solve_batch_host(helm_plan *pl, int32_t B, const double *h_scale, const
     rc = helm_solve_batch_device(pl, B, pl->d_scale, prm, pl->ws, pl->ws_bytes, pl->d_vout, pl->d_status,
                                  pl->d_ncoef, pl->d_nswitch, st, stats);
     if (rc) return rc;
-    pl->last_B = B; pl->last_G = L.G; pl->last_maxcoef = prm->max_coefficients;
+    pl->last_B = B; pl->last_G = L.G; pl->last_maxcoef = prm->max_coefficients; pl->last_resident = prm->max_resident;
     CUDA_TRY(cudaMemcpyAsync(h_vout, pl->d_vout, sizeof(double) * 2 * N * B, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(h_status, pl->d_status, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
     if (h_ncoef) CUDA_TRY(cudaMemcpyAsync(h_ncoef, pl->d_ncoef, sizeof(int) * B * HELM_MAX_PASSES, cudaMemcpyDeviceToHost, st));
@@ -1712,8 +1762,9 @@ int helm_last_state_host(helm_plan *pl, int32_t B, double *h_qg, uint8_t *h_bus_
     if (!pl || B <= 0 || B != pl->last_B || !pl->ws) { g_err = "no matching host solve to read state from"; return HELM_E_ARG; }
     helm_params prm;
     memset(&prm, 0, sizeof(prm));
-    prm.mismatch = 1.0; prm.max_coefficients = pl->last_maxcoef; prm.group = pl->last_G;
+    prm.mismatch = 1.0; prm.max_coefficients = pl->last_maxcoef; prm.group = pl->last_G; prm.max_resident = pl->last_resident;
     WsLayout L = layout(pl, B, &prm);
+    if (L.Bp < B) { g_err = "per-bus state is only kept when every scenario has its own slot (n_scen <= max_resident)"; return HELM_E_ARG; }
     const size_t N = pl->S.N, per = (size_t)L.Bp * N;
     std::vector<double> qg(per);
     std::vector<unsigned char> bt(per);

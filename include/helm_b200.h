@@ -78,6 +78,8 @@ typedef struct helm_params {
     int32_t group;              /* scenarios per lock-step group: 1,2,4,8,16,32; 0 = auto */
     int32_t use_graph;          /* replay the per-order step as a CUDA graph    */
     int32_t poll_every;         /* steps between host polls of the done counter; 0 = auto */
+    int32_t max_resident;       /* scenarios resident on the GPU at once (slots); the rest of the
+                                   batch queues and takes over slots as scenarios end; 0 = auto */
 } helm_params;
 
 typedef struct helm_plan_info {

@@ -21,6 +21,7 @@ def main():
     Bs = [int(x) for x in (sys.argv[2] if len(sys.argv) > 2 else '256,1024').split(',')]
     Gs = [int(x) for x in (sys.argv[3] if len(sys.argv) > 3 else '1,2,4,8,16,32').split(',')]
     profile = len(sys.argv) > 4 and sys.argv[4] == 'profile'
+    resident = int(os.environ.get('HELM_RESIDENT', '0'))
     case = load_case(name)
     print('peaks', _lib.measure_peaks())
     plan = get_plan(case)
@@ -35,7 +36,7 @@ def main():
             best = None
             for rep in range(2 if profile else 3):
                 t = time.perf_counter()
-                res = helmpy_b200.helm_batch(case, scales, mismatch=1e-8, max_coefficients=40, group=G)
+                res = helmpy_b200.helm_batch(case, scales, mismatch=1e-8, max_coefficients=40, group=G, max_resident=resident)
                 wall = time.perf_counter() - t
                 if best is None or res.stats['ms_total'] < best[0]:
                     best = (res.stats['ms_total'], wall, res)
