@@ -21,8 +21,9 @@ Third-party arithmetic on the path, as in the reference: SuperLU through
 ``numpy.linalg.solve`` (analytic_continuation.py:39); neither is pinned by the
 reference (setup.py:27-28).
 
-Scope: pv_bus_model=2 with the classic slack (the ``helm(case)`` default,
-helm.py:901).  PV1 / distributed-slack variants are SURVEY §8(f) row 1.
+Scope: every variant of the reference's own test matrix (test/test_helmpy.py:111-122):
+pv_bus_model 1 / 2, classic slack, distributed-slack methods 1 / 2 with or without
+participation factors.
 """
 
 import cmath
@@ -127,28 +128,61 @@ class Grid:
         self.btype0 = bt
 
 
-def build_matrix(g, btype):
-    """Real 2N x 2N recursion matrix (helm.py:30-60), CSC without explicit zeros."""
+def build_matrix(g, btype, pv_bus_model=2, DSB_model_method=None, K=None, list_gen=None):
+    """Real recursion matrix (helm.py:30-107), CSC without explicit zeros.
+
+    Returns (A, pv1_columns) where pv1_columns[i] = dict row -> removed entry of
+    column 2i (pv_bus_model 1, helm.py:72-103)."""
     N = g.N
+    length = 2 * N if DSB_model_method is None else 2 * N + 1
     rt = btype[g.row]
     G = g.ytr.real
     B = g.ytr.imag
     r2, c2 = 2 * g.row, 2 * g.idx
     ns = rt != SLACK
-    pq = rt == PQ
-    rows = [r2[ns], r2[ns], r2[pq] + 1, r2[pq] + 1]
-    cols = [c2[ns], c2[ns] + 1, c2[pq], c2[pq] + 1]
-    vals = [G[ns], -B[ns], B[pq], G[pq]]
+    full = (rt == PQ) | ((rt == PV) & (pv_bus_model == 1))        # helm.py:50
+    rows = [r2[ns], r2[ns], r2[full] + 1, r2[full] + 1]
+    cols = [c2[ns], c2[ns] + 1, c2[full], c2[full] + 1]
+    vals = [G[ns], -B[ns], B[full], G[full]]
     sl = np.nonzero(btype == SLACK)[0]
     pv = np.nonzero(btype == PV)[0]
-    rows += [2 * sl, 2 * sl + 1, 2 * pv + 1]
-    cols += [2 * sl, 2 * sl + 1, 2 * pv]
-    vals += [np.ones(len(sl)), np.ones(len(sl)), np.ones(len(pv))]
+    rows += [2 * sl, 2 * sl + 1]
+    cols += [2 * sl, 2 * sl + 1]
+    vals += [np.ones(len(sl)), np.ones(len(sl))]
+    if pv_bus_model == 2:
+        rows.append(2 * pv + 1)
+        cols.append(2 * pv)
+        vals.append(np.ones(len(pv)))                             # helm.py:57
+    if DSB_model_method is not None:                              # helm.py:62-70
+        s = g.slack
+        p0, p1 = g.ptr[s], g.ptr[s + 1]
+        rows += [np.full(p1 - p0, 2 * N), np.full(p1 - p0, 2 * N)]
+        cols += [2 * g.idx[p0:p1], 2 * g.idx[p0:p1] + 1]
+        vals += [G[p0:p1], -B[p0:p1]]
+        lg = np.asarray(list_gen, dtype=np.int64)
+        rows += [2 * lg, np.array([2 * N])]
+        cols += [np.full(len(lg), 2 * N), np.array([2 * N])]
+        vals += [-K[lg], np.array([-K[s]])]
     rows, cols, vals = map(np.concatenate, (rows, cols, vals))
-    keep = vals != 0           # csc_matrix(dense) stores no explicit zeros (helm.py:106)
-    A = coo_matrix((vals[keep], (rows[keep], cols[keep])), shape=(2 * N, 2 * N)).tocsc()
+    A = coo_matrix((vals, (rows, cols)), shape=(length, length)).tolil()
+    pv1_columns = {}
+    if pv_bus_model == 1:                                         # helm.py:72-103
+        for i in list_gen:
+            col = {}
+            for k in g.idx[g.ptr[i]:g.ptr[i + 1]]:
+                col[2 * k] = A[2 * k, 2 * i]
+                col[2 * k + 1] = A[2 * k + 1, 2 * i]
+                A[2 * k, 2 * i] = 0
+                A[2 * k + 1, 2 * i] = 0
+            if DSB_model_method is not None and g.slack in g.idx[g.ptr[i]:g.ptr[i + 1]]:
+                col[2 * N] = A[2 * N, 2 * i]
+                A[2 * N, 2 * i] = 0
+            pv1_columns[int(i)] = col
+            A[2 * i + 1, 2 * i] = 1
+    A = A.tocsc()
+    A.eliminate_zeros()        # csc_matrix(dense) stores no explicit zeros (helm.py:106)
     A.sort_indices()
-    return A
+    return A, pv1_columns
 
 
 def _spmv_rows(g, rows, vec):
@@ -165,41 +199,79 @@ def _spmv_rows(g, rows, vec):
 
 
 def helm_oracle(case, mismatch=1e-4, scale=1, max_coefficients=100, enforce_Q_limits=True,
-                record=False):
-    """Restatement of ``helm(case, pv_bus_model=2, DSB_model=False)`` (helm.py:896-985).
+                record=False, pv_bus_model=2, DSB_model=False, DSB_model_method=None):
+    """Restatement of ``helm(case, ...)`` (helm.py:896-985) for every variant:
+    pv_bus_model 1 / 2, classic slack, distributed slack methods 1 / 2.
 
     Does not mutate ``case``.  Returns (V complex128[N] or None, info) where
-    info = {'list_coef': [...], 'switched': [...], 'passes': [per-pass dict]}.
+    info = {'list_coef': [...], 'switched': [...], 'passes': [per-pass dict], 'Ploss': ...}.
     """
+    if DSB_model and DSB_model_method is None:
+        DSB_model_method = 2                                      # helm.py:913-914
     g = Grid(case)
     N = g.N
+    dsb = DSB_model_method is not None
+    length = 2 * N + 1 if dsb else 2 * N
     # set_scale (classes.py:215-219): three in-place multiplications
     Pd = g.Pd * scale if scale != 1 else g.Pd.copy()
     Qd = g.Qd * scale if scale != 1 else g.Qd.copy()
     Pg = g.Pg * scale if scale != 1 else g.Pg.copy()
+    Pg_imbalance = np.sum(Pd) - np.sum(Pg)                        # classes.py:286
     btype = g.btype0.copy()
     Qg = np.zeros(N)
+    K = np.zeros(N)
     list_gen = g.list_gen.copy()
     list_coef, switched, passes = [], [], []
     max_coef = max_coefficients
     Vprof = np.empty(N, dtype=complex)
     phase_items = [(i, np.asarray(v[0], dtype=np.int64), np.asarray(v[1], dtype=complex))
                    for i, v in sorted(g.phase.items())]
+    phase_map = {i: (nb, val) for (i, nb, val) in phase_items}
+    s_ = g.slack
+    m = 1
+
+    def phase_pp(i, vecs):
+        """sum_k phase_ik * vecs[k] (helm.py:375-377 and alike)"""
+        if i not in phase_map:
+            return 0
+        nb, val = phase_map[i]
+        acc = 0
+        for k in range(len(nb)):
+            acc += val[k] * vecs[nb[k]]
+        return acc
 
     while True:                                                   # helm.py:936
-        A = build_matrix(g, btype)
+        if DSB_model:                                             # compute_k_factor, helm.py:493-516
+            K = np.zeros(N)
+            Pg[s_] = Pg_imbalance
+            contrib = [int(i) for i in list_gen if Pg[i] > 0]
+            tot = sum(Pg[i] for i in contrib)
+            if Pg[s_] > 0:
+                tot += Pg[s_]
+                contrib.append(s_)
+            for i in contrib:
+                K[i] = Pg[i] / tot
+        elif dsb:                                                 # K_slack_1, helm.py:519-525
+            K = np.zeros(N)
+            K[s_] = 1
+        A, pv1_cols = build_matrix(g, btype, pv_bus_model, DSB_model_method, K, list_gen)
         solve = factorized(A)                                     # helm.py:106
         pq = np.nonzero(btype == PQ)[0]
         pv = np.nonzero(btype == PV)[0]
         V = np.zeros((N, max_coef + 1), dtype=complex)
         W = np.zeros((N, max_coef + 1), dtype=complex)
         CC = np.zeros((len(pv), max_coef + 1), dtype=complex)     # barras_CC
-        coeff = np.zeros((2 * N, max_coef + 1))
-        rhs_hist = np.zeros((2 * N, max_coef + 1))
+        slack_CC = np.zeros(max_coef + 1, dtype=complex)
+        Vre_PV = np.zeros((N, max_coef + 1))
+        coeff = np.zeros((length, max_coef + 1))
+        rhs_hist = np.zeros((length, max_coef + 1))
         VVant = np.zeros(len(pv))
-        V[:, 0] = 1                                               # helm.py:118-135, 556
-        W[:, 0] = 1                                               # helm.py:551
-        coeff[0::2, 0] = 1
+        V[:, 0] = 1                                               # helm.py:118-135, 551-556
+        W[:, 0] = 1
+        coeff[0:2 * N:2, 0] = 1
+        if pv_bus_model == 1:
+            coeff[2 * pv, 0] = 0                                  # helm.py:124-126
+            Vre_PV[:, 0] = 1
         Pi = Pg - Pd                                              # helm.py:559
         Si = Pi + Qg * 1j - Qd * 1j                               # helm.py:560
         pv_pos = {int(b): k for k, b in enumerate(pv)}
@@ -209,22 +281,28 @@ def helm_oracle(case, mismatch=1e-4, scale=1, max_coefficients=100, enforce_Q_li
         recalc = False
         while True:                                               # helm.py:567
             n += 1
-            rhs = np.zeros(2 * N)
+            rhs = np.zeros(length)
+            if pv_bus_model == 1:                                 # Calculo_Vre_PV, helm.py:142-159
+                for i in list_gen:
+                    if n > 1:
+                        aux = 0
+                        for k in range(1, n):
+                            aux += V[i, k] * np.conj(V[i, n - k])
+                        Vre_PV[i, n] = (-aux / 2).real
+                    else:
+                        Vre_PV[i, n] = (g.Vsp[i] ** 2 - 1) / 2
             # ---- PQ buses (helm.py:367-385)
             PPq = np.zeros(N, dtype=complex)
             for (i, nb, val) in phase_items:
-                acc = 0
-                for k in range(len(nb)):
-                    acc += val[k] * V[nb[k], n - 1]
-                PPq[i] = acc
+                PPq[i] = phase_pp(i, V[:, n - 1])
             res = np.conj(Si[pq]) * np.conj(W[pq, n - 1]) - g.Yshunt[pq] * V[pq, n - 1] - PPq[pq]
             rhs[2 * pq] = res.real
             rhs[2 * pq + 1] = res.imag
             # ---- slack (helm.py:388-398)
             if n == 1:
-                rhs[2 * g.slack] = g.Vsp[g.slack] - 1
-            # ---- PV buses, model 2 (helm.py:293-364)
-            if len(pv):
+                rhs[2 * s_] = g.Vsp[s_] - 1
+            # ---- PV buses
+            if len(pv) and pv_bus_model == 2:                     # helm.py:293-364
                 if n == 1:
                     cc = Pi[pv] - g.Yshunt[pv].real
                     for (i, nb, val) in phase_items:
@@ -249,10 +327,7 @@ def helm_oracle(case, mismatch=1e-4, scale=1, max_coefficients=100, enforce_Q_li
                         if i in pv_pos:
                             acc2 = 0
                             for x in range(n):
-                                pp = 0
-                                for k in range(len(nb)):
-                                    pp += val[k] * V[nb[k], n - 1 - x]
-                                acc2 += np.conj(V[i, x]) * pp
+                                acc2 += np.conj(V[i, x]) * phase_pp(i, V[:, n - 1 - x])
                             cc[pv_pos[i]] -= acc2.real
                     VVc = np.zeros(len(pv), dtype=complex)
                     for k in range(1, n):
@@ -261,10 +336,75 @@ def helm_oracle(case, mismatch=1e-4, scale=1, max_coefficients=100, enforce_Q_li
                     vv = -VVc.real
                 rhs[2 * pv] = cc
                 rhs[2 * pv + 1] = vv / 2
+            elif len(pv):                                         # pv model 1, helm.py:261-290
+                aux = np.zeros(len(pv), dtype=complex)
+                auxP = np.zeros(len(pv), dtype=complex)
+                for k in range(1, n):
+                    aux = aux + coeff[2 * pv, k] * np.conj(W[pv, n - k])
+                    if dsb:
+                        auxP = auxP + coeff[2 * N, k] * np.conj(W[pv, n - k])
+                res = Pi[pv] * np.conj(W[pv, n - 1]) - g.Yshunt[pv] * V[pv, n - 1] - PPq[pv] \
+                    - aux * 1j + K[pv] * auxP
+                rhs[2 * pv] = res.real
+                rhs[2 * pv + 1] = res.imag
+            # ---- distributed slack: extra equation (helm.py:164-258)
+            if DSB_model_method == 1:
+                auxP = 0
+                for k in range(1, n):
+                    auxP += coeff[2 * N, k] * np.conj(W[s_, n - k])
+                res = Pi[s_] * np.conj(W[s_, n - 1]) - g.Yshunt[s_] * V[s_, n - 1] \
+                    - phase_pp(s_, V[:, n - 1]) + K[s_] * auxP
+                rhs[2 * N] = np.real(res)
+            elif DSB_model_method == 2:
+                if n > 2:
+                    cc_s = 0
+                    PPP = 0
+                    for x in range(1, n - 1):
+                        PPP += np.conj(V[s_, n - x]) * slack_CC[x]
+                    PP = _spmv_rows(g, np.array([s_]), V[:, n - 1])[0]
+                    slack_CC[n - 1] = PP
+                    PPP += np.conj(V[s_, 1]) * PP
+                    cc_s -= PPP.real
+                    if g.conduc[s_]:
+                        VV = 0
+                        for k in range(1, n - 1):
+                            VV += V[s_, k] * np.conj(V[s_, n - k])            # helm.py:219-222 (as written)
+                        cc_s -= np.real(g.Yshunt[s_]) * (VV + 2 * V[s_, n - 1].real)
+                    if s_ in phase_map:
+                        acc2 = 0
+                        for x in range(n):
+                            acc2 += np.conj(V[s_, x]) * phase_pp(s_, V[:, n - 1 - x])
+                        cc_s -= acc2.real
+                elif n == 1:
+                    cc_s = Pi[s_] - np.real(g.Yshunt[s_])
+                    if s_ in phase_map:
+                        for v_ in phase_map[s_][1]:
+                            cc_s -= v_.real
+                else:
+                    PP = _spmv_rows(g, np.array([s_]), V[:, 1])[0]
+                    slack_CC[1] = PP
+                    cc_s = 0 - (np.conj(V[s_, 1]) * PP).real
+                    if g.conduc[s_]:
+                        cc_s -= np.real(g.Yshunt[s_]) * 2 * V[s_, 1].real
+                    if s_ in phase_map:
+                        acc2 = 0
+                        for x in range(n):
+                            acc2 += np.conj(V[s_, x]) * phase_pp(s_, V[:, n - 1 - x])
+                        cc_s -= acc2.real
+                rhs[2 * N] = np.real(cc_s)
             rhs_hist[:, n] = rhs
-            x_ = solve(rhs)                                       # helm.py:602
+            if pv_bus_model == 1:                                 # helm.py:584-597
+                sub = np.zeros(length)
+                for i in list_gen:
+                    for r_, v_ in pv1_cols[int(i)].items():
+                        sub[r_] += Vre_PV[i, n] * v_
+                x_ = solve(rhs - sub)
+            else:
+                x_ = solve(rhs)                                   # helm.py:602
             coeff[:, n] = x_
-            V[:, n] = x_[0::2] + 1j * x_[1::2]                    # helm.py:412-414
+            V[:, n] = x_[0:2 * N:2] + 1j * x_[1:2 * N:2]          # helm.py:412-420
+            if pv_bus_model == 1:
+                V[pv, n] = Vre_PV[pv, n] + 1j * x_[2 * pv + 1]
             aux = np.zeros(N, dtype=complex)                      # helm.py:423-433
             for k in range(n):
                 aux = aux + W[:, k] * V[:, n - k]
@@ -320,6 +460,8 @@ def helm_oracle(case, mismatch=1e-4, scale=1, max_coefficients=100, enforce_Q_li
     info = {'list_coef': list_coef, 'switched': switched, 'passes': passes}
     if diverged:
         return None, info
+    if dsb:
+        info['Ploss'] = pade(coeff[2 * N], m)                     # helm.py:963-965
     return Vprof.copy(), info
 
 

@@ -37,7 +37,7 @@ def test_factor_solve_stage_matches_superlu(hb, name, group):
     rhs = rng.standard_normal((B, 2 * case.N))
     x = plan.debug_factor_solve(bts, rhs, group=group)
     for b in range(B):
-        A = ho.build_matrix(g, bts[b].astype(np.int8))
+        A, _ = ho.build_matrix(g, bts[b].astype(np.int8))
         xs = splu(A).solve(rhs[b])
         assert np.max(np.abs(x[b] - xs)) <= 1e-10 * np.max(np.abs(xs))
 

@@ -52,6 +52,42 @@ def test_oracle_series_coefficients(name):
     assert np.max(np.abs(info['passes'][-1]['W'] - z['last_pass_W'])) < 1e-9
 
 
+VARIANTS = [(2, False, None), (1, False, None), (2, False, 1), (2, False, 2), (1, False, 1), (1, False, 2),
+            (2, True, 1), (2, True, 2), (1, True, 1), (1, True, 2)]       # test/test_helmpy.py:111-122
+
+
+@pytest.mark.parametrize('name', FAST)
+@pytest.mark.parametrize('variant', VARIANTS)
+def test_oracle_variants_match_reference_golden_xlsx(name, variant):
+    """The reference's full test matrix (test/test_helmpy.py:103-158): classic-slack runs against
+    'Results HELM <case> 1 1e-08.xlsx', distributed-slack runs (scale 1.02) against
+    'Results HELM DS <case> 1.02 1e-08.xlsx'."""
+    pv, dsb, method = variant
+    case = load_case(name)
+    V, info = ho.helm_oracle(case, mismatch=1e-8, scale=1.02 if dsb else 1, max_coefficients=40,
+                             pv_bus_model=pv, DSB_model=dsb, DSB_model_method=method)
+    g = golden_results(name)
+    key = 'ds' if dsb else 'classic'
+    assert V is not None
+    assert np.max(np.abs(np.abs(V) - g[key + '_mag'])) < 1e-11
+    assert np.max(np.abs(np.angle(V, deg=True) - g[key + '_ang_deg'])) < 1e-9
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize('variant', VARIANTS[1:])
+def test_oracle_variants_against_live_reference(variant):
+    from oracle import ref_shim
+    pv, dsb, method = variant
+    rc = ref_shim.ref_case('/root/reference/data/cases/case118.xlsx')
+    case = load_case('case118')
+    for s in (1.0, 1.1):
+        Vr, ir = ref_shim.ref_helm(rc, scale=s, pv_bus_model=pv, DSB_model=dsb, DSB_model_method=method)
+        Vo, io = ho.helm_oracle(case, mismatch=1e-8, scale=s, max_coefficients=40, pv_bus_model=pv,
+                                DSB_model=dsb, DSB_model_method=method)
+        assert ir['list_coef'] == io['list_coef'] and ir['switched'] == io['switched']
+        assert np.max(np.abs(Vr - Vo)) < 1e-11
+
+
 def test_pade_equals_epsilon_and_known_answer():
     """Pade [L/L](1) of a geometric series is exact: sum r^k = 1/(1-r)."""
     r = 0.5 + 0.3j
