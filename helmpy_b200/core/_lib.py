@@ -37,6 +37,7 @@ class Params(C.Structure):
         ("mismatch", C.c_double), ("max_coefficients", C.c_int32),
         ("enforce_q_limits", C.c_int32), ("group", C.c_int32),
         ("use_graph", C.c_int32), ("poll_every", C.c_int32), ("max_resident", C.c_int32),
+        ("pv_bus_model", C.c_int32), ("dsb_method", C.c_int32), ("dsb_model", C.c_int32),
     ]
 
 
@@ -198,7 +199,7 @@ class Plan:
 
     @staticmethod
     def make_params(mismatch, max_coefficients, enforce_q_limits, group=0, use_graph=True,
-                    poll_every=0, max_resident=0):
+                    poll_every=0, max_resident=0, pv_bus_model=2, dsb_method=0, dsb_model=False):
         p = Params()
         p.mismatch = float(mismatch)
         p.max_coefficients = int(max_coefficients)
@@ -207,6 +208,9 @@ class Plan:
         p.use_graph = int(bool(use_graph))
         p.poll_every = int(poll_every)
         p.max_resident = int(max_resident)
+        p.pv_bus_model = int(pv_bus_model)
+        p.dsb_method = int(dsb_method or 0)
+        p.dsb_model = int(bool(dsb_model))
         return p
 
     def workspace_bytes(self, n_scen, params):

@@ -10,8 +10,11 @@ the restart loop — executes in the CUDA library behind the C ABI
 (include/helm_b200.h).  There is no CPU path: without the built library or
 without a CUDA device these functions raise ``HelmB200Error``.
 
-Scope of this build: pv_bus_model=2 with the classic slack (the reference's
-default).  Other variants raise ``NotImplementedError``.
+All ten variants of the reference's test matrix run on the GPU: pv_bus_model 1 / 2,
+classic slack, distributed slack methods 1 / 2 with or without participation
+factors (test/test_helmpy.py:111-122).  The default (PV2, classic slack) uses the
+tuned kernels; the others use straightforward variant kernels
+(csrc/helm_variants.cuh).
 
 Documented deviation: the reference's argument validation
 prints its message and then runs anyway because ``(False, None)`` is truthy
@@ -86,7 +89,8 @@ class BatchResult:
 
 
 def helm_batch(case, scales, mismatch=1e-4, max_coefficients=100, enforce_Q_limits=True,
-               group=0, use_graph=True, poll_every=0, max_resident=0):
+               group=0, use_graph=True, poll_every=0, max_resident=0,
+               pv_bus_model=2, DSB_model=False, DSB_model_method=None):
     """Solve ``len(scales)`` load-scaling scenarios of ``case`` on the current GPU.
 
     Scenario b equals ``helm(case, scale=scales[b], mismatch=..., ...)``
@@ -96,8 +100,11 @@ def helm_batch(case, scales, mismatch=1e-4, max_coefficients=100, enforce_Q_limi
     over slots as scenarios finish, so device memory does not grow with the batch.
     """
     plan = get_plan(case)
+    if DSB_model and DSB_model_method is None:
+        DSB_model_method = 2                                   # helm.py:913-914
     prm = _lib.Plan.make_params(mismatch, max_coefficients, enforce_Q_limits, group, use_graph,
-                                poll_every, max_resident)
+                                poll_every, max_resident, pv_bus_model, DSB_model_method or 0,
+                                DSB_model)
     V, status, ncoef, nswitch, stats = plan.solve_host(np.asarray(scales, dtype=np.float64), prm)
     return BatchResult(V, status, ncoef, nswitch, stats)
 
@@ -116,12 +123,14 @@ def helm(case, detailed_run_print=False, mismatch=1e-4, scale=1, max_coefficient
         return None
     if DSB_model and DSB_model_method is None:
         DSB_model_method = 2
-    if pv_bus_model != 2 or DSB_model_method is not None:
-        raise NotImplementedError(
-            "helmpy_b200 currently implements pv_bus_model=2 with the classic slack; "
-            "PV model 1 and the distributed-slack variants are not built yet")
+    pv_str = 'PV1' if pv_bus_model == 1 else 'PV2'             # helm.py:916-922
+    if DSB_model_method is not None:
+        algorithm = 'HELM DS ' + ('M1' if DSB_model_method == 1 else 'M2') + ' ' + pv_str
+    else:
+        algorithm = 'HELM ' + pv_str
     res = helm_batch(case, [float(scale)], mismatch=mismatch, max_coefficients=max_coefficients,
-                     enforce_Q_limits=enforce_Q_limits, group=1)
+                     enforce_Q_limits=enforce_Q_limits, group=1, pv_bus_model=pv_bus_model,
+                     DSB_model=DSB_model, DSB_model_method=DSB_model_method)
     coefs = res.list_coef(0)
     if detailed_run_print:
         for p, m in enumerate(coefs[:-1]):
@@ -135,7 +144,7 @@ def helm(case, detailed_run_print=False, mismatch=1e-4, scale=1, max_coefficient
         from . import reporting
         Qg, bus_types = get_plan(case).last_state(1)
         reporting.report(case, V, Qg[0], bus_types[0], scale=scale, mismatch=mismatch, list_coef=coefs,
-                         algorithm='HELM PV2', enforce_Q_limits=enforce_Q_limits,
+                         algorithm=algorithm, enforce_Q_limits=enforce_Q_limits,
                          detailed_run_print=detailed_run_print, save_results=save_results,
                          results_file_name=results_file_name)
     return V

@@ -57,7 +57,8 @@ struct PlanDev {
     const int *perm;  // new index -> original bus
     const int *lptr, *lcol, *llev_ptr;
     const int *urow, *ulev_ptr, *uptr, *ucol, *dslot;
-    const int *slot_src, *slot_row;
+    const int *slot_src, *slot_row, *slot_col;
+    double pg_imb0;   // sum(Pd) - sum(Pg) of the unscaled case (classes.py:286)
     const int *fptr, *fsrc, *fdst, *fdstl, *qof;
     const int *fchunk_row, *fchunk_lpr, *frow_off;
     const int *sstep_kind, *sstep_a, *sstep_b, *sring_desc;
@@ -85,6 +86,13 @@ struct WorkDev {
     double2 *Vh, *Hh, *Eh;            // [group][K][N][G]
     double2 *vout;                    // [B][N] original order
     unsigned long long *tl;           // timeline buffer (HELM_TIMELINE builds only), else null
+    // variants (helm_variants.cuh): PV bus model 1 and the distributed slack
+    int pv_model, dsb_method, dsb_model;
+    double *ktot, *sden, *beta, *pcur;   // [slots]
+    double *ploss;                       // [slots][K]  Ploss series (coefficients[2N][n])
+    double2 *zb;                         // [slots][N]  A^-1 c of the bordered system
+    double *Qh;                          // [slots][K][N] Q_i[n] of PV buses (PV model 1)
+    double *vre, *qcur;                  // [slots][N]
 };
 
 // Optional kernel timeline (compile with -DHELM_TIMELINE): per step and kernel, the first CTA
@@ -184,8 +192,16 @@ __global__ void __launch_bounds__(256) k_assemble(PlanDev p, WorkDev w) {
         } else if (a >= 0) {
             double2 y = p.ytr[a];
             r0 = make_double2(y.x, -y.y);                                 // helm.py:52-53 / 59-60
-            if (bt == HELM_BUS_PQ) r1 = make_double2(y.y, y.x);           // helm.py:54-55
+            if (bt == HELM_BUS_PQ || w.pv_model == 1) r1 = make_double2(y.y, y.x);   // helm.py:50-55
             else if (diag) r1 = make_double2(1.0, 0.0);                   // helm.py:57
+        }
+        if (w.pv_model == 1 && bt != HELM_BUS_SLACK) {
+            // PV model 1: the column of Re V of a PV bus leaves the matrix (helm.py:72-103)
+            int c = p.slot_col[slot];
+            if (w.btype[ix<G>(grp, p.N, c, s)] == HELM_BUS_PV) {
+                r0.x = 0.0;
+                r1.x = diag ? 1.0 : 0.0;
+            }
         }
         double2 *dst = w.lu + ix<G>(grp, p.nslots, slot, s) * 2;
         dst[0] = r0;
@@ -557,12 +573,17 @@ __global__ void __launch_bounds__(WPB * 32) k_solve(PlanDev p, WorkDev w) {
 // the elimination tree: 1-8 rows of 20-60 entries each) give each row to a sub-warp whose lanes
 // split the row's entries and combine with shuffles, instead of leaving 31 lanes idle while one
 // lane walks a 57-entry row.  Cuts the executed warp instructions per solve ~4x (ncu, profiles/).
+// side = 1: solve for the scenarios being factorized in the side branch (z = A^-1 c of the
+// distributed-slack border, helm_variants.cuh) instead of the ones advancing in the main branch.
 template <int WPB>
-__global__ void __launch_bounds__(WPB * 32, 8) k_solve_warp(PlanDev p, WorkDev w) {
+__global__ void __launch_bounds__(WPB * 32, 8) k_solve_warp(PlanDev p, WorkDev w, int side) {
     TL_SCOPE(w, 2);
     int grp = blockIdx.x * WPB + (threadIdx.x >> 5);
     if (grp >= w.ngroups) return;
-    if (w.g_flags[grp] & (GF_DONE | GF_FACTORING)) return;
+    {
+        int gfl = w.g_flags[grp];
+        if (side ? !(gfl & GF_FACTORING) : (gfl & (GF_DONE | GF_FACTORING)) != 0) return;
+    }
     if (w.s_status[grp] != ST_ACTIVE) return;
     const int lane = threadIdx.x & 31;
     const double2 *lu = w.lu + (size_t)grp * p.nslots * 2;
@@ -1191,6 +1212,8 @@ __global__ void k_pass_end(WorkDev w) {
     w.g_flags[grp] = gf;
 }
 
+#include "helm_variants.cuh"
+
 // ---- K_begin: start of a step.  Groups factorized during the previous step rejoin the main
 // branch; groups whose pass ended in the previous step move to the factorization branch.
 __global__ void k_step_begin(WorkDev w) {
@@ -1305,12 +1328,13 @@ int pick_group(int n_scen, int requested) {
 struct WsLayout {
     size_t total = 0;
     size_t off_scale, off_sint, off_gint, off_btype, off_Qg, off_VVant, off_Pcur, off_rhs, off_xb, off_lu, off_Vh, off_Hh, off_Eh;
+    size_t off_var_s, off_ploss, off_zb, off_Qh, off_vre, off_qcur;
     int G, ngroups, Bp, K;
 };
 
 WsLayout layout(const helm_plan *pl, int B, const helm_params *prm) {
     WsLayout L;
-    L.G = pick_group(B, prm->group);
+    L.G = (prm->dsb_method || prm->pv_bus_model == 1) ? 1 : pick_group(B, prm->group);
     // resident scenarios (slots): the rest of the batch waits in the queue and takes over slots as
     // scenarios finish (continuous batching)
     int resident = prm->max_resident > 0 ? prm->max_resident : 4096;
@@ -1334,6 +1358,17 @@ WsLayout layout(const helm_plan *pl, int B, const helm_params *prm) {
     L.off_Vh = take(per * L.K * sizeof(double2));
     L.off_Hh = take(per * L.K * sizeof(double2));
     L.off_Eh = take(per * L.K * sizeof(double2));
+    L.off_var_s = L.off_ploss = L.off_zb = L.off_Qh = L.off_vre = L.off_qcur = 0;
+    if (prm->dsb_method) {
+        L.off_var_s = take(sizeof(double) * 4 * L.Bp);
+        L.off_ploss = take(sizeof(double) * (size_t)L.Bp * L.K);
+        L.off_zb = take(per * sizeof(double2));
+    }
+    if (prm->pv_bus_model == 1) {
+        L.off_Qh = take(per * L.K * sizeof(double));
+        L.off_vre = take(per * sizeof(double));
+        L.off_qcur = take(per * sizeof(double));
+    }
     L.total = o;
     return L;
 }
@@ -1362,13 +1397,29 @@ WorkDev bind(const helm_plan *pl, const WsLayout &L, int B, const helm_params *p
     w.Eh = (double2 *)(b + L.off_Eh);
     w.vout = (double2 *)vout;
     w.tl = pl->tl;
+    w.pv_model = prm->pv_bus_model == 1 ? 1 : 2;
+    w.dsb_method = prm->dsb_method;
+    w.dsb_model = prm->dsb_model;
+    w.ktot = w.sden = w.beta = w.pcur = w.ploss = nullptr; w.zb = nullptr; w.Qh = w.vre = w.qcur = nullptr;
+    if (prm->dsb_method) {
+        double *vs = (double *)(b + L.off_var_s);
+        w.ktot = vs; w.sden = vs + L.Bp; w.beta = vs + 2 * L.Bp; w.pcur = vs + 3 * L.Bp;
+        w.ploss = (double *)(b + L.off_ploss);
+        w.zb = (double2 *)(b + L.off_zb);
+    }
+    if (prm->pv_bus_model == 1) {
+        w.Qh = (double *)(b + L.off_Qh);
+        w.vre = (double *)(b + L.off_vre);
+        w.qcur = (double *)(b + L.off_qcur);
+    }
     return w;
 }
 
 constexpr int T_ELEM = 256;   // threads per CTA of the per-(item, scenario) kernels
 constexpr int WPB_SOLVE = 4;  // warps (= scenario groups) per CTA of the factor / solve kernels
 
-enum { KI_ASM = 0, KI_FACTOR, KI_SOLVE, KI_RHS, KI_ADV, KI_QLIM, KI_PEND, KI_INIT, KI_BEGIN, KI_COUNT };
+enum { KI_ASM = 0, KI_FACTOR, KI_SOLVE, KI_RHS, KI_ADV, KI_QLIM, KI_PEND, KI_INIT, KI_BEGIN,
+       KI_SOLVE_SIDE, KI_BPREP, KI_BFIN, KI_BP, KI_VPRE, KI_PV1C_MAIN, KI_PV1C_SIDE, KI_COUNT };
 
 template <int G>
 void launch_kernel(int which, const PlanDev &p, const WorkDev &w, cudaStream_t st) {
@@ -1385,19 +1436,34 @@ void launch_kernel(int which, const PlanDev &p, const WorkDev &w, cudaStream_t s
                 k_factor<G, WPB_SOLVE><<<(w.ngroups + WPB_SOLVE - 1) / WPB_SOLVE, WPB_SOLVE * 32, 0, st>>>(p, w);
             }
             break;
-        case KI_INIT: k_init<G><<<gridBus, T_ELEM, 0, st>>>(p, w); break;
+        case KI_INIT:
+            if (w.pv_model == 1 || w.dsb_method) k_init_var<<<gridBus, T_ELEM, 0, st>>>(p, w);
+            else k_init<G><<<gridBus, T_ELEM, 0, st>>>(p, w);
+            break;
+        case KI_BPREP: k_border_prep<<<w.ngroups, 256, 0, st>>>(p, w); break;
+        case KI_BFIN: k_border_fin<<<w.ngroups, 256, 0, st>>>(p, w); break;
+        case KI_BP: k_border_p<<<gridGrp, 128, 0, st>>>(p, w); break;
+        case KI_VPRE: k_var_pre<<<gridBus, T_ELEM, 0, st>>>(p, w); break;
+        case KI_PV1C_MAIN: k_pv1_correct<<<gridBus, T_ELEM, 0, st>>>(p, w, 0); break;
+        case KI_PV1C_SIDE: k_pv1_correct<<<gridBus, T_ELEM, 0, st>>>(p, w, 1); break;
+        case KI_SOLVE_SIDE:
+            k_solve_warp<WPB_SOLVE><<<(w.ngroups + WPB_SOLVE - 1) / WPB_SOLVE, WPB_SOLVE * 32, 0, st>>>(p, w, 1);
+            break;
         case KI_SOLVE:
             // shared-memory solve for small batches (<= ~3 CTAs per SM of concurrency is enough);
             // large batches keep more scenarios in flight with the warp-per-scenario kernel
             if (G == 1 && p.use_smem_solve && w.ngroups <= p.smem_solve_max_groups) {
                 k_solve_smem<<<w.ngroups, SM_T, solve_smem_bytes(p.N, p.nring, p.nsteps), st>>>(p, w);
             } else if (G == 1) {
-                k_solve_warp<WPB_SOLVE><<<(w.ngroups + WPB_SOLVE - 1) / WPB_SOLVE, WPB_SOLVE * 32, 0, st>>>(p, w);
+                k_solve_warp<WPB_SOLVE><<<(w.ngroups + WPB_SOLVE - 1) / WPB_SOLVE, WPB_SOLVE * 32, 0, st>>>(p, w, 0);
             } else {
                 k_solve<G, WPB_SOLVE><<<(w.ngroups + WPB_SOLVE - 1) / WPB_SOLVE, WPB_SOLVE * 32, 0, st>>>(p, w);
             }
             break;
-        case KI_RHS: k_rhs_conv<G><<<gridBus, T_ELEM, 0, st>>>(p, w); break;
+        case KI_RHS:
+            if (w.pv_model == 1 || w.dsb_method) k_rhs_conv_var<<<gridBus, T_ELEM, 0, st>>>(p, w);
+            else k_rhs_conv<G><<<gridBus, T_ELEM, 0, st>>>(p, w);
+            break;
         case KI_ADV: k_advance<<<gridGrp, 128, 0, st>>>(w); break;
         case KI_QLIM: k_qlimit<G><<<gridBus, T_ELEM, 0, st>>>(p, w); break;
         case KI_PEND: k_pass_end<<<gridGrp, 128, 0, st>>>(w); break;
@@ -1437,42 +1503,63 @@ void launch_setup(int G, const PlanDev &p, const WorkDev &w, const double *d_sca
 // hidden behind the solves of the rest of the batch; the factorized groups rejoin at the
 // next k_step_begin.  Both in eager mode and under stream capture the fork/join is expressed
 // with events, so the captured CUDA graph has the two branches as parallel paths.
-const int MAIN_SEQ[] = {KI_SOLVE, KI_RHS, KI_ADV, KI_QLIM, KI_PEND};
-const int SIDE_SEQ[] = {KI_ASM, KI_FACTOR, KI_INIT};
-constexpr int MAIN_LEN = sizeof(MAIN_SEQ) / sizeof(int);
-constexpr int SIDE_LEN = sizeof(SIDE_SEQ) / sizeof(int);
-constexpr int STEP_LEN = 1 + MAIN_LEN + SIDE_LEN;
+constexpr int SEQ_MAX = 12;
+struct StepSeq {
+    int main_seq[SEQ_MAX], side_seq[SEQ_MAX];
+    int main_len = 0, side_len = 0;
+};
+// default: main = solve, rhs_conv, advance, qlimit, pass_end; side = assemble, factor, init.
+// Variants (helm_variants.cuh) add the bordered-system kernels and the PV-model-1 fix-ups.
+StepSeq make_seq(const WorkDev &w) {
+    StepSeq q;
+    const bool dsb = w.dsb_method != 0, pv1 = w.pv_model == 1;
+    q.side_seq[q.side_len++] = KI_ASM;
+    q.side_seq[q.side_len++] = KI_FACTOR;
+    if (dsb) { q.side_seq[q.side_len++] = KI_BPREP; q.side_seq[q.side_len++] = KI_SOLVE_SIDE; q.side_seq[q.side_len++] = KI_BFIN; }
+    q.side_seq[q.side_len++] = KI_INIT;
+    if (pv1) q.side_seq[q.side_len++] = KI_PV1C_SIDE;
+    q.main_seq[q.main_len++] = KI_SOLVE;
+    if (dsb) q.main_seq[q.main_len++] = KI_BP;
+    if (dsb || pv1) q.main_seq[q.main_len++] = KI_VPRE;
+    q.main_seq[q.main_len++] = KI_RHS;
+    if (pv1) q.main_seq[q.main_len++] = KI_PV1C_MAIN;
+    q.main_seq[q.main_len++] = KI_ADV;
+    q.main_seq[q.main_len++] = KI_QLIM;
+    q.main_seq[q.main_len++] = KI_PEND;
+    return q;
+}
+constexpr int STEP_LEN_MAX = 1 + 2 * SEQ_MAX;
 
 struct StepCtx {
     cudaStream_t st, side;
     cudaEvent_t fork, join;
 };
 
-void launch_step(int G, const PlanDev &p, const WorkDev &w, const StepCtx &c) {
+void launch_step(int G, const PlanDev &p, const WorkDev &w, const StepCtx &c, const StepSeq &q) {
     static const bool nofork = getenv("HELM_B200_NOFORK") != nullptr;   // A/B switch: serial step
     if (nofork) {
         launch_any(G, KI_BEGIN, p, w, c.st);
-        for (int k = 0; k < SIDE_LEN; ++k) launch_any(G, SIDE_SEQ[k], p, w, c.st);
-        for (int k = 0; k < MAIN_LEN; ++k) launch_any(G, MAIN_SEQ[k], p, w, c.st);
+        for (int k = 0; k < q.side_len; ++k) launch_any(G, q.side_seq[k], p, w, c.st);
+        for (int k = 0; k < q.main_len; ++k) launch_any(G, q.main_seq[k], p, w, c.st);
         return;
     }
     launch_any(G, KI_BEGIN, p, w, c.st);
     cudaEventRecord(c.fork, c.st);
     cudaStreamWaitEvent(c.side, c.fork, 0);
-    for (int k = 0; k < SIDE_LEN; ++k) launch_any(G, SIDE_SEQ[k], p, w, c.side);
+    for (int k = 0; k < q.side_len; ++k) launch_any(G, q.side_seq[k], p, w, c.side);
     cudaEventRecord(c.join, c.side);
-    for (int k = 0; k < MAIN_LEN; ++k) launch_any(G, MAIN_SEQ[k], p, w, c.st);
+    for (int k = 0; k < q.main_len; ++k) launch_any(G, q.main_seq[k], p, w, c.st);
     cudaStreamWaitEvent(c.st, c.join, 0);
 }
 
 // serial variant with an event around every kernel (profile mode)
 void launch_step_profiled(int G, const PlanDev &p, const WorkDev &w, cudaStream_t st,
-                          std::vector<cudaEvent_t> &ev, helm_stats &acc) {
-    int seq[STEP_LEN];
+                          std::vector<cudaEvent_t> &ev, helm_stats &acc, const StepSeq &q) {
+    int seq[STEP_LEN_MAX];
     int n = 0;
     seq[n++] = KI_BEGIN;
-    for (int k = 0; k < SIDE_LEN; ++k) seq[n++] = SIDE_SEQ[k];
-    for (int k = 0; k < MAIN_LEN; ++k) seq[n++] = MAIN_SEQ[k];
+    for (int k = 0; k < q.side_len; ++k) seq[n++] = q.side_seq[k];
+    for (int k = 0; k < q.main_len; ++k) seq[n++] = q.main_seq[k];
     for (int k = 0; k < n; ++k) {
         cudaEventRecord(ev[k], st);
         launch_any(G, seq[k], p, w, st);
@@ -1507,6 +1594,11 @@ int helm_plan_create(const helm_grid_host *g, helm_plan **out) {
     d.N = N; d.nL = S.nL; d.nU = S.nU; d.nslots = S.nslots;
     d.nLlev = (int)S.llev_ptr.size() - 1; d.nUlev = (int)S.ulev_ptr.size() - 1;
     d.nadj = S.nnz_adj; d.slack = S.iperm[g->slack];
+    {
+        double spd = 0.0, spg = 0.0;
+        for (int i = 0; i < N; ++i) { spd += g->pd[i]; spg += g->pg[i]; }
+        d.pg_imb0 = spd - spg;
+    }
     pl->n_factor_updates = (int)S.fsrc.size();
     // permute the grid data into the elimination numbering
     std::vector<double2> ytr(S.nnz_adj), yfull(S.nnz_adj), ysh(N), phv;
@@ -1538,7 +1630,7 @@ int helm_plan_create(const helm_grid_host *g, helm_plan **out) {
     UP(vsp, vsp) UP(pg, pg) UP(pd, pd) UP(qd, qd) UP(qmax, qmax) UP(qmin, qmin) UP(bt, btype0)
     UP(S.perm, perm) UP(S.lptr, lptr) UP(S.lcol, lcol) UP(S.llev_ptr, llev_ptr)
     UP(S.urow, urow) UP(S.ulev_ptr, ulev_ptr) UP(S.uptr, uptr) UP(S.ucol, ucol) UP(S.dslot, dslot)
-    UP(S.slot_src, slot_src) UP(S.slot_row, slot_row)
+    UP(S.slot_src, slot_src) UP(S.slot_row, slot_row) UP(S.slot_col, slot_col)
     UP(S.fptr, fptr) UP(S.fsrc, fsrc) UP(S.fdst, fdst) UP(S.fdst_local, fdstl) UP(S.qof, qof)
     UP(S.fchunk_row, fchunk_row) UP(S.fchunk_lpr, fchunk_lpr) UP(S.frow_off, frow_off)
     UP(S.sstep_kind, sstep_kind) UP(S.sstep_a, sstep_a) UP(S.sstep_b, sstep_b) UP(S.sring_desc, sring_desc)
@@ -1615,6 +1707,9 @@ static int check_params(const helm_params *prm) {
     if (!prm) { g_err = "null params"; return HELM_E_ARG; }
     if (prm->max_coefficients < 5) { g_err = "max_coefficients must be >= 5 (helm.py:882-884)"; return HELM_E_ARG; }
     if (!(prm->mismatch > 0)) { g_err = "mismatch must be positive"; return HELM_E_ARG; }
+    if (prm->pv_bus_model != 0 && prm->pv_bus_model != 1 && prm->pv_bus_model != 2) { g_err = "pv_bus_model must be 1 or 2"; return HELM_E_ARG; }
+    if (prm->dsb_method < 0 || prm->dsb_method > 2) { g_err = "dsb_method must be 0, 1 or 2"; return HELM_E_ARG; }
+    if (prm->dsb_model && !prm->dsb_method) { g_err = "dsb_model needs dsb_method 1 or 2"; return HELM_E_ARG; }
     return HELM_OK;
 }
 
@@ -1668,17 +1763,19 @@ int helm_solve_batch_device(helm_plan *pl, int32_t B, const double *d_scale, con
         CUDA_TRY(cudaEventCreateWithFlags(&pl->ev_join, cudaEventDisableTiming));
     }
     StepCtx ctx{st, pl->side, pl->ev_fork, pl->ev_join};
+    const StepSeq seq = make_seq(w);
+    const int STEP_LEN = 1 + seq.main_len + seq.side_len;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t gexec = nullptr;
     if (use_graph) {
         CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        for (int rep = 0; rep < poll_every; ++rep) launch_step(L.G, p, w, ctx);
+        for (int rep = 0; rep < poll_every; ++rep) launch_step(L.G, p, w, ctx, seq);
         CUDA_TRY(cudaStreamEndCapture(st, &graph));
         CUDA_TRY(cudaGraphInstantiate(&gexec, graph, 0));
     }
     std::vector<cudaEvent_t> pev;
     if (profile) {
-        pev.resize(STEP_LEN + 1);
+        pev.resize(STEP_LEN_MAX + 1);
         for (auto &e : pev) cudaEventCreate(&e);
     }
     const long max_steps = (long)(prm->max_coefficients + 2) * 4 * HELM_MAX_PASSES * ((B + L.Bp - 1) / L.Bp);
@@ -1692,8 +1789,8 @@ int helm_solve_batch_device(helm_plan *pl, int32_t B, const double *d_scale, con
             steps += poll_every;
         } else {
             for (int rep = 0; rep < poll_every; ++rep) {
-                if (profile) launch_step_profiled(L.G, p, w, st, pev, local);
-                else launch_step(L.G, p, w, ctx);
+                if (profile) launch_step_profiled(L.G, p, w, st, pev, local, seq);
+                else launch_step(L.G, p, w, ctx, seq);
                 local.kernel_launches += STEP_LEN;
                 steps++;
             }

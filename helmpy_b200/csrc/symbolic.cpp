@@ -363,11 +363,16 @@ bool build_symbolic(int N, const int32_t *adj_ptr, const int32_t *adj_idx, const
     S.adj_slot.resize(S.nnz_adj);
     S.slot_src.assign(S.nslots, -1);
     S.slot_row.assign(S.nslots, 0);
+    S.slot_col.assign(S.nslots, 0);
     for (int r = 0; r < N; ++r) {
-        for (int e = S.lptr[r]; e < S.lptr[r + 1]; ++e) S.slot_row[e] = r;
+        for (int e = S.lptr[r]; e < S.lptr[r + 1]; ++e) { S.slot_row[e] = r; S.slot_col[e] = S.lcol[e]; }
         int q = S.qof[r];
         S.slot_row[S.slotD(q)] = r;
-        for (int t = 0; t < S.uptr[q + 1] - S.uptr[q]; ++t) S.slot_row[S.slotU(q, t)] = r;
+        S.slot_col[S.slotD(q)] = r;
+        for (int t = 0; t < S.uptr[q + 1] - S.uptr[q]; ++t) {
+            S.slot_row[S.slotU(q, t)] = r;
+            S.slot_col[S.slotU(q, t)] = S.ucol[S.uptr[q] + t];
+        }
     }
     for (int r = 0; r < N; ++r) {
         int o = S.perm[r];

@@ -36,7 +36,7 @@ struct Symbolic {
     std::vector<int> frow_off;                   // row -> block offset of its buffer inside its chunk
     int cap_upd = 0, cap_ent = 0, cap_rowblk = 0;  // staging capacities (max over chunks)
     // assembly map: slot -> adjacency entry (or -1 for fill), slot -> row
-    std::vector<int> slot_src, slot_row;
+    std::vector<int> slot_src, slot_row, slot_col;
 
     // triangular-solve schedule for the shared-memory solve kernel: steps in execution order
     // (forward levels, then backward levels).  kind: 0 = forward level, rows from global memory;

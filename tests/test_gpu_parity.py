@@ -279,3 +279,46 @@ def test_continuous_batching_equals_all_resident(hb):
     assert np.array_equal(a.V, b.V)                  # same kernels, different slots: bit-identical
     assert np.max(np.abs(a.V - c.V)) < 1e-11         # lock-step groups use the generic kernels
     assert a.converged.sum() > 150
+
+
+VARIANTS = [(1, False, None), (2, False, 1), (2, False, 2), (1, False, 1), (1, False, 2),
+            (2, True, 1), (2, True, 2), (1, True, 1), (1, True, 2)]        # test/test_helmpy.py:111-122
+
+
+@pytest.mark.parametrize('name', ['case9', 'case118', 'case1354pegase'])
+@pytest.mark.parametrize('variant', VARIANTS)
+def test_helm_variants_match_reference_golden_xlsx(hb, name, variant):
+    """The rest of the reference's own test matrix: PV model 1 and the distributed-slack
+    formulations, against the golden classic / DS result files (scale 1 / 1.02) and the oracle."""
+    pv, dsb, method = variant
+    case = load_case(name)
+    scale = 1.02 if dsb else 1
+    V = hb.helm(case, mismatch=1e-8, scale=scale, max_coefficients=40, pv_bus_model=pv,
+                DSB_model=dsb, DSB_model_method=method)
+    g = golden_results(name)
+    key = 'ds' if dsb else 'classic'
+    assert V is not None
+    assert np.max(np.abs(np.abs(V) - g[key + '_mag'])) <= TOL_MAG
+    assert np.max(np.abs(np.angle(V) - np.deg2rad(g[key + '_ang_deg']))) <= TOL_ANG
+    Vo, info = ho.helm_oracle(case, mismatch=1e-8, scale=scale, max_coefficients=40, pv_bus_model=pv,
+                              DSB_model=dsb, DSB_model_method=method)
+    dmag, dang = polar_err(V, Vo)
+    assert dmag <= TOL_MAG and dang <= TOL_ANG
+
+
+@pytest.mark.parametrize('variant', [(1, False, None), (2, True, 2), (1, True, 1)])
+def test_variant_batches_match_oracle(hb, variant):
+    pv, dsb, method = variant
+    case = load_case('case118')
+    scales = np.random.default_rng(5).uniform(0.85, 1.2, 24)
+    res = hb.helm_batch(case, scales, mismatch=1e-8, max_coefficients=40, pv_bus_model=pv,
+                        DSB_model=dsb, DSB_model_method=method, max_resident=10)
+    for b, s in enumerate(scales):
+        Vo, info = ho.helm_oracle(case, mismatch=1e-8, scale=s, max_coefficients=40, pv_bus_model=pv,
+                                  DSB_model=dsb, DSB_model_method=method)
+        assert bool(res.converged[b]) == (Vo is not None)
+        if Vo is not None:
+            assert res.list_coef(b) == info['list_coef']
+            assert res.nswitch[b] == len(info['switched'])
+            dmag, dang = polar_err(res.V[b], Vo)
+            assert dmag <= TOL_MAG and dang <= TOL_ANG
