@@ -59,7 +59,7 @@ KERNEL_NAMES = ("assemble", "factor", "solve", "rhs_conv", "advance", "qlimit", 
 EXPORTED_SYMBOLS = (
     "helm_last_error", "helm_plan_create", "helm_plan_destroy", "helm_plan_get_info",
     "helm_plan_get_perm", "helm_workspace_bytes", "helm_solve_batch_device",
-    "helm_solve_batch_host", "helm_last_state_host", "helm_debug_factor_solve", "helm_debug_timeline", "helm_measure_peaks",
+    "helm_solve_batch_host", "helm_last_state_host", "helm_last_ploss_host", "helm_debug_factor_solve", "helm_debug_timeline", "helm_measure_peaks",
     "helm_symbolic_create", "helm_symbolic_destroy", "helm_symbolic_array",
 )
 
@@ -96,6 +96,7 @@ def load():
         C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p,
         C.c_void_p, C.c_void_p, C.POINTER(Stats)]
     lib.helm_last_state_host.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.helm_last_ploss_host.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     lib.helm_debug_factor_solve.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                             C.c_void_p, C.c_void_p]
     lib.helm_debug_timeline.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
@@ -249,6 +250,13 @@ class Plan:
         bt = np.zeros((n_scen, self.N), dtype=np.uint8)
         check(load().helm_last_state_host(self.handle, n_scen, _ptr(qg), _ptr(bt)), "helm_last_state_host")
         return qg, bt
+
+    def last_ploss(self, n_scen, max_coefficients, dsb_method, pv_bus_model):
+        """Ploss series [B, max_coefficients+1] of the last distributed-slack ``solve_host``."""
+        out = np.zeros((n_scen, max_coefficients + 1), dtype=np.float64)
+        check(load().helm_last_ploss_host(self.handle, n_scen, int(dsb_method), int(pv_bus_model), _ptr(out)),
+              "helm_last_ploss_host")
+        return out
 
     def debug_factor_solve(self, bus_types, rhs, group=1):
         bus_types = np.ascontiguousarray(bus_types, dtype=np.uint8)

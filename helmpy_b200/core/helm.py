@@ -142,9 +142,13 @@ def helm(case, detailed_run_print=False, mismatch=1e-4, scale=1, max_coefficient
     V = res.V[0].copy()
     if detailed_run_print or save_results:
         from . import reporting
-        Qg, bus_types = get_plan(case).last_state(1)
+        plan = get_plan(case)
+        Qg, bus_types = plan.last_state(1)
+        ploss = None
+        if DSB_model_method is not None:
+            ploss = plan.last_ploss(1, max_coefficients, DSB_model_method, pv_bus_model)[0]
         reporting.report(case, V, Qg[0], bus_types[0], scale=scale, mismatch=mismatch, list_coef=coefs,
                          algorithm=algorithm, enforce_Q_limits=enforce_Q_limits,
                          detailed_run_print=detailed_run_print, save_results=save_results,
-                         results_file_name=results_file_name)
+                         results_file_name=results_file_name, DSB_model=DSB_model, ploss_series=ploss)
     return V

@@ -136,14 +136,47 @@ def write_results_on_files(mismatch, scale, algorithm, V, V_polar_final, Power_b
     return xlsx_name, txt_name
 
 
+def pade(series, m):
+    """[L/L] Pade approximant at s = 1 of a scalar series (analytic_continuation.py:29-50); used
+    here only for the Ploss line of the distributed-slack report (helm.py:963-965)."""
+    s = np.asarray(series[:m], dtype=complex)
+    L = (len(s) - 1) // 2
+    C = np.array([[s[r + c + 1] for c in range(L)] for r in range(L)], dtype=complex)
+    b = np.ones(L + 1, dtype=complex)
+    b[1:] = (-np.linalg.solve(C, s[L + 1:len(s)]))[::-1]
+    a = np.array([sum(s[k] * b[i - k] for k in range(i + 1)) for i in range(L + 1)])
+    return np.sum(a) / np.sum(b)
+
+
+def k_factors(case, Pg_run, list_gen, DSB_model):
+    """compute_k_factor / K_slack_1 (helm.py:493-525)."""
+    K = np.zeros(case.N)
+    if not DSB_model:
+        K[case.slack] = 1
+        return K
+    contrib = [i for i in list_gen if Pg_run[i] > 0]
+    if Pg_run[case.slack] > 0:
+        contrib.append(case.slack)
+    tot = sum(Pg_run[i] for i in contrib)
+    for i in contrib:
+        K[i] = Pg_run[i] / tot
+    return K
+
+
 def report(case, V, Qg, bus_types, scale, mismatch, list_coef, algorithm, enforce_Q_limits,
-           detailed_run_print, save_results, results_file_name):
+           detailed_run_print, save_results, results_file_name, DSB_model=False, ploss_series=None):
     """What helm() does after convergence when printing or saving (helm.py:962-984)."""
     Pg_run = case.Pg * scale                       # run.Pg: copy taken while the case was scaled
     list_gen = [int(i) for i in np.nonzero(np.asarray(bus_types) == 1)[0]]
-    Pb, S_gen, S_load, S_mis, Pmis = power_balance(case, V, Qg, Pg_run, list_gen, enforce_Q_limits, algorithm)
+    K = Ploss = None
+    if 'DS' in algorithm:
+        if DSB_model:                              # helm.py:506 with classes.py:286
+            Pg_run[case.slack] = np.sum(case.Pd * scale) - np.sum(case.Pg * scale)
+        K = k_factors(case, Pg_run, list_gen, DSB_model)
+        Ploss = pade(ploss_series, list_coef[-1])
+    Pb, S_gen, S_load, S_mis, Pmis = power_balance(case, V, Qg, Pg_run, list_gen, enforce_Q_limits, algorithm, K)
     polar = convert_complex_to_polar_voltages(V)
-    text = create_power_balance_string(mismatch, scale, algorithm, list_coef, S_gen, S_load, S_mis)
+    text = create_power_balance_string(mismatch, scale, algorithm, list_coef, S_gen, S_load, S_mis, Ploss, Pmis)
     if detailed_run_print:
         print_voltage_profile(polar, case.N)
         print(text)

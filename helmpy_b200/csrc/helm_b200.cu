@@ -1300,7 +1300,7 @@ struct helm_plan {
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     unsigned long long *tl = nullptr;
-    int last_B = 0, last_G = 0, last_maxcoef = 0, last_resident = 0;   // layout of the last host-buffer solve
+    int last_B = 0, last_G = 0, last_maxcoef = 0, last_resident = 0, last_dsb = 0, last_pv = 0;   // layout of the last host-buffer solve
 };
 
 namespace {
@@ -1846,7 +1846,7 @@ int helm_solve_batch_host(helm_plan *pl, int32_t B, const double *h_scale, const
     rc = helm_solve_batch_device(pl, B, pl->d_scale, prm, pl->ws, pl->ws_bytes, pl->d_vout, pl->d_status,
                                  pl->d_ncoef, pl->d_nswitch, st, stats);
     if (rc) return rc;
-    pl->last_B = B; pl->last_G = L.G; pl->last_maxcoef = prm->max_coefficients; pl->last_resident = prm->max_resident;
+    pl->last_B = B; pl->last_G = L.G; pl->last_maxcoef = prm->max_coefficients; pl->last_resident = prm->max_resident; pl->last_dsb = prm->dsb_method; pl->last_pv = prm->pv_bus_model;
     CUDA_TRY(cudaMemcpyAsync(h_vout, pl->d_vout, sizeof(double) * 2 * N * B, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(h_status, pl->d_status, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
     if (h_ncoef) CUDA_TRY(cudaMemcpyAsync(h_ncoef, pl->d_ncoef, sizeof(int) * B * HELM_MAX_PASSES, cudaMemcpyDeviceToHost, st));
@@ -1859,7 +1859,7 @@ int helm_last_state_host(helm_plan *pl, int32_t B, double *h_qg, uint8_t *h_bus_
     if (!pl || B <= 0 || B != pl->last_B || !pl->ws) { g_err = "no matching host solve to read state from"; return HELM_E_ARG; }
     helm_params prm;
     memset(&prm, 0, sizeof(prm));
-    prm.mismatch = 1.0; prm.max_coefficients = pl->last_maxcoef; prm.group = pl->last_G; prm.max_resident = pl->last_resident;
+    prm.mismatch = 1.0; prm.max_coefficients = pl->last_maxcoef; prm.group = pl->last_G; prm.max_resident = pl->last_resident; prm.dsb_method = pl->last_dsb; prm.pv_bus_model = pl->last_pv;
     WsLayout L = layout(pl, B, &prm);
     if (L.Bp < B) { g_err = "per-bus state is only kept when every scenario has its own slot (n_scen <= max_resident)"; return HELM_E_ARG; }
     const size_t N = pl->S.N, per = (size_t)L.Bp * N;
@@ -1876,6 +1876,18 @@ int helm_last_state_host(helm_plan *pl, int32_t B, double *h_qg, uint8_t *h_bus_
             if (h_bus_type) h_bus_type[(size_t)b * N + o] = bt[bi];
         }
     }
+    return HELM_OK;
+}
+
+int helm_last_ploss_host(helm_plan *pl, int32_t B, int32_t dsb_method, int32_t pv_bus_model, double *h_ploss) {
+    if (!pl || !h_ploss || B <= 0 || B != pl->last_B || !pl->ws || !dsb_method) { g_err = "no matching distributed-slack host solve"; return HELM_E_ARG; }
+    helm_params prm;
+    memset(&prm, 0, sizeof(prm));
+    prm.mismatch = 1.0; prm.max_coefficients = pl->last_maxcoef; prm.group = 1; prm.max_resident = pl->last_resident;
+    prm.dsb_method = dsb_method; prm.pv_bus_model = pv_bus_model;
+    WsLayout L = layout(pl, B, &prm);
+    if (L.Bp < B) { g_err = "per-scenario state is only kept when every scenario has its own slot"; return HELM_E_ARG; }
+    CUDA_TRY(cudaMemcpy(h_ploss, (char *)pl->ws + L.off_ploss, sizeof(double) * (size_t)B * L.K, cudaMemcpyDeviceToHost));
     return HELM_OK;
 }
 

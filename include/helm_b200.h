@@ -151,6 +151,11 @@ int helm_solve_batch_host(helm_plan *plan, int32_t n_scen, const double *h_scale
  * original bus order; either pointer may be NULL. */
 int helm_last_state_host(helm_plan *plan, int32_t n_scen, double *h_qg, uint8_t *h_bus_type);
 
+/* Ploss series of the last distributed-slack helm_solve_batch_host call (reference
+ * run.coefficients[2N][:], used by the report, helm.py:963-965): h_ploss [n_scen*(max_coefficients+1)]. */
+int helm_last_ploss_host(helm_plan *plan, int32_t n_scen, int32_t dsb_method, int32_t pv_bus_model,
+                         double *h_ploss);
+
 /* Debug/testing hooks: run one kernel stage in isolation on device buffers.
  * Used by the parity tests to compare individual stages with the oracle. */
 int helm_debug_factor_solve(helm_plan *plan, int32_t n_scen, int32_t group,

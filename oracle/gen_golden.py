@@ -87,6 +87,13 @@ def main():
                     h.helm(case, detailed_run_print=True, mismatch=1e-8, scale=sc, max_coefficients=40)
                 with open(os.path.join(out, 'ref_stdout_%s_%s.txt' % (name, sc)), 'w') as f:
                     f.write(buf.getvalue())
+            for (pv, dm, me) in ((2, True, 2), (1, True, 1), (2, False, 1)):
+                buf = io.StringIO()
+                with contextlib.redirect_stdout(buf):
+                    h.helm(case, detailed_run_print=True, mismatch=1e-8, scale=1.02, max_coefficients=40,
+                           pv_bus_model=pv, DSB_model=dm, DSB_model_method=me)
+                with open(os.path.join(out, 'ref_stdout_%s_ds_%d_%d_%d.txt' % (name, pv, int(dm), me)), 'w') as f:
+                    f.write(buf.getvalue())
 
 
 if __name__ == '__main__':

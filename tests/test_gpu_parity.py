@@ -322,3 +322,28 @@ def test_variant_batches_match_oracle(hb, variant):
             assert res.nswitch[b] == len(info['switched'])
             dmag, dang = polar_err(res.V[b], Vo)
             assert dmag <= TOL_MAG and dang <= TOL_ANG
+
+
+@pytest.mark.parametrize('name', ['case9', 'case118'])
+@pytest.mark.parametrize('variant', [(2, True, 2), (1, True, 1), (2, False, 1)])
+def test_distributed_slack_report_matches_reference_stdout(hb, name, variant, capsys):
+    """Report text of the distributed-slack variants (Ploss line, K-weighted generation) against the
+    unmodified reference's stdout at scale 1.02."""
+    import os, re
+    from common import GOLDEN
+    pv, dsb, method = variant
+    case = load_case(name)
+    hb.helm(case, detailed_run_print=True, mismatch=1e-8, scale=1.02, max_coefficients=40,
+            pv_bus_model=pv, DSB_model=dsb, DSB_model_method=method)
+    out = capsys.readouterr().out
+    ref = open(os.path.join(GOLDEN, 'ref_stdout_%s_ds_%d_%d_%d.txt' % (name, pv, int(dsb), method))).read()
+    ours = out[out.index('\tVoltage profile:'):]
+    theirs = ref[ref.index('\tVoltage profile:'):]
+    strip = lambda t: [' '.join(l.split()) for l in t.strip().splitlines()]
+    lo, lt = strip(ours), strip(theirs)
+    assert len(lo) == len(lt)
+    for a, b in zip(lo, lt):
+        assert re.sub(r'[-+]?\d+\.\d+', '#', a) == re.sub(r'[-+]?\d+\.\d+', '#', b)
+        na, nb = _numbers(a), _numbers(b)
+        for x, y in zip(na, nb):
+            assert abs(x - y) <= 1e-6 + 1e-9 * abs(y), (a, b)
