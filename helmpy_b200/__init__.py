@@ -4,4 +4,5 @@
 (reference helmpy/core/__init__.py:1-4) plus ``helm_batch``.
 """
 from helmpy_b200.core import *  # noqa: F401,F403
-from helmpy_b200.core import helm, helm_batch, create_case_data_object_from_xlsx, nr, nr_ds  # noqa: F401
+from helmpy_b200.core import (helm, helm_batch, non_islanding_branches,  # noqa: F401
+                              create_case_data_object_from_xlsx, nr, nr_ds)

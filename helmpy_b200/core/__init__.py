@@ -1,4 +1,4 @@
-from helmpy_b200.core.helm import helm, helm_batch
+from helmpy_b200.core.helm import helm, helm_batch, non_islanding_branches
 from helmpy_b200.core.classes import create_case_data_object_from_xlsx
 from helmpy_b200.core.nr import nr
 from helmpy_b200.core.nr import nr_ds

@@ -29,6 +29,9 @@ class GridHost(C.Structure):
         ("phase_ptr", C.c_void_p), ("phase_idx", C.c_void_p), ("phase_val", C.c_void_p),
         ("vsp", C.c_void_p), ("pg", C.c_void_p), ("pd", C.c_void_p), ("qd", C.c_void_p),
         ("qgmax", C.c_void_p), ("qgmin", C.c_void_p), ("bus_type", C.c_void_p),
+        ("n_branch", C.c_int32), ("br_from", C.c_void_p), ("br_to", C.c_void_p), ("br_y", C.c_void_p),
+        ("br_sh_from", C.c_void_p), ("br_sh_to", C.c_void_p), ("br_ph_ft", C.c_void_p),
+        ("br_ph_tf", C.c_void_p),
     ]
 
 
@@ -58,7 +61,7 @@ KERNEL_NAMES = ("assemble", "factor", "solve", "rhs_conv", "advance", "qlimit", 
 
 EXPORTED_SYMBOLS = (
     "helm_last_error", "helm_plan_create", "helm_plan_destroy", "helm_plan_get_info",
-    "helm_plan_get_perm", "helm_workspace_bytes", "helm_solve_batch_device",
+    "helm_plan_get_perm", "helm_plan_set_outages", "helm_workspace_bytes", "helm_solve_batch_device",
     "helm_solve_batch_host", "helm_last_state_host", "helm_last_ploss_host", "helm_debug_factor_solve", "helm_debug_timeline", "helm_measure_peaks",
     "helm_symbolic_create", "helm_symbolic_destroy", "helm_symbolic_array",
 )
@@ -87,6 +90,7 @@ def load():
     lib.helm_plan_destroy.restype = None
     lib.helm_plan_get_info.argtypes = [C.c_void_p, C.POINTER(PlanInfo)]
     lib.helm_plan_get_perm.argtypes = [C.c_void_p, C.c_void_p]
+    lib.helm_plan_set_outages.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
     lib.helm_workspace_bytes.argtypes = [C.c_void_p, C.c_int32, C.POINTER(Params)]
     lib.helm_workspace_bytes.restype = C.c_size_t
     lib.helm_solve_batch_device.argtypes = [
@@ -178,6 +182,18 @@ class Plan:
         for name in ("adj_ptr", "adj_idx", "ytrans", "yfull", "yshunt", "phase_ptr", "phase_idx",
                      "phase_val", "vsp", "pg", "pd", "qd", "qgmax", "qgmin", "bus_type"):
             setattr(g, name, k[name].ctypes.data)
+        bc = getattr(case, 'branch_contrib', None)
+        g.n_branch = 0
+        if bc is not None and len(bc['f']):
+            k["br_from"] = np.ascontiguousarray(bc['f'], dtype=np.int32)
+            k["br_to"] = np.ascontiguousarray(bc['t'], dtype=np.int32)
+            for name, key in (("br_y", 'y'), ("br_sh_from", 'sh_f'), ("br_sh_to", 'sh_t'),
+                              ("br_ph_ft", 'ph_ft'), ("br_ph_tf", 'ph_tf')):
+                k[name] = np.ascontiguousarray(bc[key], dtype=np.complex128)
+            g.n_branch = len(k["br_from"])
+            for name in ("br_from", "br_to", "br_y", "br_sh_from", "br_sh_to", "br_ph_ft", "br_ph_tf"):
+                setattr(g, name, k[name].ctypes.data)
+        self.n_branch = int(g.n_branch)
         self.handle = C.c_void_p()
         check(lib.helm_plan_create(C.byref(g), C.byref(self.handle)), "helm_plan_create")
         self.N = case.N
@@ -217,11 +233,17 @@ class Plan:
     def workspace_bytes(self, n_scen, params):
         return int(load().helm_workspace_bytes(self.handle, n_scen, C.byref(params)))
 
-    def solve_host(self, scales, params):
-        """Host-buffer call: numpy in, numpy out (H2D/D2H inside)."""
+    def solve_host(self, scales, params, outages=None):
+        """Host-buffer call: numpy in, numpy out (H2D/D2H inside).  ``outages[b]`` = index of the
+        branch removed in scenario b (-1: none)."""
         lib = load()
         scales = np.ascontiguousarray(scales, dtype=np.float64)
         B = len(scales)
+        if outages is not None:
+            outages = np.ascontiguousarray(outages, dtype=np.int32)
+            if len(outages) != B:
+                raise HelmB200Error("outages and scales must have the same length")
+            check(lib.helm_plan_set_outages(self.handle, B, _ptr(outages)), "helm_plan_set_outages")
         vout = np.zeros((B, self.N), dtype=np.complex128)
         status = np.zeros(B, dtype=np.int32)
         ncoef = np.zeros((B, HELM_MAX_PASSES), dtype=np.int32)

@@ -65,6 +65,9 @@ class CaseData:
         self.phase_idx = None    # int32 [nph]
         self.phase_val = None    # complex128 [nph]
         self.branch_table = None  # float64 [N_branches, >=10] raw Branches sheet
+        # per-branch contributions (for N-1 outage scenarios): what each branch added to Ytrans
+        # (series admittance y), to Yshunt at its two ends and to the phase-shifter terms
+        self.branch_contrib = None  # dict of arrays: f, t, y, sh_f, sh_t, ph_ft, ph_tf
         self._dense = {}
 
     # ---- reference API (classes.py:215-225) ---------------------------------
@@ -145,11 +148,17 @@ def _stamp_branches(case, branches, skip_branch=None):
             case.phase_barras[bus] = True
 
     nb = branches.shape[0]
+    contrib = dict(f=np.zeros(nb, dtype=np.int32), t=np.zeros(nb, dtype=np.int32),
+                   y=np.zeros(nb, dtype=np.complex128), sh_f=np.zeros(nb, dtype=np.complex128),
+                   sh_t=np.zeros(nb, dtype=np.complex128), ph_ft=np.zeros(nb, dtype=np.complex128),
+                   ph_tf=np.zeros(nb, dtype=np.complex128))
+    case.branch_contrib = contrib
     for b in range(nb):
         f = case.Number_bus[int(branches[b, 0])]
         t = case.Number_bus[int(branches[b, 1])]
         ybr = np.zeros((2, 2), dtype=np.complex128)
         case.Ybr_list.append([f, t, ybr])
+        contrib['f'][b], contrib['t'][b] = f, t
         if skip_branch is not None and b == skip_branch:
             continue   # branch outage: contributes nothing, adjacency not created
         z = branches[b, 2] + 1j * branches[b, 3]
@@ -171,16 +180,19 @@ def _stamp_branches(case, branches, skip_branch=None):
                 ybr[1, 0] = -y_tf
                 add_phase(f, t, y - y_ft)
                 add_phase(t, f, y - y_tf)
+                contrib['ph_ft'][b], contrib['ph_tf'][b] = y - y_ft, y - y_tf
             acc(ytr, f, t, -y)
             acc(ytr, f, f, y)
             acc(ytr, t, f, -y)
             acc(ytr, t, t, y)
+            contrib['y'][b] = y
         else:
             ys = y = 0
         if untapped:
             ybr[0, 0] = ybr[1, 1] = half_b + y
             Yshunt[f] += half_b
             Yshunt[t] += half_b
+            contrib['sh_f'][b] = contrib['sh_t'][b] = half_b
         else:
             sh_f = (ys + half_b) * (tap_inv * tap_inv)
             sh_t = ys + half_b
@@ -188,6 +200,7 @@ def _stamp_branches(case, branches, skip_branch=None):
             ybr[1, 1] = sh_t
             Yshunt[f] += sh_f - y
             Yshunt[t] += sh_t - y
+            contrib['sh_f'][b], contrib['sh_t'][b] = sh_f - y, sh_t - y
         if t not in adj[f]:
             adj[f].append(t)
         if f not in adj[t]:

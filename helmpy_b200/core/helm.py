@@ -90,7 +90,7 @@ class BatchResult:
 
 def helm_batch(case, scales, mismatch=1e-4, max_coefficients=100, enforce_Q_limits=True,
                group=0, use_graph=True, poll_every=0, max_resident=0,
-               pv_bus_model=2, DSB_model=False, DSB_model_method=None):
+               pv_bus_model=2, DSB_model=False, DSB_model_method=None, outages=None):
     """Solve ``len(scales)`` load-scaling scenarios of ``case`` on the current GPU.
 
     Scenario b equals ``helm(case, scale=scales[b], mismatch=..., ...)``
@@ -98,6 +98,11 @@ def helm_batch(case, scales, mismatch=1e-4, max_coefficients=100, enforce_Q_limi
     mutated.  Host buffers in, host buffers out.  At most ``max_resident`` scenarios
     (default 4096) hold GPU state at a time; the rest of the batch queues and takes
     over slots as scenarios finish, so device memory does not grow with the batch.
+
+    N-1 scenarios: ``outages[b]`` = row of the Branches sheet removed in scenario b
+    (-1: none); equals ``helm`` on a case loaded without that branch.  Outages that
+    island part of the grid (``non_islanding_branches`` lists the safe ones) end with
+    status 3/4, as a singular system would.
     """
     plan = get_plan(case)
     if DSB_model and DSB_model_method is None:
@@ -105,7 +110,9 @@ def helm_batch(case, scales, mismatch=1e-4, max_coefficients=100, enforce_Q_limi
     prm = _lib.Plan.make_params(mismatch, max_coefficients, enforce_Q_limits, group, use_graph,
                                 poll_every, max_resident, pv_bus_model, DSB_model_method or 0,
                                 DSB_model)
-    V, status, ncoef, nswitch, stats = plan.solve_host(np.asarray(scales, dtype=np.float64), prm)
+    if scales is None:
+        scales = np.ones(len(outages))
+    V, status, ncoef, nswitch, stats = plan.solve_host(np.asarray(scales, dtype=np.float64), prm, outages)
     return BatchResult(V, status, ncoef, nswitch, stats)
 
 
@@ -152,3 +159,58 @@ def helm(case, detailed_run_print=False, mismatch=1e-4, scale=1, max_coefficient
                          detailed_run_print=detailed_run_print, save_results=save_results,
                          results_file_name=results_file_name, DSB_model=DSB_model, ploss_series=ploss)
     return V
+
+
+def non_islanding_branches(case):
+    """Rows of the Branches sheet whose removal keeps the grid connected (no bridge).
+
+    A branch with a parallel twin is never a bridge; the rest are checked with one
+    DFS low-link pass over the bus graph (host code, O(N + branches)).
+    """
+    import sys
+    f = np.asarray(case.branch_contrib['f'])
+    t = np.asarray(case.branch_contrib['t'])
+    N = case.N
+    mult = {}
+    for b in range(len(f)):
+        key = (min(f[b], t[b]), max(f[b], t[b]))
+        mult[key] = mult.get(key, 0) + 1
+    adj = [[] for _ in range(N)]
+    for (a, c) in mult:
+        if a != c:
+            adj[a].append(c)
+            adj[c].append(a)
+    disc = [-1] * N
+    low = [0] * N
+    bridges = set()
+    timer = 0
+    for root in range(N):
+        if disc[root] != -1:
+            continue
+        stack = [(root, -1, 0)]
+        disc[root] = low[root] = timer
+        timer += 1
+        while stack:
+            v, parent, idx = stack.pop()
+            if idx < len(adj[v]):
+                stack.append((v, parent, idx + 1))
+                u = adj[v][idx]
+                if u == parent:
+                    continue
+                if disc[u] == -1:
+                    disc[u] = low[u] = timer
+                    timer += 1
+                    stack.append((u, v, 0))
+                else:
+                    low[v] = min(low[v], disc[u])
+            else:
+                if parent >= 0:
+                    low[parent] = min(low[parent], low[v])
+                    if low[v] > disc[parent]:
+                        bridges.add((min(v, parent), max(v, parent)))
+    out = []
+    for b in range(len(f)):
+        key = (min(f[b], t[b]), max(f[b], t[b]))
+        if mult[key] > 1 or key not in bridges:
+            out.append(b)
+    return np.asarray(out, dtype=np.int32)

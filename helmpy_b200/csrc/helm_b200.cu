@@ -59,6 +59,10 @@ struct PlanDev {
     const int *urow, *ulev_ptr, *uptr, *ucol, *dslot;
     const int *slot_src, *slot_row, *slot_col;
     double pg_imb0;   // sum(Pd) - sum(Pg) of the unscaled case (classes.py:286)
+    // branch table for N-1 outage scenarios (elimination numbering)
+    int n_branch;
+    const int *br_f, *br_t, *br_a, *br_p;   // br_a[4b..]: adjacency entries (f,t),(t,f),(f,f),(t,t); br_p[2b..]: phase entries
+    const double *br_val;                   // [10b..]: y, sh_f, sh_t, ph_ft, ph_tf (complex)
     const int *fptr, *fsrc, *fdst, *fdstl, *qof;
     const int *fchunk_row, *fchunk_lpr, *frow_off;
     const int *sstep_kind, *sstep_a, *sstep_b, *sring_desc;
@@ -77,6 +81,8 @@ struct WorkDev {
     int *queue_next;                  // [1] next scenario of the queue to be given a slot
     int *slot_scen;                   // [Bp] scenario currently held by a slot (-1: none)
     const double *scale_in;           // [B] scenario scales (queue)
+    const int *outage_in;             // [B] removed branch per scenario (or null)
+    int *o_b;                         // [Bp] removed branch of the scenario in the slot (-1: none)
     int *out_status, *out_ncoef, *out_nswitch;   // per-scenario outputs, written when a scenario ends
     unsigned char *btype;             // [group][N][G]
     double *Qg, *VVant;               // [group][N][G]
@@ -150,6 +156,11 @@ __device__ __forceinline__ double2 crecip_guard(double2 d) {
     return make_double2(d.x * inv, -d.y * inv);
 }
 
+// ---- N-1 outage scenarios: the network of a scenario is the base network minus what one branch
+// contributed (classes.py:9-113).  Kernels read the shared base arrays and correct the few
+// entries the removed branch touches.
+struct OutageRef { int b, f, t; };
+
 template <int G>
 __device__ __forceinline__ size_t ix(int grp, int count, int item, int s) {
     return ((size_t)grp * count + item) * G + s;
@@ -157,6 +168,59 @@ __device__ __forceinline__ size_t ix(int grp, int count, int item, int s) {
 template <int G>
 __device__ __forceinline__ size_t hx(const WorkDev &w, int N, int grp, int k, int i, int s) {
     return (((size_t)grp * w.K + k) * N + i) * G + s;
+}
+
+__device__ __forceinline__ OutageRef load_outage(const PlanDev &p, const WorkDev &w, int sg) {
+    OutageRef o{w.o_b[sg], -1, -1};
+    if (o.b >= 0) { o.f = p.br_f[o.b]; o.t = p.br_t[o.b]; }
+    return o;
+}
+__device__ __forceinline__ double2 br_value(const PlanDev &p, int b, int k) {   // k: 0 y, 1 sh_f, 2 sh_t, 3 ph_ft, 4 ph_tf
+    return make_double2(p.br_val[(size_t)b * 10 + 2 * k], p.br_val[(size_t)b * 10 + 2 * k + 1]);
+}
+__device__ __forceinline__ double2 ytr_eff(const PlanDev &p, const OutageRef &o, int a) {
+    double2 y = p.ytr[a];
+    if (o.b >= 0) {
+        const int *ai = p.br_a + (size_t)o.b * 4;
+        double2 dy = br_value(p, o.b, 0);
+        if (a == ai[0] || a == ai[1]) y = cadd(y, dy);           // off-diagonal was -y
+        else if (a == ai[2] || a == ai[3]) y = csub(y, dy);      // diagonal was +y
+    }
+    return y;
+}
+__device__ __forceinline__ double2 ysh_eff(const PlanDev &p, const OutageRef &o, int i) {
+    double2 y = p.yshunt[i];
+    if (o.b >= 0) {
+        if (i == o.f) y = csub(y, br_value(p, o.b, 1));
+        if (i == o.t) y = csub(y, br_value(p, o.b, 2));
+    }
+    return y;
+}
+__device__ __forceinline__ double2 ph_eff(const PlanDev &p, const OutageRef &o, int a) {
+    double2 v = p.ph_val[a];
+    if (o.b >= 0) {
+        if (a == p.br_p[2 * o.b]) v = csub(v, br_value(p, o.b, 3));
+        else if (a == p.br_p[2 * o.b + 1]) v = csub(v, br_value(p, o.b, 4));
+    }
+    return v;
+}
+// full Y = Ytrans + diag(Yshunt) + phase (classes.py:168-175) of the scenario, adjacency entry a = (i, col)
+__device__ __forceinline__ double2 yfull_eff(const PlanDev &p, const OutageRef &o, int a, int i, int col) {
+    double2 y = p.yfull[a];
+    if (o.b >= 0 && (i == o.f || i == o.t)) {
+        const int *ai = p.br_a + (size_t)o.b * 4;
+        double2 dy = br_value(p, o.b, 0);
+        if (a == ai[0]) y = csub(cadd(y, dy), br_value(p, o.b, 3));
+        else if (a == ai[1]) y = csub(cadd(y, dy), br_value(p, o.b, 4));
+        else if (a == ai[2] || a == ai[3]) {
+            y = csub(y, dy);
+            if (col == i) {
+                if (i == o.f) y = csub(y, br_value(p, o.b, 1));
+                if (i == o.t) y = csub(y, br_value(p, o.b, 2));
+            }
+        }
+    }
+    return y;
 }
 
 // ---- K_asm: scatter A into the LU slots (reference helm.py:46-60) -------------------
@@ -190,7 +254,7 @@ __global__ void __launch_bounds__(256) k_assemble(PlanDev p, WorkDev w) {
         if (bt == HELM_BUS_SLACK) {
             if (diag) { r0.x = 1.0; r1.y = 1.0; }                         // helm.py:47-49
         } else if (a >= 0) {
-            double2 y = p.ytr[a];
+            double2 y = ytr_eff(p, load_outage(p, w, grp * G + s), a);
             r0 = make_double2(y.x, -y.y);                                 // helm.py:52-53 / 59-60
             if (bt == HELM_BUS_PQ || w.pv_model == 1) r1 = make_double2(y.y, y.x);   // helm.py:50-55
             else if (diag) r1 = make_double2(1.0, 0.0);                   // helm.py:57
@@ -887,6 +951,7 @@ __global__ void k_init(PlanDev p, WorkDev w) {
     w.Hh[hx<G>(w, N, grp, 0, i, s)] = one;     // W[0] = 1
     w.Eh[hx<G>(w, N, grp, 0, i, s)] = one;     // partial sum S_0
     w.VVant[bi] = 0.0;
+    const OutageRef og = load_outage(p, w, sg);
     double2 r;
     if (bt == HELM_BUS_SLACK) {
         r = make_double2(p.vsp[i] - 1.0, 0.0);                                   // helm.py:393-394
@@ -895,12 +960,12 @@ __global__ void k_init(PlanDev p, WorkDev w) {
         double Pi = p.pg[i] * sc - p.pd[i] * sc;
         double Qi = w.Qg[bi] - p.qd[i] * sc;
         double2 pp = make_double2(0.0, 0.0);
-        for (int a = p.ph_ptr[i]; a < p.ph_ptr[i + 1]; ++a) pp = cadd(pp, p.ph_val[a]);
-        double2 ysh = p.yshunt[i];
+        for (int a = p.ph_ptr[i]; a < p.ph_ptr[i + 1]; ++a) pp = cadd(pp, ph_eff(p, og, a));
+        double2 ysh = ysh_eff(p, og, i);
         r = make_double2(Pi - ysh.x - pp.x, -Qi - ysh.y - pp.y);
     } else {
-        double cc = (p.pg[i] * sc - p.pd[i] * sc) - p.yshunt[i].x;               // helm.py:347-352
-        for (int a = p.ph_ptr[i]; a < p.ph_ptr[i + 1]; ++a) cc -= p.ph_val[a].x;
+        double cc = (p.pg[i] * sc - p.pd[i] * sc) - ysh_eff(p, og, i).x;         // helm.py:347-352
+        for (int a = p.ph_ptr[i]; a < p.ph_ptr[i + 1]; ++a) cc -= ph_eff(p, og, a).x;
         double vs = p.vsp[i];
         r = make_double2(cc, (vs * vs - 1.0) * 0.5);                             // helm.py:354-355, 364
     }
@@ -962,11 +1027,18 @@ __global__ void __launch_bounds__(256) k_rhs_conv(PlanDev p, WorkDev w) {
     const double sc = w.scale[sg];
     const double qg = w.Qg[bi];
     const double pgi = p.pg[i], pdi = p.pd[i], qdi = p.qd[i];
-    const double2 ysh = p.yshunt[i];
+    double2 ysh = p.yshunt[i];
+    const int ob = w.o_b[sg];
     const int ph0 = p.ph_ptr[i], ph1 = p.ph_ptr[i + 1];
     const int a0 = p.adj_ptr[i], a1 = p.adj_ptr[i + 1];
     if (gf & (GF_DONE | GF_PASSEND | GF_FACTORING)) return;
     if (status != ST_ACTIVE) return;
+    // N-1 scenario: only the two end buses of the removed branch see different admittances
+    OutageRef og{-1, -1, -1};
+    if (ob >= 0) {
+        OutageRef t_ = load_outage(p, w, sg);
+        if (i == t_.f || i == t_.t) { og = t_; ysh = ysh_eff(p, og, i); }
+    }
     Vb[(size_t)j * plane] = v;                                                    // helm.py:412-414
     if (bt == HELM_BUS_SLACK) {
         w.rhs[bi] = make_double2(0.0, 0.0);                                       // helm.py:395-397
@@ -1008,7 +1080,7 @@ __global__ void __launch_bounds__(256) k_rhs_conv(PlanDev p, WorkDev w) {
         double Qi = qg - qdi * sc;
         double2 pp = zero;
         for (int a = ph0; a < ph1; ++a)
-            pp = cadd(pp, cmul(p.ph_val[a], xb[(size_t)p.ph_idx[a] * G + s]));
+            pp = cadd(pp, cmul(ph_eff(p, og, a), xb[(size_t)p.ph_idx[a] * G + s]));
         double2 tt = cmul(make_double2(Pi, -Qi), make_double2(wj.x, -wj.y));
         double2 ysv = cmul(ysh, v);
         out = make_double2(tt.x - ysv.x - pp.x, tt.y - ysv.y - pp.y);
@@ -1016,7 +1088,7 @@ __global__ void __launch_bounds__(256) k_rhs_conv(PlanDev p, WorkDev w) {
         // PV bus, model 2 (helm.py:293-364); n = j+1 >= 2
         double2 PP = zero;
         for (int a = a0; a < a1; ++a)
-            PP = cadd(PP, cmul(p.ytr[a], xb[(size_t)p.adj_idx[a] * G + s]));      // helm.py:310-312
+            PP = cadd(PP, cmul(ytr_eff(p, og, a), xb[(size_t)p.adj_idx[a] * G + s]));   // helm.py:310-312
         Hb[(size_t)j * plane] = PP;                                               // barras_CC[i][n-1]
         double2 ppp = zero;
         double vvre = 0.0;
@@ -1054,7 +1126,7 @@ __global__ void __launch_bounds__(256) k_rhs_conv(PlanDev p, WorkDev w) {
                 for (int a = ph0; a < ph1; ++a) {
                     int k = p.ph_idx[a];
                     double2 vk = (x == 0) ? xb[(size_t)k * G + s] : w.Vh[hx<G>(w, N, grp, j - x, k, s)];
-                    pp = cadd(pp, cmul(p.ph_val[a], vk));
+                    pp = cadd(pp, cmul(ph_eff(p, og, a), vk));
                 }
                 double2 vx = (x == j) ? v : Vb[(size_t)x * plane];
                 acc = cadd(acc, cmulc(pp, vx));
@@ -1127,9 +1199,10 @@ __global__ void k_qlimit(PlanDev p, WorkDev w) {
     if (!w.enforce_q) return;
     if (w.btype[bi] != HELM_BUS_PV) return;
     const double2 *pc = w.Pcur + (size_t)grp * N * G;
+    const OutageRef og = load_outage(p, w, sg);
     double q = 0.0;
     for (int a = p.adj_ptr[i]; a < p.adj_ptr[i + 1]; ++a) {                       // helm.py:461-464
-        double2 y = p.yfull[a];
+        double2 y = yfull_eff(p, og, a, i, p.adj_idx[a]);
         double2 vk = pc[(size_t)p.adj_idx[a] * G + s];
         q += vi.y * (y.x * vk.x - y.y * vk.y) - vi.x * (y.x * vk.y + y.y * vk.x);
     }
@@ -1192,6 +1265,7 @@ __global__ void k_pass_end(WorkDev w) {
             if (next < w.B) {
                 w.slot_scen[sg] = next;
                 w.scale[sg] = w.scale_in[next];
+                w.o_b[sg] = w.outage_in ? w.outage_in[next] : -1;
                 w.s_status[sg] = ST_ACTIVE;
                 w.s_mconv[sg] = 0; w.s_fail[sg] = 0; w.s_viol[sg] = 0; w.s_npass[sg] = 0; w.s_nswitch[sg] = 0;
                 for (int k = 0; k < HELM_MAX_PASSES; ++k) w.s_ncoef[sg * HELM_MAX_PASSES + k] = 0;
@@ -1246,6 +1320,7 @@ __global__ void k_setup(PlanDev p, WorkDev w, const double *scale_in) {
         bool real = sg < w.B;
         w.scale[sg] = real ? scale_in[sg] : 1.0;
         w.slot_scen[sg] = real ? sg : -1;
+        w.o_b[sg] = (real && w.outage_in) ? w.outage_in[sg] : -1;
         w.s_status[sg] = real ? ST_ACTIVE : ST_PAD;
         w.s_mconv[sg] = 0; w.s_fail[sg] = 0; w.s_viol[sg] = 0; w.s_npass[sg] = 0; w.s_nswitch[sg] = 0;
         for (int k = 0; k < HELM_MAX_PASSES; ++k) w.s_ncoef[sg * HELM_MAX_PASSES + k] = 0;
@@ -1300,6 +1375,8 @@ struct helm_plan {
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     unsigned long long *tl = nullptr;
+    int *d_outage = nullptr;      // pending N-1 list for the next solve (helm_plan_set_outages)
+    int outage_n = 0;
     int last_B = 0, last_G = 0, last_maxcoef = 0, last_resident = 0, last_dsb = 0, last_pv = 0;   // layout of the last host-buffer solve
 };
 
@@ -1346,7 +1423,7 @@ WsLayout layout(const helm_plan *pl, int B, const helm_params *prm) {
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes); return r; };
     L.off_scale = take(sizeof(double) * L.Bp);
-    L.off_sint = take(sizeof(int) * L.Bp * (7 + HELM_MAX_PASSES));
+    L.off_sint = take(sizeof(int) * L.Bp * (8 + HELM_MAX_PASSES));
     L.off_gint = take(sizeof(int) * (2 * L.ngroups + 4));
     L.off_btype = take(per);
     L.off_Qg = take(per * sizeof(double));
@@ -1381,10 +1458,10 @@ WorkDev bind(const helm_plan *pl, const WsLayout &L, int B, const helm_params *p
     w.scale = (double *)(b + L.off_scale);
     int *si = (int *)(b + L.off_sint);
     w.s_status = si; w.s_mconv = si + L.Bp; w.s_fail = si + 2 * L.Bp; w.s_viol = si + 3 * L.Bp;
-    w.s_npass = si + 4 * L.Bp; w.s_nswitch = si + 5 * L.Bp; w.slot_scen = si + 6 * L.Bp; w.s_ncoef = si + 7 * L.Bp;
+    w.s_npass = si + 4 * L.Bp; w.s_nswitch = si + 5 * L.Bp; w.slot_scen = si + 6 * L.Bp; w.o_b = si + 7 * L.Bp; w.s_ncoef = si + 8 * L.Bp;
     int *gi = (int *)(b + L.off_gint);
     w.g_n = gi; w.g_flags = gi + L.ngroups; w.active_groups = gi + 2 * L.ngroups; w.queue_next = gi + 2 * L.ngroups + 1;
-    w.scale_in = nullptr; w.out_status = nullptr; w.out_ncoef = nullptr; w.out_nswitch = nullptr;
+    w.scale_in = nullptr; w.outage_in = nullptr; w.out_status = nullptr; w.out_ncoef = nullptr; w.out_nswitch = nullptr;
     w.btype = (unsigned char *)(b + L.off_btype);
     w.Qg = (double *)(b + L.off_Qg);
     w.VVant = (double *)(b + L.off_VVant);
@@ -1622,6 +1699,35 @@ int helm_plan_create(const helm_grid_host *g, helm_plan **out) {
         }
         php[r + 1] = (int)phi.size();
     }
+    // branch table (N-1 scenarios): bus indices and adjacency / phase entries in the new numbering
+    std::vector<int> br_f, br_t, br_a, br_p;
+    std::vector<double> br_val;
+    d.n_branch = (g->n_branch > 0 && g->br_from && g->br_to && g->br_y) ? g->n_branch : 0;
+    if (d.n_branch) {
+        auto find_adj = [&](int r, int c) -> int {
+            for (int a = S.adj_ptr[r]; a < S.adj_ptr[r + 1]; ++a)
+                if (S.adj_idx[a] == c) return a;
+            return -1;
+        };
+        auto find_ph = [&](int r, int c) -> int {
+            for (int a = php[r]; a < php[r + 1]; ++a)
+                if (phi[a] == c) return a;
+            return -1;
+        };
+        for (int b = 0; b < d.n_branch; ++b) {
+            int f = S.iperm[g->br_from[b]], t = S.iperm[g->br_to[b]];
+            br_f.push_back(f);
+            br_t.push_back(t);
+            br_a.push_back(find_adj(f, t)); br_a.push_back(find_adj(t, f));
+            br_a.push_back(find_adj(f, f)); br_a.push_back(find_adj(t, t));
+            br_p.push_back(find_ph(f, t)); br_p.push_back(find_ph(t, f));
+            const double *src[5] = {g->br_y, g->br_sh_from, g->br_sh_to, g->br_ph_ft, g->br_ph_tf};
+            for (int k = 0; k < 5; ++k) {
+                br_val.push_back(src[k] ? src[k][2 * b] : 0.0);
+                br_val.push_back(src[k] ? src[k][2 * b + 1] : 0.0);
+            }
+        }
+    }
     int rc;
 #define UP(vec, field) if ((rc = upload(pl, vec, &d.field)) != HELM_OK) { helm_plan_destroy(pl); return rc; }
     UP(S.adj_ptr, adj_ptr) UP(S.adj_idx, adj_idx) UP(S.adj_slot, adj_slot)
@@ -1631,6 +1737,7 @@ int helm_plan_create(const helm_grid_host *g, helm_plan **out) {
     UP(S.perm, perm) UP(S.lptr, lptr) UP(S.lcol, lcol) UP(S.llev_ptr, llev_ptr)
     UP(S.urow, urow) UP(S.ulev_ptr, ulev_ptr) UP(S.uptr, uptr) UP(S.ucol, ucol) UP(S.dslot, dslot)
     UP(S.slot_src, slot_src) UP(S.slot_row, slot_row) UP(S.slot_col, slot_col)
+    UP(br_f, br_f) UP(br_t, br_t) UP(br_a, br_a) UP(br_p, br_p) UP(br_val, br_val)
     UP(S.fptr, fptr) UP(S.fsrc, fsrc) UP(S.fdst, fdst) UP(S.fdst_local, fdstl) UP(S.qof, qof)
     UP(S.fchunk_row, fchunk_row) UP(S.fchunk_lpr, fchunk_lpr) UP(S.frow_off, frow_off)
     UP(S.sstep_kind, sstep_kind) UP(S.sstep_a, sstep_a) UP(S.sstep_b, sstep_b) UP(S.sring_desc, sring_desc)
@@ -1676,6 +1783,7 @@ void helm_plan_destroy(helm_plan *pl) {
     if (pl->d_nswitch) cudaFree(pl->d_nswitch);
     if (pl->h_pinned) cudaFreeHost(pl->h_pinned);
     if (pl->h_vout_pinned) cudaFreeHost(pl->h_vout_pinned);
+    if (pl->d_outage) cudaFree(pl->d_outage);
     if (pl->stream) cudaStreamDestroy(pl->stream);
     if (pl->side) cudaStreamDestroy(pl->side);
     if (pl->ev_fork) cudaEventDestroy(pl->ev_fork);
@@ -1695,6 +1803,18 @@ int helm_plan_get_info(const helm_plan *pl, helm_plan_info *info) {
 int helm_plan_get_perm(const helm_plan *pl, int32_t *perm_out) {
     if (!pl || !perm_out) { g_err = "null argument"; return HELM_E_ARG; }
     std::copy(pl->S.perm.begin(), pl->S.perm.end(), perm_out);
+    return HELM_OK;
+}
+
+int helm_plan_set_outages(helm_plan *pl, int32_t n, const int32_t *h_outage) {
+    if (!pl || n <= 0 || !h_outage) { g_err = "null/invalid argument"; return HELM_E_ARG; }
+    if (pl->d.n_branch <= 0) { g_err = "the plan was created without a branch table"; return HELM_E_ARG; }
+    for (int b = 0; b < n; ++b)
+        if (h_outage[b] < -1 || h_outage[b] >= pl->d.n_branch) { g_err = "outage branch index out of range"; return HELM_E_ARG; }
+    if (pl->d_outage) { cudaFree(pl->d_outage); pl->d_outage = nullptr; }
+    CUDA_TRY(cudaMalloc((void **)&pl->d_outage, sizeof(int) * n));
+    CUDA_TRY(cudaMemcpy(pl->d_outage, h_outage, sizeof(int) * n, cudaMemcpyHostToDevice));
+    pl->outage_n = n;
     return HELM_OK;
 }
 
@@ -1723,6 +1843,10 @@ int helm_solve_batch_device(helm_plan *pl, int32_t B, const double *d_scale, con
     if (ws_bytes < L.total) { g_err = "workspace too small"; return HELM_E_NOMEM; }
     cudaStream_t st = (cudaStream_t)stream_;
     WorkDev w = bind(pl, L, B, prm, d_ws, d_vout);
+    if (pl->d_outage && pl->outage_n == B) {
+        if (prm->dsb_method || prm->pv_bus_model == 1) { g_err = "outage scenarios need pv_bus_model 2 and the classic slack"; return HELM_E_ARG; }
+        w.outage_in = pl->d_outage;
+    }
     w.scale_in = d_scale; w.out_status = d_status; w.out_ncoef = d_ncoef; w.out_nswitch = d_nswitch;
     const PlanDev &p = pl->d;
     const bool profile = getenv("HELM_B200_PROFILE") != nullptr;
@@ -1810,6 +1934,7 @@ int helm_solve_batch_device(helm_plan *pl, int32_t B, const double *d_scale, con
     for (auto &e : pev) cudaEventDestroy(e);
     if (gexec) cudaGraphExecDestroy(gexec);
     if (graph) cudaGraphDestroy(graph);
+    if (pl->d_outage) { cudaFree(pl->d_outage); pl->d_outage = nullptr; pl->outage_n = 0; }   // consumed
     CUDA_TRY(cudaGetLastError());
     if (stats) *stats = local;
     return HELM_OK;

@@ -69,6 +69,16 @@ typedef struct helm_grid_host {
     const double *qgmax;        /* [n_bus]                                      */
     const double *qgmin;        /* [n_bus]                                      */
     const uint8_t *bus_type;    /* [n_bus] HELM_BUS_*                           */
+    /* optional: what every branch contributed to the network (classes.py:9-113), needed only for
+     * N-1 branch-outage scenarios; n_branch = 0 disables them */
+    int32_t n_branch;
+    const int32_t *br_from;     /* [n_branch] bus index                         */
+    const int32_t *br_to;       /* [n_branch]                                   */
+    const double *br_y;         /* [n_branch] complex: series admittance stamped into Ytrans */
+    const double *br_sh_from;   /* [n_branch] complex: added to Yshunt[from]    */
+    const double *br_sh_to;     /* [n_branch] complex: added to Yshunt[to]      */
+    const double *br_ph_ft;     /* [n_branch] complex: phase term of (from, to) */
+    const double *br_ph_tf;     /* [n_branch] complex: phase term of (to, from) */
 } helm_grid_host;
 
 typedef struct helm_params {
@@ -119,6 +129,11 @@ void helm_plan_destroy(helm_plan *plan);
 int helm_plan_get_info(const helm_plan *plan, helm_plan_info *info);
 /* elimination order: perm[new index] = original bus index; buffer of n_bus */
 int helm_plan_get_perm(const helm_plan *plan, int32_t *perm_out);
+
+/* N-1 scenarios: branch removed in scenario b of the NEXT helm_solve_batch_* call with the same
+ * n_scen (h_outage[b] = branch index into the grid's branch table, or -1 for none).  The list is
+ * consumed by that call.  Only the default variant (pv_bus_model 2, classic slack). */
+int helm_plan_set_outages(helm_plan *plan, int32_t n_scen, const int32_t *h_outage);
 
 /* bytes of device workspace needed for n_scen scenarios */
 size_t helm_workspace_bytes(const helm_plan *plan, int32_t n_scen, const helm_params *params);

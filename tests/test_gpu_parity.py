@@ -347,3 +347,33 @@ def test_distributed_slack_report_matches_reference_stdout(hb, name, variant, ca
         na, nb = _numbers(a), _numbers(b)
         for x, y in zip(na, nb):
             assert abs(x - y) <= 1e-6 + 1e-9 * abs(y), (a, b)
+
+
+@pytest.mark.parametrize('name', ['case118', 'case1354pegase'])
+def test_n_minus_1_outages_match_oracle(hb, name):
+    """BASELINE config 5 shape (N-1 branch-outage sweep, per-scenario refactorization): scenario b
+    removes one branch; equals the oracle on a case loaded without that branch (tap branches,
+    phase shifters and parallel twins included)."""
+    from common import load_tables
+    from helmpy_b200.core.classes import create_case_data_object_from_arrays
+    case = load_case(name)
+    b_, br_, g_ = load_tables(name)
+    safe = hb.non_islanding_branches(case)
+    assert 0 < len(safe) < case.N_branches or name == 'case118'
+    rng = np.random.default_rng(2)
+    picks = list(rng.choice(safe, size=10, replace=False))
+    taps = [k for k in safe if br_[k, 8] not in (0, 1)][:2]
+    shifters = [k for k in safe if br_[k, 9] != 0][:2]
+    outages = np.array([-1] + picks + taps + shifters, dtype=np.int32)
+    scales = np.full(len(outages), 1.0)
+    scales[3] = 0.9
+    res = hb.helm_batch(case, scales, mismatch=1e-8, max_coefficients=40, outages=outages, max_resident=6)
+    for k, ob in enumerate(outages):
+        c2 = case if ob < 0 else create_case_data_object_from_arrays(b_, br_, g_, name, skip_branch=int(ob))
+        Vo, info = ho.helm_oracle(c2, mismatch=1e-8, scale=scales[k], max_coefficients=40)
+        assert bool(res.converged[k]) == (Vo is not None), (k, ob)
+        if Vo is not None:
+            assert res.list_coef(k) == info['list_coef'], (k, ob)
+            assert res.nswitch[k] == len(info['switched'])
+            dmag, dang = polar_err(res.V[k], Vo)
+            assert dmag <= TOL_MAG and dang <= TOL_ANG, (k, ob, dmag, dang)

@@ -155,3 +155,20 @@ def test_branch_flows_match_golden_results(name):
     assert P.shape == ref.shape
     assert np.array_equal(P[:, :2], ref[:, :2])
     assert np.max(np.abs(P[:, 2:] - ref[:, 2:])) < 1e-6      # MW / MVAr
+
+
+def test_non_islanding_branches():
+    """Bridge detection for the N-1 sweep: removing a listed branch keeps the bus graph connected,
+    removing an unlisted one splits it."""
+    import helmpy_b200
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    case = load_case('case118')
+    safe = set(int(b) for b in helmpy_b200.non_islanding_branches(case))
+    f, t = case.branch_contrib['f'], case.branch_contrib['t']
+    nb = len(f)
+    for b in range(nb):
+        keep = [k for k in range(nb) if k != b]
+        A = coo_matrix((np.ones(len(keep)), (f[keep], t[keep])), shape=(case.N, case.N))
+        ncomp, _ = connected_components(A, directed=False)
+        assert (ncomp == 1) == (b in safe), b
