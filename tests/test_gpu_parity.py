@@ -377,3 +377,38 @@ def test_n_minus_1_outages_match_oracle(hb, name):
             assert res.nswitch[k] == len(info['switched'])
             dmag, dang = polar_err(res.V[k], Vo)
             assert dmag <= TOL_MAG and dang <= TOL_ANG, (k, ob, dmag, dang)
+
+
+def test_edge_cases_and_errors(hb):
+    """Degenerate inputs: one-scenario batches, empty outage list entries, a two-bus grid, bad
+    arguments at the C ABI (error codes, no crash)."""
+    from helmpy_b200.core import _lib
+    from helmpy_b200.core.classes import create_case_data_object_from_arrays
+    # two-bus grid: slack + one load, no generators besides the slack
+    buses = np.array([[1, 3, 0, 0, 0, 0, 1, 1, 0, 100, 1, 1.1, 0.9],
+                      [2, 1, 50, 20, 0, 0, 1, 1, 0, 100, 1, 1.1, 0.9]], dtype=float)
+    branches = np.array([[1, 2, 0.01, 0.1, 0.02, 0, 0, 0, 0, 0, 1, -360, 360]], dtype=float)
+    gens = np.zeros((1, 21)); gens[0, 0] = 1; gens[0, 3] = 300; gens[0, 4] = -300; gens[0, 5] = 1.02
+    case = create_case_data_object_from_arrays(buses, branches, gens, 'two_bus')
+    res = hb.helm_batch(case, [1.0, 0.5], mismatch=1e-8, max_coefficients=40)
+    assert res.converged.all()
+    for b, s in enumerate([1.0, 0.5]):
+        Vo, info = ho.helm_oracle(case, mismatch=1e-8, scale=s, max_coefficients=40)
+        assert res.list_coef(b) == info['list_coef']
+        assert np.max(np.abs(res.V[b] - Vo)) < 1e-10
+    assert abs(res.V[0][0] - 1.02) == 0
+    # too heavy a load: no solution -> status 3, helm() returns None
+    res = hb.helm_batch(case, [40.0], mismatch=1e-8, max_coefficients=20)
+    assert res.status[0] == 3
+    # C-ABI argument errors
+    plan = hb.core.helm.get_plan(case) if hasattr(hb.core, 'helm') and not callable(hb.core.helm) else None
+    from helmpy_b200.core.helm import get_plan
+    plan = get_plan(case)
+    with pytest.raises(_lib.HelmB200Error):
+        plan.solve_host(np.array([1.0]), _lib.Plan.make_params(1e-8, 4, True))        # max_coefficients < 5
+    with pytest.raises(_lib.HelmB200Error):
+        plan.solve_host(np.array([1.0]), _lib.Plan.make_params(-1.0, 40, True))       # mismatch <= 0
+    with pytest.raises(_lib.HelmB200Error):
+        plan.solve_host(np.array([1.0]), _lib.Plan.make_params(1e-8, 40, True), outages=np.array([5]))
+    with pytest.raises(_lib.HelmB200Error):
+        plan.solve_host(np.array([1.0]), _lib.Plan.make_params(1e-8, 40, True, dsb_method=0, dsb_model=True))
