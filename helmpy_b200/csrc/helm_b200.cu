@@ -83,6 +83,11 @@ struct WorkDev {
     const double *scale_in;           // [B] scenario scales (queue)
     const int *outage_in;             // [B] removed branch per scenario (or null)
     int *o_b;                         // [Bp] removed branch of the scenario in the slot (-1: none)
+    // groups being factorized in the current step, compacted by k_step_begin (double-buffered by
+    // step parity) so that the side-branch kernels launch only as many CTAs as there is work
+    int *fact_list;                   // [2][ngroups]
+    int *fact_count;                  // [2]
+    int parity;                       // parity of the current step (host-set per launch)
     int *out_status, *out_ncoef, *out_nswitch;   // per-scenario outputs, written when a scenario ends
     unsigned char *btype;             // [group][N][G]
     double *Qg, *VVant;               // [group][N][G]
@@ -228,9 +233,10 @@ __device__ __forceinline__ double2 yfull_eff(const PlanDev &p, const OutageRef &
 template <int G>
 __global__ void __launch_bounds__(256) k_assemble(PlanDev p, WorkDev w) {
     TL_SCOPE(w, 0);
-    int grp = blockIdx.x;
+  const int nfact = w.fact_count[w.parity];
+  for (int fi = blockIdx.x; fi < nfact; fi += gridDim.x) {
+    const int grp = w.fact_list[(size_t)w.parity * w.ngroups + fi];
     const int gflags = w.g_flags[grp];
-    if (!(gflags & GF_FACTORING)) return;
     if (gflags & GF_NEWSCEN) {      // slots refilled from the queue: fresh per-bus state (classes.py:230-297)
         for (int flat = threadIdx.x; flat < p.N * G; flat += blockDim.x) {
             int i = flat / G, s = flat % G;
@@ -271,6 +277,8 @@ __global__ void __launch_bounds__(256) k_assemble(PlanDev p, WorkDev w) {
         dst[0] = r0;
         dst[1] = r1;
     }
+    __syncthreads();
+  }
 }
 
 struct Blk { double a, b, c, d; };  // [[a b][c d]]
@@ -396,12 +404,12 @@ template <int WPB>
 __global__ void __launch_bounds__(WPB * 32) k_factor_coop(PlanDev p, WorkDev w) {
     TL_SCOPE(w, 1);
     extern __shared__ double2 smem_f[];
-    int wib = threadIdx.x >> 5;
-    int grp = blockIdx.x * WPB + wib;
-    if (grp >= w.ngroups) return;
-    if (!(w.g_flags[grp] & GF_FACTORING)) return;
-    int lane = threadIdx.x & 31;
-    if (w.s_status[grp] != ST_ACTIVE) return;               // G = 1: warp-uniform
+    const int wib = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int nfact = w.fact_count[w.parity];
+  for (int fi = blockIdx.x * WPB + wib; fi < nfact; fi += gridDim.x * WPB) {
+    const int grp = w.fact_list[(size_t)w.parity * w.ngroups + fi];
+    if (w.s_status[grp] != ST_ACTIVE) continue;             // G = 1: warp-uniform
     double2 *lu = w.lu + (size_t)grp * p.nslots * 2;
     char *base = (char *)smem_f + (size_t)wib * factor_smem_per_warp(p.cap_upd, p.cap_ent, p.cap_rowblk);
     double2 *sSrc = (double2 *)base;
@@ -508,6 +516,8 @@ __global__ void __launch_bounds__(WPB * 32) k_factor_coop(PlanDev p, WorkDev w) 
         __syncwarp();
     }
     if (__any_sync(0xFFFFFFFFu, singular) && lane == 0) w.s_status[grp] = ST_SINGULAR;
+    __syncwarp();
+  }
 }
 
 // ---- K2: level-scheduled block SpTRSV (replaces SuperLU gstrs, helm.py:602) -----------
@@ -935,13 +945,14 @@ __global__ void __launch_bounds__(SM_T) k_solve_smem(PlanDev p, WorkDev w) {
 template <int G>
 __global__ void k_init(PlanDev p, WorkDev w) {
     TL_SCOPE(w, 7);
-    int grp = blockIdx.y;
-    if (!(w.g_flags[grp] & GF_FACTORING)) return;
+  const int nfact = w.fact_count[w.parity];
+  for (int fi = blockIdx.y; fi < nfact; fi += gridDim.y) {
+    int grp = w.fact_list[(size_t)w.parity * w.ngroups + fi];
     int flat = blockIdx.x * blockDim.x + threadIdx.x;
     int i = flat / G, s = flat % G;
     if (i >= p.N) return;
     int sg = grp * G + s;
-    if (w.s_status[sg] != ST_ACTIVE) return;
+    if (w.s_status[sg] != ST_ACTIVE) continue;
     const int N = p.N;
     double sc = w.scale[sg];
     size_t bi = ix<G>(grp, N, i, s);
@@ -970,6 +981,7 @@ __global__ void k_init(PlanDev p, WorkDev w) {
         r = make_double2(cc, (vs * vs - 1.0) * 0.5);                             // helm.py:354-355, 364
     }
     w.rhs[bi] = r;
+  }
 }
 
 // ---- K1: V/W update, epsilon-table column, Pade check, RHS of the next order ------------
@@ -1296,9 +1308,14 @@ __global__ void k_step_begin(WorkDev w) {
 #endif
     int grp = blockIdx.x * blockDim.x + threadIdx.x;
     if (grp >= w.ngroups) return;
+    if (grp == 0) w.fact_count[w.parity ^ 1] = 0;          // the list of the next step starts empty
     int gf = w.g_flags[grp];
     if (gf & GF_FACTORING) gf &= ~(GF_FACTORING | GF_NEWSCEN);
-    else if (gf & GF_PENDING) gf = (gf & ~GF_PENDING) | GF_FACTORING;
+    else if (gf & GF_PENDING) {
+        gf = (gf & ~GF_PENDING) | GF_FACTORING;
+        int pos = atomicAdd(&w.fact_count[w.parity], 1);
+        w.fact_list[(size_t)w.parity * w.ngroups + pos] = grp;
+    }
     w.g_flags[grp] = gf;
 }
 
@@ -1331,6 +1348,7 @@ __global__ void k_setup(PlanDev p, WorkDev w, const double *scale_in) {
         if (grp == 0) {
             *w.active_groups = w.ngroups;
             *w.queue_next = w.ngroups * G;      // slots 0..Bp-1 start with scenarios 0..Bp-1
+            w.fact_count[0] = 0; w.fact_count[1] = 0;
         }
     }
 }
@@ -1424,7 +1442,7 @@ WsLayout layout(const helm_plan *pl, int B, const helm_params *prm) {
     auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes); return r; };
     L.off_scale = take(sizeof(double) * L.Bp);
     L.off_sint = take(sizeof(int) * L.Bp * (8 + HELM_MAX_PASSES));
-    L.off_gint = take(sizeof(int) * (2 * L.ngroups + 4));
+    L.off_gint = take(sizeof(int) * (4 * L.ngroups + 8));
     L.off_btype = take(per);
     L.off_Qg = take(per * sizeof(double));
     L.off_VVant = take(per * sizeof(double));
@@ -1461,6 +1479,7 @@ WorkDev bind(const helm_plan *pl, const WsLayout &L, int B, const helm_params *p
     w.s_npass = si + 4 * L.Bp; w.s_nswitch = si + 5 * L.Bp; w.slot_scen = si + 6 * L.Bp; w.o_b = si + 7 * L.Bp; w.s_ncoef = si + 8 * L.Bp;
     int *gi = (int *)(b + L.off_gint);
     w.g_n = gi; w.g_flags = gi + L.ngroups; w.active_groups = gi + 2 * L.ngroups; w.queue_next = gi + 2 * L.ngroups + 1;
+    w.fact_count = gi + 2 * L.ngroups + 2; w.fact_list = gi + 2 * L.ngroups + 8; w.parity = 0;
     w.scale_in = nullptr; w.outage_in = nullptr; w.out_status = nullptr; w.out_ncoef = nullptr; w.out_nswitch = nullptr;
     w.btype = (unsigned char *)(b + L.off_btype);
     w.Qg = (double *)(b + L.off_Qg);
@@ -1503,19 +1522,19 @@ void launch_kernel(int which, const PlanDev &p, const WorkDev &w, cudaStream_t s
     dim3 gridBus((p.N * G + T_ELEM - 1) / T_ELEM, w.ngroups);
     int gridGrp = (w.ngroups + 127) / 128;
     switch (which) {
-        case KI_ASM: k_assemble<G><<<w.ngroups, 256, 0, st>>>(p, w); break;
+        case KI_ASM: k_assemble<G><<<std::min(w.ngroups, 592), 256, 0, st>>>(p, w); break;
         case KI_BEGIN: k_step_begin<<<gridGrp, 128, 0, st>>>(w); break;
         case KI_FACTOR:
             if (G == 1 && p.use_coop_factor) {
                 size_t smem = WPB_FACTOR * factor_smem_per_warp(p.cap_upd, p.cap_ent, p.cap_rowblk);
-                k_factor_coop<WPB_FACTOR><<<(w.ngroups + WPB_FACTOR - 1) / WPB_FACTOR, WPB_FACTOR * 32, smem, st>>>(p, w);
+                k_factor_coop<WPB_FACTOR><<<std::min((w.ngroups + WPB_FACTOR - 1) / WPB_FACTOR, 296), WPB_FACTOR * 32, smem, st>>>(p, w);
             } else {
                 k_factor<G, WPB_SOLVE><<<(w.ngroups + WPB_SOLVE - 1) / WPB_SOLVE, WPB_SOLVE * 32, 0, st>>>(p, w);
             }
             break;
         case KI_INIT:
             if (w.pv_model == 1 || w.dsb_method) k_init_var<<<gridBus, T_ELEM, 0, st>>>(p, w);
-            else k_init<G><<<gridBus, T_ELEM, 0, st>>>(p, w);
+            else k_init<G><<<dim3(gridBus.x, std::min(w.ngroups, 512)), T_ELEM, 0, st>>>(p, w);
             break;
         case KI_BPREP: k_border_prep<<<w.ngroups, 256, 0, st>>>(p, w); break;
         case KI_BFIN: k_border_fin<<<w.ngroups, 256, 0, st>>>(p, w); break;
@@ -1612,7 +1631,9 @@ struct StepCtx {
     cudaEvent_t fork, join;
 };
 
-void launch_step(int G, const PlanDev &p, const WorkDev &w, const StepCtx &c, const StepSeq &q) {
+void launch_step(int G, const PlanDev &p, const WorkDev &w_in, const StepCtx &c, const StepSeq &q, int parity) {
+    WorkDev w = w_in;
+    w.parity = parity & 1;
     static const bool nofork = getenv("HELM_B200_NOFORK") != nullptr;   // A/B switch: serial step
     if (nofork) {
         launch_any(G, KI_BEGIN, p, w, c.st);
@@ -1630,8 +1651,10 @@ void launch_step(int G, const PlanDev &p, const WorkDev &w, const StepCtx &c, co
 }
 
 // serial variant with an event around every kernel (profile mode)
-void launch_step_profiled(int G, const PlanDev &p, const WorkDev &w, cudaStream_t st,
-                          std::vector<cudaEvent_t> &ev, helm_stats &acc, const StepSeq &q) {
+void launch_step_profiled(int G, const PlanDev &p, const WorkDev &w_in, cudaStream_t st,
+                          std::vector<cudaEvent_t> &ev, helm_stats &acc, const StepSeq &q, int parity) {
+    WorkDev w = w_in;
+    w.parity = parity & 1;
     int seq[STEP_LEN_MAX];
     int n = 0;
     seq[n++] = KI_BEGIN;
@@ -1764,7 +1787,7 @@ int helm_plan_create(const helm_grid_host *g, helm_plan **out) {
         static size_t smem_set = 48 * 1024;
         if (smem > smem_set) {
             CUDA_TRY(cudaFuncSetAttribute(k_factor_coop<WPB_FACTOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CUDA_TRY(cudaFuncSetAttribute(k_factor_coop<WPB_FACTOR>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            if (getenv("HELM_B200_FACTOR_CARVEOUT")) CUDA_TRY(cudaFuncSetAttribute(k_factor_coop<WPB_FACTOR>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             smem_set = smem;
         }
     }
@@ -1852,6 +1875,7 @@ int helm_solve_batch_device(helm_plan *pl, int32_t B, const double *d_scale, con
     const bool profile = getenv("HELM_B200_PROFILE") != nullptr;
     const bool use_graph = prm->use_graph && !profile;
     int poll_every = prm->poll_every > 0 ? prm->poll_every : 4;
+    poll_every += poll_every & 1;      // even: the step parity of a captured graph must repeat
     if (!pl->h_pinned) CUDA_TRY(cudaMallocHost((void **)&pl->h_pinned, 64));
 
 #ifdef HELM_TIMELINE
@@ -1893,7 +1917,7 @@ int helm_solve_batch_device(helm_plan *pl, int32_t B, const double *d_scale, con
     cudaGraphExec_t gexec = nullptr;
     if (use_graph) {
         CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        for (int rep = 0; rep < poll_every; ++rep) launch_step(L.G, p, w, ctx, seq);
+        for (int rep = 0; rep < poll_every; ++rep) launch_step(L.G, p, w, ctx, seq, rep);
         CUDA_TRY(cudaStreamEndCapture(st, &graph));
         CUDA_TRY(cudaGraphInstantiate(&gexec, graph, 0));
     }
@@ -1913,8 +1937,8 @@ int helm_solve_batch_device(helm_plan *pl, int32_t B, const double *d_scale, con
             steps += poll_every;
         } else {
             for (int rep = 0; rep < poll_every; ++rep) {
-                if (profile) launch_step_profiled(L.G, p, w, st, pev, local, seq);
-                else launch_step(L.G, p, w, ctx, seq);
+                if (profile) launch_step_profiled(L.G, p, w, st, pev, local, seq, (int)steps);
+                else launch_step(L.G, p, w, ctx, seq, (int)steps);
                 local.kernel_launches += STEP_LEN;
                 steps++;
             }
@@ -2048,9 +2072,10 @@ int helm_debug_factor_solve(helm_plan *pl, int32_t B, int32_t group, const uint8
     }
     CUDA_TRY(cudaMemcpy(w.btype, bt.data(), per, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(w.rhs, rhs.data(), per * sizeof(double2), cudaMemcpyHostToDevice));
-    launch_any(L.G, KI_BEGIN, p, w, 0);   // PENDING -> FACTORING
+    launch_any(L.G, KI_BEGIN, p, w, 0);   // PENDING -> FACTORING (list of parity 0)
     launch_any(L.G, KI_ASM, p, w, 0);
     launch_any(L.G, KI_FACTOR, p, w, 0);
+    w.parity = 1;
     launch_any(L.G, KI_BEGIN, p, w, 0);   // FACTORING -> main branch
     launch_any(L.G, KI_SOLVE, p, w, 0);
     CUDA_TRY(cudaDeviceSynchronize());

@@ -8,10 +8,11 @@ import helmpy_b200
 from helmpy_b200.core import _lib
 from helmpy_b200.core.helm import get_plan
 name, B = sys.argv[1], int(sys.argv[2])
+resident = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 case = load_case(name)
 scales = np.random.default_rng(0).uniform(0.8, 1.05, B)
 for rep in range(2):
-    res = helmpy_b200.helm_batch(case, scales, mismatch=1e-8, max_coefficients=40, group=1)
+    res = helmpy_b200.helm_batch(case, scales, mismatch=1e-8, max_coefficients=40, group=1, max_resident=resident)
 print('ms', res.stats['ms_total'], 'steps', res.stats['steps'])
 plan = get_plan(case)
 n = 400
@@ -19,6 +20,7 @@ buf = np.zeros((n, 16, 2), dtype=np.uint64)
 _lib.check(_lib.load().helm_debug_timeline(plan.handle, buf.ctypes.data_as(C.c_void_p), n), 'timeline')
 names = _lib.KERNEL_NAMES
 rows = []
+prev_end = None
 for s in range(1, n):
     row = buf[s][:8]
     valid = row[:, 1] > 0
@@ -28,4 +30,4 @@ for s in range(1, n):
     d = {names[k]: (int(row[k, 1]) - int(row[k, 0])) / 1e3 for k in range(8) if valid[k]}
     rows.append((s, (int(t1) - int(t0)) / 1e3, d))
 for s, dt, d in rows:
-    print('%3d %7.0f us  solve %6.0f rhs %6.0f factor %6.0f' % (s, dt, d.get('solve', 0), d.get('rhs_conv', 0), d.get('factor', 0)))
+    print('%3d %7.0f us  solve %6.0f rhs %6.0f factor %6.0f asm %5.0f init %5.0f qlim %5.0f adv %4.0f pend %4.0f' % (s, dt, d.get('solve', 0), d.get('rhs_conv', 0), d.get('factor', 0), d.get('assemble', 0), d.get('init', 0), d.get('qlimit', 0), d.get('advance', 0), d.get('pass_end', 0)))
