@@ -1013,8 +1013,10 @@ __device__ __forceinline__ void eps_step(EpsState &st, int t, int j, double2 v, 
     st.cur = e;
 }
 
+// 128-thread CTAs: a CTA is 16 K registers, so an SM that also hosts a factorization CTA of the
+// side branch loses a quarter of this kernel's occupancy instead of half (measured: timeline r1).
 template <int G>
-__global__ void __launch_bounds__(256) k_rhs_conv(PlanDev p, WorkDev w) {
+__global__ void __launch_bounds__(128) k_rhs_conv(PlanDev p, WorkDev w) {
     TL_SCOPE(w, 3);
     const int grp = blockIdx.y;
     const int flat = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1558,7 +1560,7 @@ void launch_kernel(int which, const PlanDev &p, const WorkDev &w, cudaStream_t s
             break;
         case KI_RHS:
             if (w.pv_model == 1 || w.dsb_method) k_rhs_conv_var<<<gridBus, T_ELEM, 0, st>>>(p, w);
-            else k_rhs_conv<G><<<gridBus, T_ELEM, 0, st>>>(p, w);
+            else k_rhs_conv<G><<<dim3((p.N * G + 127) / 128, w.ngroups), 128, 0, st>>>(p, w);
             break;
         case KI_ADV: k_advance<<<gridGrp, 128, 0, st>>>(w); break;
         case KI_QLIM: k_qlimit<G><<<gridBus, T_ELEM, 0, st>>>(p, w); break;
