@@ -340,15 +340,18 @@ def roofline_model(info, ncoef, stats, N):
     orders = float(np.sum(m - 1))                       # scenario-orders = triangular solves
     passes = float(len(m))
     sum_j = float(np.sum((m - 1) * m / 2))              # sum over orders of j
+    half = np.floor((m - 1) / 2)
+    sum_j_even = float(np.sum(half * (half + 1)))       # sum over the even orders of j
     nslots = info['n_slots']
     out = {}
     ms = stats['ms_kernel']
     steps = max(1, stats['steps'])
     # K2 solve: LU blocks (32 B each) once + rhs read + x write (16 B each per bus)
     b_solve = orders * (32.0 * nslots + 32.0 * N)
-    # K1 rhs_conv at order j, per bus: histories V, W|CC (read j each) + eps column (read j, write j+1)
+    # K1 rhs_conv at order j, per bus: histories V, W|CC (read j each); at even orders also the
+    #   epsilon anti-diagonal (read j-1, write j+1; odd orders do not touch the table)
     #   + x read, V[j], H[j], rhs written: 16 B each
-    b_rhs = (64.0 * sum_j + 80.0 * orders) * N
+    b_rhs = (32.0 * sum_j + 32.0 * sum_j_even + 80.0 * orders) * N
     # K2f factor: read A blocks + write LU blocks (32 B per slot each way), per pass
     b_fac = passes * 64.0 * nslots
     b_asm = passes * 32.0 * nslots

@@ -68,6 +68,9 @@ struct PlanDev {
     const int *sstep_kind, *sstep_a, *sstep_b, *sring_desc;
     int nsteps, nring, use_smem_solve, smem_solve_max_groups, use_coop_factor;
     int max_row_blocks, nfchunks, cap_upd, cap_ent, cap_rowblk;
+    const int2 *wave_tab;
+    const int *smeta;
+    int nwaves, n_rows_nol, use_flat_solve;
 };
 
 struct WorkDev {
@@ -771,6 +774,139 @@ __global__ void __launch_bounds__(WPB * 32, 8) k_solve_warp(PlanDev p, WorkDev w
     }
 }
 
+// ---- K2 (G = 1), flat wave solve ----------------------------------------------------------------
+// One warp per scenario.  The blocks of L and of [D|U], in storage (= consumption) order, are cut on
+// the host into waves of <= 32 consecutive slots (symbolic.cpp 4b-flat): one block per lane, so the
+// factor loads of a wave are one contiguous run of up to 1 KB, and which row a lane's block belongs to
+// comes from a per-slot table shared by all scenarios.  The row sums are segmented shuffle
+// reductions towards the first lane of each row piece.  Nothing but the gathers of x depends on
+// earlier results, so the factor blocks, columns and row tables of wave w+2 are already in flight
+// while wave w is reduced (three register stages), and the gather of wave w+1 is issued before the
+// reduction of wave w whenever both belong to the same level.
+struct FlatStage { double2 m0, m1; int col, meta, info; };
+
+constexpr int FLAT_WPB = 4;
+constexpr int FLAT_NST = 3;
+
+__device__ __forceinline__ void flat_prefetch(const PlanDev &p, const double2 *lu, FlatStage &S, int wp, int lane,
+                                              int2 &wt, int2 &wtn) {
+    const double2 zero = make_double2(0.0, 0.0);
+    S.m0 = zero; S.m1 = zero; S.col = 0; S.meta = helm::Symbolic::META_DIAG; S.info = 0;
+    if (wp < p.nwaves) {
+        if ((wp & 31) == 0 && wp > 0) {          // next chunk of the wave table (loaded 32 waves ago)
+            wt = wtn;
+            int idx = wp + 32 + lane;
+            wtn = (idx < p.nwaves) ? __ldg(p.wave_tab + idx) : make_int2(0, 0);
+        }
+        const int e0 = __shfl_sync(0xFFFFFFFFu, wt.x, wp & 31);
+        S.info = __shfl_sync(0xFFFFFFFFu, wt.y, wp & 31);
+        if (lane < (S.info & 63)) {
+            const size_t e = (size_t)(e0 + lane);
+            S.m0 = __ldcs(lu + 2 * e);
+            S.m1 = __ldcs(lu + 2 * e + 1);
+            S.col = __ldg(p.slot_col + e);
+            S.meta = __ldg(p.smeta + e);
+        }
+    }
+}
+
+// gather of x for the lane's block and, on the first lane of a row that starts here, the value
+// the row sum is subtracted from (rhs in the forward solve, the forward result in the backward one)
+__device__ __forceinline__ void flat_gather(const FlatStage &S, const double2 *rhs, const double2 *xb,
+                                            double2 &xg, double2 &bs) {
+    using Sy = helm::Symbolic;
+    xg = make_double2(0.0, 0.0);
+    if (!(S.meta & Sy::META_DIAG)) xg = xb[S.col];
+    if ((S.meta & (Sy::META_HEAD | Sy::META_ROWSTART)) == (Sy::META_HEAD | Sy::META_ROWSTART)) {
+        const int r = S.meta >> 9;
+        bs = (S.info & Sy::WAVE_ISU) ? xb[r] : rhs[r];
+    }
+}
+
+template <int WPB>
+__global__ void __launch_bounds__(WPB * 32, 5) k_solve_flat(PlanDev p, WorkDev w, int side) {
+    using Sy = helm::Symbolic;
+    TL_SCOPE(w, 2);
+    int grp = blockIdx.x * WPB + (threadIdx.x >> 5);
+    if (grp >= w.ngroups) return;
+    {
+        int gfl = w.g_flags[grp];
+        if (side ? !(gfl & GF_FACTORING) : (gfl & (GF_DONE | GF_FACTORING)) != 0) return;
+    }
+    if (w.s_status[grp] != ST_ACTIVE) return;
+    const int lane = threadIdx.x & 31;
+    const double2 *lu = w.lu + (size_t)grp * p.nslots * 2;
+    const double2 *rhs = w.rhs + (size_t)grp * p.N;
+    double2 *xb = w.xb + (size_t)grp * p.N;
+    const int nw = p.nwaves;
+    int2 wt = (lane < nw) ? __ldg(p.wave_tab + lane) : make_int2(0, 0);
+    int2 wtn = (32 + lane < nw) ? __ldg(p.wave_tab + 32 + lane) : make_int2(0, 0);
+    FlatStage st[FLAT_NST];
+#pragma unroll
+    for (int s = 0; s < FLAT_NST - 1; ++s) flat_prefetch(p, lu, st[s], s, lane, wt, wtn);
+    // rows without L entries: y = rhs
+    for (int r = lane; r < p.n_rows_nol; r += 32) xb[r] = rhs[r];
+    const double2 zero = make_double2(0.0, 0.0);
+    double2 xg = zero, bs = zero, xgn = zero, bsn = zero;
+    double2 carry = zero, cd0 = zero, cd1 = zero;
+    bool early = false;
+    for (int w0 = 0; w0 < nw; w0 += FLAT_NST) {
+#pragma unroll
+        for (int s = 0; s < FLAT_NST; ++s) {
+            const int wv = w0 + s;
+            if (wv < nw) {
+                FlatStage &S = st[s];
+                FlatStage &Sn = st[(s + 1) % FLAT_NST];
+                if (!early) {
+                    if (S.info & Sy::WAVE_SYNC) __syncwarp();
+                    flat_gather(S, rhs, xb, xg, bs);
+                }
+                const bool nxt_early = (wv + 1 < nw) && !(Sn.info & Sy::WAVE_SYNC);
+                if (nxt_early) flat_gather(Sn, rhs, xb, xgn, bsn);
+                flat_prefetch(p, lu, st[(s + FLAT_NST - 1) % FLAT_NST], wv + FLAT_NST - 1, lane, wt, wtn);
+                // ---- reduce wave wv
+                const int meta = S.meta, info = S.info;
+                double2 v = make_double2(S.m0.x * xg.x + S.m0.y * xg.y, S.m1.x * xg.x + S.m1.y * xg.y);
+                const int span = meta & 31, maxspan = (info >> 9) & 31;
+                for (int o = 1; o <= maxspan; o <<= 1) {
+                    double tx = __shfl_down_sync(0xFFFFFFFFu, v.x, o);
+                    double ty = __shfl_down_sync(0xFFFFFFFFu, v.y, o);
+                    if (o <= span) { v.x += tx; v.y += ty; }
+                }
+                double2 acc = zero;
+                const bool head = (meta & Sy::META_HEAD) != 0;
+                if (head) {
+                    const double2 b = (meta & Sy::META_ROWSTART) ? bs : carry;
+                    acc = make_double2(b.x - v.x, b.y - v.y);
+                    if (meta & Sy::META_ROWEND) {
+                        double2 out = acc;
+                        if (info & Sy::WAVE_ISU) {
+                            const double2 d0 = (meta & Sy::META_ROWSTART) ? S.m0 : cd0;
+                            const double2 d1 = (meta & Sy::META_ROWSTART) ? S.m1 : cd1;
+                            out = make_double2(d0.x * acc.x + d0.y * acc.y, d1.x * acc.x + d1.y * acc.y);
+                        }
+                        xb[meta >> 9] = out;
+                    }
+                }
+                if (info & Sy::WAVE_CONT) {                 // the last row continues in the next wave
+                    const unsigned bal = __ballot_sync(0xFFFFFFFFu, head && !(meta & Sy::META_ROWEND));
+                    const int src = __ffs(bal) - 1;
+                    carry.x = __shfl_sync(0xFFFFFFFFu, acc.x, src);
+                    carry.y = __shfl_sync(0xFFFFFFFFu, acc.y, src);
+                    if (info & Sy::WAVE_ISU) {
+                        const double2 d0 = (meta & Sy::META_ROWSTART) ? S.m0 : cd0;
+                        const double2 d1 = (meta & Sy::META_ROWSTART) ? S.m1 : cd1;
+                        cd0.x = __shfl_sync(0xFFFFFFFFu, d0.x, src); cd0.y = __shfl_sync(0xFFFFFFFFu, d0.y, src);
+                        cd1.x = __shfl_sync(0xFFFFFFFFu, d1.x, src); cd1.y = __shfl_sync(0xFFFFFFFFu, d1.y, src);
+                    }
+                }
+                early = nxt_early;
+                xg = xgn; bs = bsn;
+            }
+        }
+    }
+}
+
 // ---- K2 (G = 1, N*16 B fits in shared memory): shared-memory solve ------------------------------
 // One CTA per scenario.  The solution vector lives in shared memory, so a dependent level costs a
 // barrier and a shared-memory round trip instead of an L2 one.  The levels near the root of the
@@ -1013,10 +1149,90 @@ __device__ __forceinline__ void eps_step(EpsState &st, int t, int j, double2 v, 
     st.cur = e;
 }
 
+// Two anti-diagonals of the epsilon table per visit (even orders only).  `o` is the stored
+// anti-diagonal j-2, `a` the anti-diagonal j-1 (never stored), `b` the anti-diagonal j (stored over o):
+//   a_t = o_{t-2} + 1/(a_{t-1} - o_{t-1}),  b_t = a_{t-2} + 1/(b_{t-1} - a_{t-1}).
+// Same operations in the same order as appending one anti-diagonal per order (eps_step), so the
+// values are bit-identical; the table is read and written every second order instead of every order.
+struct Eps2State { double2 o1, o2, a1, a2, b1; };
+
+__device__ __forceinline__ void eps2_step(Eps2State &st, int t, int j, double2 vjm1, double2 v, double2 eold_t,
+                                          double2 *Eb, size_t plane) {
+    double2 a = st.a1;
+    if (t < j) a = cadd(st.o2, crecip_guard((t == 1) ? vjm1 : csub(st.a1, st.o1)));
+    double2 b = cadd(st.a2, crecip_guard((t == 1) ? v : csub(st.b1, st.a1)));
+    Eb[(size_t)t * plane] = b;
+    st.o2 = st.o1; st.o1 = eold_t;
+    st.a2 = st.a1; st.a1 = a;
+    st.b1 = b;
+}
+
+// O(j) loop of a PQ bus at order j: W recurrence (+ two epsilon anti-diagonals when EPS).
+template <bool EPS>
+__device__ __forceinline__ double2 conv_loop_pq(int j, double2 v, double2 vjm1, const double2 *Vb, const double2 *Hb,
+                                                double2 *Eb, size_t plane, Eps2State &es) {
+    const double2 zero = make_double2(0.0, 0.0);
+    double2 aux = zero;
+    for (int t0 = 1; t0 <= j; t0 += KU) {
+        double2 vr[KU], eo[KU], hh[KU];
+#pragma unroll
+        for (int u = 0; u < KU; ++u) {
+            int t = t0 + u;
+            if (t <= j) {
+                vr[u] = (t == 1) ? v : Vb[(size_t)(j + 1 - t) * plane];
+                if (EPS) eo[u] = (t < j - 1) ? Eb[(size_t)t * plane] : zero;
+                hh[u] = Hb[(size_t)(t - 1) * plane];                              // W[t-1]
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < KU; ++u) {
+            int t = t0 + u;
+            if (t <= j) {
+                if (EPS) eps2_step(es, t, j, vjm1, v, eo[u], Eb, plane);
+                aux = cadd(aux, cmul(hh[u], vr[u]));                              // helm.py:430-432
+            }
+        }
+    }
+    return aux;
+}
+
+// O(j) loop of a PV bus (model 2) at order j: P-row convolution, |V|^2 convolution (+ epsilon).
+template <bool EPS>
+__device__ __forceinline__ void conv_loop_pv(int j, double2 v, double2 vjm1, double2 PP, const double2 *Vb,
+                                             const double2 *Hb, double2 *Eb, size_t plane, Eps2State &es,
+                                             double2 &ppp, double &vvre) {
+    const double2 zero = make_double2(0.0, 0.0);
+    for (int t0 = 1; t0 <= j; t0 += KU) {
+        double2 vr[KU], eo[KU], hh[KU], vf[KU];
+#pragma unroll
+        for (int u = 0; u < KU; ++u) {
+            int t = t0 + u;
+            if (t <= j) {
+                vr[u] = (t == 1) ? v : Vb[(size_t)(j + 1 - t) * plane];
+                if (EPS) eo[u] = (t < j - 1) ? Eb[(size_t)t * plane] : zero;
+                hh[u] = (t < j) ? Hb[(size_t)t * plane] : PP;                     // CC[t]
+                vf[u] = (t < j) ? Vb[(size_t)t * plane] : v;                      // V[t]
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < KU; ++u) {
+            int t = t0 + u;
+            if (t <= j) {
+                if (EPS) eps2_step(es, t, j, vjm1, v, eo[u], Eb, plane);
+                ppp = cadd(ppp, cmulc(hh[u], vr[u]));                             // helm.py:306-314
+                vvre += vf[u].x * vr[u].x + vf[u].y * vr[u].y;                    // helm.py:356-361
+            }
+        }
+    }
+}
+
 // 128-thread CTAs: a CTA is 16 K registers, so an SM that also hosts a factorization CTA of the
 // side branch loses a quarter of this kernel's occupancy instead of half (measured: timeline r1).
+#ifndef RHS_MINB
+#define RHS_MINB 4
+#endif
 template <int G>
-__global__ void __launch_bounds__(128) k_rhs_conv(PlanDev p, WorkDev w) {
+__global__ void __launch_bounds__(128, RHS_MINB) k_rhs_conv(PlanDev p, WorkDev w) {
     TL_SCOPE(w, 3);
     const int grp = blockIdx.y;
     const int flat = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1037,7 +1253,8 @@ __global__ void __launch_bounds__(128) k_rhs_conv(PlanDev p, WorkDev w) {
     const int j = w.g_n[grp] + 1;  // order just solved
     const unsigned char bt = w.btype[bi];
     const double2 v = xb[(size_t)i * G + s];
-    const double2 e_prev0 = Eb[0];
+    const double2 e_old0 = Eb[0];
+    const double2 vjm1 = Vb[(size_t)(j - 1) * plane];       // V[j-1] (j >= 1)
     const double sc = w.scale[sg];
     const double qg = w.Qg[bi];
     const double pgi = p.pg[i], pdi = p.pd[i], qdi = p.qd[i];
@@ -1059,34 +1276,20 @@ __global__ void __launch_bounds__(128) k_rhs_conv(PlanDev p, WorkDev w) {
         return;
     }
     const double2 zero = make_double2(0.0, 0.0);
-    EpsState es;
-    es.prev1 = e_prev0;                                    // eps_0^(j-1) = S_{j-1}
-    es.prev2 = zero;                                       // eps_{-1} = 0
-    es.cur = cadd(es.prev1, v);                            // S_j
-    Eb[0] = es.cur;
+    // The epsilon table advances by two anti-diagonals at every even order (the orders at which
+    // the Pade value is needed, helm.py:611); odd orders do not touch it.
+    const bool even = (j & 1) == 0;
+    Eps2State es;
+    es.o1 = e_old0;                                        // eps_0^(j-2) = S_{j-2}
+    es.o2 = zero;                                          // eps_{-1} = 0
+    es.a1 = cadd(e_old0, vjm1);                            // S_{j-1}
+    es.a2 = zero;
+    es.b1 = cadd(es.a1, v);                                // S_j
+    if (even) Eb[0] = es.b1;
     double2 out;
     if (bt == HELM_BUS_PQ) {
-        double2 aux = zero;
-        for (int t0 = 1; t0 <= j; t0 += KU) {
-            double2 vr[KU], eo[KU], hh[KU];
-#pragma unroll
-            for (int u = 0; u < KU; ++u) {
-                int t = t0 + u;
-                if (t <= j) {
-                    vr[u] = (t == 1) ? v : Vb[(size_t)(j + 1 - t) * plane];
-                    eo[u] = (t < j) ? Eb[(size_t)t * plane] : zero;
-                    hh[u] = Hb[(size_t)(t - 1) * plane];                          // W[t-1]
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < KU; ++u) {
-                int t = t0 + u;
-                if (t <= j) {
-                    eps_step(es, t, j, v, eo[u], Eb, plane);
-                    aux = cadd(aux, cmul(hh[u], vr[u]));                          // helm.py:430-432
-                }
-            }
-        }
+        double2 aux = even ? conv_loop_pq<true>(j, v, vjm1, Vb, Hb, Eb, plane, es)
+                           : conv_loop_pq<false>(j, v, vjm1, Vb, Hb, Eb, plane, es);
         double2 wj = make_double2(-aux.x, -aux.y);
         Hb[(size_t)j * plane] = wj;                                               // W[j]
         // RHS of order j+1 (helm.py:367-385)
@@ -1106,28 +1309,8 @@ __global__ void __launch_bounds__(128) k_rhs_conv(PlanDev p, WorkDev w) {
         Hb[(size_t)j * plane] = PP;                                               // barras_CC[i][n-1]
         double2 ppp = zero;
         double vvre = 0.0;
-        for (int t0 = 1; t0 <= j; t0 += KU) {
-            double2 vr[KU], eo[KU], hh[KU], vf[KU];
-#pragma unroll
-            for (int u = 0; u < KU; ++u) {
-                int t = t0 + u;
-                if (t <= j) {
-                    vr[u] = (t == 1) ? v : Vb[(size_t)(j + 1 - t) * plane];
-                    eo[u] = (t < j) ? Eb[(size_t)t * plane] : zero;
-                    hh[u] = (t < j) ? Hb[(size_t)t * plane] : PP;                 // CC[t]
-                    vf[u] = (t < j) ? Vb[(size_t)t * plane] : v;                  // V[t]
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < KU; ++u) {
-                int t = t0 + u;
-                if (t <= j) {
-                    eps_step(es, t, j, v, eo[u], Eb, plane);
-                    ppp = cadd(ppp, cmulc(hh[u], vr[u]));                         // helm.py:306-314
-                    vvre += vf[u].x * vr[u].x + vf[u].y * vr[u].y;                // helm.py:356-361
-                }
-            }
-        }
+        if (even) conv_loop_pv<true>(j, v, vjm1, PP, Vb, Hb, Eb, plane, es, ppp, vvre);
+        else conv_loop_pv<false>(j, v, vjm1, PP, Vb, Hb, Eb, plane, es, ppp, vvre);
         double cc_ = 0.0 - ppp.x;
         if (ysh.x != 0.0) {                                                      // conduc_buses
             if (j >= 2) cc_ -= ysh.x * (w.VVant[bi] + 2.0 * v.x);                // helm.py:317-318
@@ -1152,8 +1335,8 @@ __global__ void __launch_bounds__(128) k_rhs_conv(PlanDev p, WorkDev w) {
     }
     w.rhs[bi] = out;
     // --- Pade value of m = j+1 terms and the convergence test (helm.py:608-641)
-    if ((j & 1) == 0) {                                    // m odd: es.cur = [j/2 / j/2] Pade at s = 1
-        double2 cur = es.cur;
+    if (even) {                                            // m odd: es.b1 = [j/2 / j/2] Pade at s = 1
+        double2 cur = es.b1;
         if (j >= 4) {                                      // helm.py:611: m > 3
             double2 old = w.Pcur[bi];
             double mag1 = hypot(old.x, old.y), rad1 = atan2(old.y, old.x);
@@ -1545,13 +1728,16 @@ void launch_kernel(int which, const PlanDev &p, const WorkDev &w, cudaStream_t s
         case KI_PV1C_MAIN: k_pv1_correct<<<gridBus, T_ELEM, 0, st>>>(p, w, 0); break;
         case KI_PV1C_SIDE: k_pv1_correct<<<gridBus, T_ELEM, 0, st>>>(p, w, 1); break;
         case KI_SOLVE_SIDE:
-            k_solve_warp<WPB_SOLVE><<<(w.ngroups + WPB_SOLVE - 1) / WPB_SOLVE, WPB_SOLVE * 32, 0, st>>>(p, w, 1);
+            if (p.use_flat_solve) k_solve_flat<FLAT_WPB><<<(w.ngroups + FLAT_WPB - 1) / FLAT_WPB, FLAT_WPB * 32, 0, st>>>(p, w, 1);
+            else k_solve_warp<WPB_SOLVE><<<(w.ngroups + WPB_SOLVE - 1) / WPB_SOLVE, WPB_SOLVE * 32, 0, st>>>(p, w, 1);
             break;
         case KI_SOLVE:
             // shared-memory solve for small batches (<= ~3 CTAs per SM of concurrency is enough);
             // large batches keep more scenarios in flight with the warp-per-scenario kernel
             if (G == 1 && p.use_smem_solve && w.ngroups <= p.smem_solve_max_groups) {
                 k_solve_smem<<<w.ngroups, SM_T, solve_smem_bytes(p.N, p.nring, p.nsteps), st>>>(p, w);
+            } else if (G == 1 && p.use_flat_solve) {
+                k_solve_flat<FLAT_WPB><<<(w.ngroups + FLAT_WPB - 1) / FLAT_WPB, FLAT_WPB * 32, 0, st>>>(p, w, 0);
             } else if (G == 1) {
                 k_solve_warp<WPB_SOLVE><<<(w.ngroups + WPB_SOLVE - 1) / WPB_SOLVE, WPB_SOLVE * 32, 0, st>>>(p, w, 0);
             } else {
@@ -1766,6 +1952,14 @@ int helm_plan_create(const helm_grid_host *g, helm_plan **out) {
     UP(S.fptr, fptr) UP(S.fsrc, fsrc) UP(S.fdst, fdst) UP(S.fdst_local, fdstl) UP(S.qof, qof)
     UP(S.fchunk_row, fchunk_row) UP(S.fchunk_lpr, fchunk_lpr) UP(S.frow_off, frow_off)
     UP(S.sstep_kind, sstep_kind) UP(S.sstep_a, sstep_a) UP(S.sstep_b, sstep_b) UP(S.sring_desc, sring_desc)
+    UP(S.smeta, smeta)
+    {
+        const int *wt = nullptr;
+        if ((rc = upload(pl, S.wave_tab, &wt)) != HELM_OK) { helm_plan_destroy(pl); return rc; }
+        d.wave_tab = (const int2 *)wt;
+    }
+    d.nwaves = (int)S.wave_tab.size() / 2; d.n_rows_nol = S.n_rows_nol;
+    d.use_flat_solve = (S.n_rows_nol >= 0) && getenv("HELM_B200_FLAT_SOLVE") != nullptr;   // experimental (A/B)
     d.nsteps = (int)S.sstep_kind.size(); d.nring = (int)S.sring_desc.size() / 8;
     d.max_row_blocks = S.max_row_blocks;
     d.nfchunks = (int)S.fchunk_lpr.size(); d.cap_upd = S.cap_upd; d.cap_ent = S.cap_ent; d.cap_rowblk = S.cap_rowblk;

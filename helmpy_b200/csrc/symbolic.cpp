@@ -352,6 +352,70 @@ bool build_symbolic(int N, const int32_t *adj_ptr, const int32_t *adj_idx, const
         }
     }
 
+    // ---- 4b-flat. flat solve schedule ---------------------------------------------------------
+    // The blocks of both triangular solves, in storage (= consumption) order, are cut into
+    // "waves" of at most 32 consecutive slots that one warp handles with one block per lane.
+    // Rows are never split unless they are longer than 32 blocks; a wave never crosses a level.
+    {
+        S.smeta.assign(S.nslots, 0);
+        S.wave_tab.clear();
+        int w_e0 = -1, w_n = 0, w_flags = 0, w_maxspan = 0;
+        auto flush = [&]() {
+            if (w_n > 0) {
+                S.wave_tab.push_back(w_e0);
+                S.wave_tab.push_back(w_n | w_flags | (w_maxspan << 9));
+            }
+            w_e0 = -1; w_n = 0; w_flags &= Symbolic::WAVE_ISU; w_maxspan = 0;
+        };
+        // one piece of a row: slots [s0, s0 + n) go to the next n lanes of the current wave
+        auto put = [&](int s0, int n, int row, bool rowstart, bool rowend, bool diag_first) {
+            if (w_n == 0) w_e0 = s0;
+            for (int k = 0; k < n; ++k) {
+                int span = n - 1 - k;
+                int meta = span | (row << 9);
+                if (k == 0) meta |= Symbolic::META_HEAD | (rowstart ? Symbolic::META_ROWSTART : 0) |
+                                    (rowend ? Symbolic::META_ROWEND : 0);
+                if (k == 0 && diag_first) meta |= Symbolic::META_DIAG;
+                S.smeta[s0 + k] = meta;
+                w_maxspan = std::max(w_maxspan, span);
+            }
+            w_n += n;
+        };
+        auto add_row = [&](int s0, int n, int row, bool isU, bool &first_of_level) {
+            if (n <= 32 && w_n + n > 32) flush();
+            if (n > 32 && w_n > 0) flush();
+            int done = 0;
+            while (done < n) {
+                int take = std::min(32 - w_n, n - done);
+                if (first_of_level && w_n == 0) { w_flags |= Symbolic::WAVE_SYNC; first_of_level = false; }
+                put(s0 + done, take, row, done == 0, done + take == n, isU && done == 0);
+                done += take;
+                if (done < n) { w_flags |= Symbolic::WAVE_CONT; flush(); }
+            }
+        };
+        for (int l = 0; l < nLlev; ++l) {
+            bool first = true;
+            for (int r = S.llev_ptr[l]; r < S.llev_ptr[l + 1]; ++r) {
+                int n = S.lptr[r + 1] - S.lptr[r];
+                if (n > 0) add_row(S.lptr[r], n, r, false, first);
+            }
+            flush();
+        }
+        S.n_waves_l = (int)S.wave_tab.size() / 2;
+        w_flags = Symbolic::WAVE_ISU;
+        for (int l = 0; l < nUlev; ++l) {
+            bool first = true;
+            for (int q = S.ulev_ptr[l]; q < S.ulev_ptr[l + 1]; ++q)
+                add_row(S.slotD(q), 1 + (S.uptr[q + 1] - S.uptr[q]), S.urow[q], true, first);
+            flush();
+        }
+        // rows without L entries get x = rhs directly; they must form a prefix of the numbering
+        S.n_rows_nol = 0;
+        while (S.n_rows_nol < N && S.lptr[S.n_rows_nol + 1] == S.lptr[S.n_rows_nol]) S.n_rows_nol++;
+        for (int r = S.n_rows_nol; r < N; ++r)
+            if (S.lptr[r + 1] == S.lptr[r]) { S.n_rows_nol = -1; break; }   // not a prefix: flat solve unusable
+    }
+
     // ---- 4c. adjacency in the new numbering + assembly map -------------------------
     S.adj_ptr.assign(N + 1, 0);
     for (int r = 0; r < N; ++r) {

@@ -49,6 +49,15 @@ struct Symbolic {
     static constexpr int RING_BLOCKS = 128;      // 2x2 blocks per ring slot
     static constexpr int RING_ROWS = 32;         // rows per ring slot
 
+    // flat solve schedule (k_solve_flat): the slots in consumption order cut into waves of <= 32
+    // consecutive slots.  wave_tab: 2 ints per wave {first slot, n | flags | maxspan << 9};
+    // smeta[slot]: span (lanes after this one in its row piece) | flags | row << 9.
+    std::vector<int> wave_tab, smeta;
+    int n_waves_l = 0;                           // waves of the forward solve (the rest is backward)
+    int n_rows_nol = 0;                          // rows [0, n_rows_nol) have no L entries (-1: not a prefix)
+    static constexpr int WAVE_SYNC = 64, WAVE_CONT = 128, WAVE_ISU = 256;          // n in bits 0-5
+    static constexpr int META_HEAD = 32, META_ROWSTART = 64, META_ROWEND = 128, META_DIAG = 256;  // span in bits 0-4
+
     inline int slotD(int q) const { return nL + uptr[q] + q; }
     inline int slotU(int q, int t) const { return nL + uptr[q] + q + 1 + t; }
 };

@@ -172,3 +172,85 @@ def test_non_islanding_branches():
         A = coo_matrix((np.ones(len(keep)), (f[keep], t[keep])), shape=(case.N, case.N))
         ncomp, _ = connected_components(A, directed=False)
         assert (ncomp == 1) == (b in safe), b
+
+
+@pytest.mark.parametrize('name', ['case9', 'case118', 'case1354pegase', 'case2869pegase'])
+def test_flat_wave_schedule_solves(name):
+    """The wave tables of k_solve_flat (symbolic.cpp 4b-flat), emulated lane by lane on the host,
+    give the same x as the plain row-by-row block solve."""
+    case = load_case(name)
+    S = _lib.symbolic_arrays(case.adj_ptr, case.adj_idx, case.bus_types_code())
+    N = case.N
+    lptr, lcol, uptr, ucol, urow, dslot = S['lptr'], S['lcol'], S['uptr'], S['ucol'], S['urow'], S['dslot']
+    nL = int(lptr[-1])
+    nslots = nL + int(uptr[-1]) + N
+    wt = S['wave_tab'].reshape(-1, 2)
+    meta, col = S['smeta'], S['slot_col']
+    assert len(meta) == nslots and len(col) == nslots
+    rng = np.random.default_rng(3)
+    lu = rng.standard_normal((nslots, 2, 2))
+    rhs = rng.standard_normal((N, 2))
+    # reference: rows in level order
+    x = rhs.copy()
+    for r in range(N):
+        for e in range(lptr[r], lptr[r + 1]):
+            x[r] -= lu[e] @ x[lcol[e]]
+    for q in range(N):
+        r = urow[q]
+        base = nL + uptr[q] + q
+        acc = x[r].copy()
+        for t in range(uptr[q + 1] - uptr[q]):
+            acc -= lu[base + 1 + t] @ x[ucol[uptr[q] + t]]
+        x[r] = lu[base] @ acc
+    # emulation of the waves
+    covered = np.zeros(nslots, dtype=int)
+    y = np.full((N, 2), np.nan)
+    nol = 0
+    while nol < N and lptr[nol + 1] == lptr[nol]:
+        nol += 1
+    y[:nol] = rhs[:nol]
+    carry = None
+    carry_d = None
+    final_u = np.zeros(N, dtype=bool)
+    this_level = set()          # rows written since the last SYNC wave: must not be gathered
+    for e0, info in wt:
+        n = info & 63
+        is_u = bool(info & 256)
+        assert 1 <= n <= 32
+        if info & 64:
+            this_level = set()
+        covered[e0:e0 + n] += 1
+        lane = 0
+        while lane < n:
+            m = meta[e0 + lane]
+            assert m & 32, 'a row piece must start with a head lane'
+            span = m & 31
+            assert ((info >> 9) & 31) >= span and lane + span < n
+            r = m >> 9
+            v = np.zeros(2)
+            for k in range(lane, lane + span + 1):
+                mk = meta[e0 + k]
+                assert (mk & 31) == lane + span - k and (mk >> 9) == r
+                if not (mk & 256):
+                    assert not np.isnan(y[col[e0 + k]]).any(), 'gather of a value that is not yet final'
+                    assert col[e0 + k] not in this_level, 'gather inside the level that writes the value'
+                    assert final_u[col[e0 + k]] or not is_u
+                    v += lu[e0 + k] @ y[col[e0 + k]]
+            if m & 64:
+                b = y[r] if is_u else rhs[r]
+                d = lu[e0 + lane] if is_u else None
+                if is_u:
+                    assert m & 256
+            else:
+                b, d = carry, carry_d
+            acc = b - v
+            if m & 128:
+                y[r] = d @ acc if is_u else acc
+                this_level.add(r)
+                final_u[r] = is_u
+            else:
+                assert info & 128 and lane + span == n - 1
+                carry, carry_d = acc, d
+            lane += span + 1
+    assert (covered == 1).all()
+    assert np.allclose(y, x, rtol=1e-9, atol=1e-9)
