@@ -142,7 +142,7 @@ def symbolic_arrays(adj_ptr, adj_idx, bus_type=None):
                      "llev_ptr", "urow", "qof", "ulev_ptr", "uptr", "ucol", "dslot", "fptr",
                      "fsrc", "fdst", "fdst_local", "fchunk_row", "fchunk_lpr", "frow_off",
                      "sstep_kind", "sstep_a", "sstep_b", "sring_desc",
-                     "slot_src", "slot_row", "slot_col", "wave_tab", "smeta"):
+                     "slot_src", "slot_row", "slot_col", "wave_tab", "smeta", "scm", "solve_chunks"):
             data = C.c_void_p()
             n = C.c_int32()
             rc = lib.helm_symbolic_array(h, name.encode(), C.byref(data), C.byref(n))

@@ -44,6 +44,7 @@ enum : int { ST_ACTIVE = 0, ST_FROZEN = 1, ST_CONVERGED = 2, ST_DIVERGED = 3, ST
 // side branch of the current step and sits this order out (see the step graph below).
 // NEWSCEN: the group's slots were just refilled with fresh scenarios from the queue.
 enum : int { GF_PENDING = 1, GF_PASSEND = 2, GF_DONE = 4, GF_FACTORING = 8, GF_NEWSCEN = 16 };
+constexpr int MAX_SIDE_DEPTH = 3;
 
 // ---- device-side views ------------------------------------------------------------
 struct PlanDev {
@@ -71,6 +72,10 @@ struct PlanDev {
     const int2 *wave_tab;
     const int *smeta;
     int nwaves, n_rows_nol, use_flat_solve;
+    const int *scm;
+    const int4 *solve_chunks;
+    int nschunks, use_cta_solve, cta_solve_max_groups;
+    int split_eps;
 };
 
 struct WorkDev {
@@ -88,9 +93,11 @@ struct WorkDev {
     int *o_b;                         // [Bp] removed branch of the scenario in the slot (-1: none)
     // groups being factorized in the current step, compacted by k_step_begin (double-buffered by
     // step parity) so that the side-branch kernels launch only as many CTAs as there is work
-    int *fact_list;                   // [2][ngroups]
-    int *fact_count;                  // [2]
-    int parity;                       // parity of the current step (host-set per launch)
+    int *fact_list;                   // [MAX_SIDE_DEPTH + 1][ngroups]
+    int *fact_count;                  // [MAX_SIDE_DEPTH + 1]
+    int *g_fage;                      // [ngroups] steps left until a group being factorized rejoins
+    int parity;                       // list of the current step: step % (depth + 1) (host-set per launch)
+    int depth;                        // steps a factorization may take (side-branch pipeline depth)
     int *out_status, *out_ncoef, *out_nswitch;   // per-scenario outputs, written when a scenario ends
     unsigned char *btype;             // [group][N][G]
     double *Qg, *VVant;               // [group][N][G]
@@ -173,10 +180,18 @@ template <int G>
 __device__ __forceinline__ size_t ix(int grp, int count, int item, int s) {
     return ((size_t)grp * count + item) * G + s;
 }
+// Series histories are tiled: the K orders of a tile of HT consecutive buses are contiguous,
+// [group][tile][order][HT buses][G], so the O(j) loops of a CTA of k_rhs_conv / k_eps (HT threads =
+// one tile) walk ONE contiguous run of j * HT * 16 B per history instead of j pieces 16*N B apart
+// (DRAM page locality).  HPLANE<G> = distance between consecutive orders of one bus.
+constexpr int HT = 128;
 template <int G>
 __device__ __forceinline__ size_t hx(const WorkDev &w, int N, int grp, int k, int i, int s) {
-    return (((size_t)grp * w.K + k) * N + i) * G + s;
+    const int ntile = (N + HT - 1) / HT;
+    return ((((size_t)grp * ntile + (i / HT)) * w.K + k) * HT + (i % HT)) * G + s;
 }
+template <int G>
+__device__ __forceinline__ size_t hplane() { return (size_t)HT * G; }
 
 __device__ __forceinline__ OutageRef load_outage(const PlanDev &p, const WorkDev &w, int sg) {
     OutageRef o{w.o_b[sg], -1, -1};
@@ -232,53 +247,63 @@ __device__ __forceinline__ double2 yfull_eff(const PlanDev &p, const OutageRef &
 }
 
 // ---- K_asm: scatter A into the LU slots (reference helm.py:46-60) -------------------
-// One thread per (slot, scenario).  Fill slots get zero blocks.
+// asm_reset: fresh per-bus state of a slot refilled from the queue (classes.py:230-297);
+// asm_slot: the 2x2 block of one LU slot (fill slots get zero blocks).  Both are strided loops so
+// that a CTA (k_assemble) or a single warp (k_factor_coop) can run them.
+template <int G>
+__device__ __forceinline__ void asm_reset(const PlanDev &p, const WorkDev &w, int grp, int tid, int nthr) {
+    for (int flat = tid; flat < p.N * G; flat += nthr) {
+        int i = flat / G, s = flat % G;
+        if (w.s_status[grp * G + s] != ST_ACTIVE) continue;
+        size_t bi = ix<G>(grp, p.N, i, s);
+        w.btype[bi] = p.btype0[i];
+        w.Qg[bi] = 0.0;
+        w.VVant[bi] = 0.0;
+        w.Pcur[bi] = make_double2(0.0, 0.0);
+    }
+}
+template <int G>
+__device__ __forceinline__ void asm_slot(const PlanDev &p, const WorkDev &w, int grp, int slot, int s) {
+    int r = p.slot_row[slot];
+    int a = p.slot_src[slot];
+    unsigned char bt = w.btype[ix<G>(grp, p.N, r, s)];
+    bool diag = (p.dslot[r] == slot);
+    double2 r0 = make_double2(0.0, 0.0), r1 = make_double2(0.0, 0.0);
+    if (bt == HELM_BUS_SLACK) {
+        if (diag) { r0.x = 1.0; r1.y = 1.0; }                         // helm.py:47-49
+    } else if (a >= 0) {
+        double2 y = ytr_eff(p, load_outage(p, w, grp * G + s), a);
+        r0 = make_double2(y.x, -y.y);                                 // helm.py:52-53 / 59-60
+        if (bt == HELM_BUS_PQ || w.pv_model == 1) r1 = make_double2(y.y, y.x);   // helm.py:50-55
+        else if (diag) r1 = make_double2(1.0, 0.0);                   // helm.py:57
+    }
+    if (w.pv_model == 1 && bt != HELM_BUS_SLACK) {
+        // PV model 1: the column of Re V of a PV bus leaves the matrix (helm.py:72-103)
+        int c = p.slot_col[slot];
+        if (w.btype[ix<G>(grp, p.N, c, s)] == HELM_BUS_PV) {
+            r0.x = 0.0;
+            r1.x = diag ? 1.0 : 0.0;
+        }
+    }
+    double2 *dst = w.lu + ix<G>(grp, p.nslots, slot, s) * 2;
+    dst[0] = r0;
+    dst[1] = r1;
+}
+
 template <int G>
 __global__ void __launch_bounds__(256) k_assemble(PlanDev p, WorkDev w) {
     TL_SCOPE(w, 0);
   const int nfact = w.fact_count[w.parity];
   for (int fi = blockIdx.x; fi < nfact; fi += gridDim.x) {
     const int grp = w.fact_list[(size_t)w.parity * w.ngroups + fi];
-    const int gflags = w.g_flags[grp];
-    if (gflags & GF_NEWSCEN) {      // slots refilled from the queue: fresh per-bus state (classes.py:230-297)
-        for (int flat = threadIdx.x; flat < p.N * G; flat += blockDim.x) {
-            int i = flat / G, s = flat % G;
-            if (w.s_status[grp * G + s] != ST_ACTIVE) continue;
-            size_t bi = ix<G>(grp, p.N, i, s);
-            w.btype[bi] = p.btype0[i];
-            w.Qg[bi] = 0.0;
-            w.VVant[bi] = 0.0;
-            w.Pcur[bi] = make_double2(0.0, 0.0);
-        }
+    if (w.g_flags[grp] & GF_NEWSCEN) {
+        asm_reset<G>(p, w, grp, threadIdx.x, blockDim.x);
         __syncthreads();
     }
     for (int flat = threadIdx.x; flat < p.nslots * G; flat += blockDim.x) {
         int slot = flat / G, s = flat % G;
         if (w.s_status[grp * G + s] != ST_ACTIVE) continue;
-        int r = p.slot_row[slot];
-        int a = p.slot_src[slot];
-        unsigned char bt = w.btype[ix<G>(grp, p.N, r, s)];
-        bool diag = (p.dslot[r] == slot);
-        double2 r0 = make_double2(0.0, 0.0), r1 = make_double2(0.0, 0.0);
-        if (bt == HELM_BUS_SLACK) {
-            if (diag) { r0.x = 1.0; r1.y = 1.0; }                         // helm.py:47-49
-        } else if (a >= 0) {
-            double2 y = ytr_eff(p, load_outage(p, w, grp * G + s), a);
-            r0 = make_double2(y.x, -y.y);                                 // helm.py:52-53 / 59-60
-            if (bt == HELM_BUS_PQ || w.pv_model == 1) r1 = make_double2(y.y, y.x);   // helm.py:50-55
-            else if (diag) r1 = make_double2(1.0, 0.0);                   // helm.py:57
-        }
-        if (w.pv_model == 1 && bt != HELM_BUS_SLACK) {
-            // PV model 1: the column of Re V of a PV bus leaves the matrix (helm.py:72-103)
-            int c = p.slot_col[slot];
-            if (w.btype[ix<G>(grp, p.N, c, s)] == HELM_BUS_PV) {
-                r0.x = 0.0;
-                r1.x = diag ? 1.0 : 0.0;
-            }
-        }
-        double2 *dst = w.lu + ix<G>(grp, p.nslots, slot, s) * 2;
-        dst[0] = r0;
-        dst[1] = r1;
+        asm_slot<G>(p, w, grp, slot, s);
     }
     __syncthreads();
   }
@@ -387,7 +412,10 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int NPEND>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NPEND) : "memory"); }
 
-constexpr int WPB_FACTOR = 2;   // warps (= scenarios) per CTA of the staged factorization
+#ifndef WPB_FACTOR_N
+#define WPB_FACTOR_N 4
+#endif
+constexpr int WPB_FACTOR = WPB_FACTOR_N;   // warps (= scenarios) per CTA of the staged factorization
 
 // Shared-memory plan of one warp:
 // [src blocks cap_upd][Dk blocks cap_ent][row blocks cap_rowblk][dst idx cap_upd][update ptr cap_ent+1]
@@ -413,6 +441,14 @@ __global__ void __launch_bounds__(WPB * 32) k_factor_coop(PlanDev p, WorkDev w) 
   for (int fi = blockIdx.x * WPB + wib; fi < nfact; fi += gridDim.x * WPB) {
     const int grp = w.fact_list[(size_t)w.parity * w.ngroups + fi];
     if (w.s_status[grp] != ST_ACTIVE) continue;             // G = 1: warp-uniform
+    // assembly of A by the same warp (no separate kernel in front: the factorization starts at the
+    // beginning of the step, while the main branch's solve is being dispatched)
+    if (w.g_flags[grp] & GF_NEWSCEN) {
+        asm_reset<1>(p, w, grp, lane, 32);
+        __syncwarp();
+    }
+    for (int slot = lane; slot < p.nslots; slot += 32) asm_slot<1>(p, w, grp, slot, 0);
+    __syncwarp();
     double2 *lu = w.lu + (size_t)grp * p.nslots * 2;
     char *base = (char *)smem_f + (size_t)wib * factor_smem_per_warp(p.cap_upd, p.cap_ent, p.cap_rowblk);
     double2 *sSrc = (double2 *)base;
@@ -785,13 +821,17 @@ __global__ void __launch_bounds__(WPB * 32, 8) k_solve_warp(PlanDev p, WorkDev w
 // reduction of wave w whenever both belong to the same level.
 struct FlatStage { double2 m0, m1; int col, meta, info; };
 
-constexpr int FLAT_WPB = 4;
-constexpr int FLAT_NST = 3;
+// 7 warps per CTA at 64 registers: four CTAs take 57 344 of the 65 536 registers of an SM, i.e.
+// 28 scenarios per SM (148 x 28 = 4144 >= the 4096 resident scenarios, one round), and the 8192
+// registers left are what a CTA of the concurrent factorization (side branch) needs to start
+// while the solves are running instead of after them (timeline r1_h).
+constexpr int FLAT_WPB = 7;
+constexpr int FLAT_NST = 2;
 
 __device__ __forceinline__ void flat_prefetch(const PlanDev &p, const double2 *lu, FlatStage &S, int wp, int lane,
                                               int2 &wt, int2 &wtn) {
-    const double2 zero = make_double2(0.0, 0.0);
-    S.m0 = zero; S.m1 = zero; S.col = 0; S.meta = helm::Symbolic::META_DIAG; S.info = 0;
+    S.info = 0;
+    S.meta = helm::Symbolic::META_DIAG;
     if (wp < p.nwaves) {
         if ((wp & 31) == 0 && wp > 0) {          // next chunk of the wave table (loaded 32 waves ago)
             wt = wtn;
@@ -800,13 +840,13 @@ __device__ __forceinline__ void flat_prefetch(const PlanDev &p, const double2 *l
         }
         const int e0 = __shfl_sync(0xFFFFFFFFu, wt.x, wp & 31);
         S.info = __shfl_sync(0xFFFFFFFFu, wt.y, wp & 31);
-        if (lane < (S.info & 63)) {
-            const size_t e = (size_t)(e0 + lane);
-            S.m0 = __ldcs(lu + 2 * e);
-            S.m1 = __ldcs(lu + 2 * e + 1);
-            S.col = __ldg(p.slot_col + e);
-            S.meta = __ldg(p.smeta + e);
-        }
+        const int n = S.info & 63;
+        const int e = e0 + min(lane, n - 1);     // idle lanes repeat the last block (and contribute 0)
+        S.m0 = __ldcs(lu + 2 * (size_t)e);
+        S.m1 = __ldcs(lu + 2 * (size_t)e + 1);
+        const int2 cm = __ldg((const int2 *)p.scm + e);
+        S.col = cm.x;
+        S.meta = (lane < n) ? cm.y : helm::Symbolic::META_DIAG;
     }
 }
 
@@ -824,7 +864,7 @@ __device__ __forceinline__ void flat_gather(const FlatStage &S, const double2 *r
 }
 
 template <int WPB>
-__global__ void __launch_bounds__(WPB * 32, 5) k_solve_flat(PlanDev p, WorkDev w, int side) {
+__global__ void __maxnreg__(64) k_solve_flat(PlanDev p, WorkDev w, int side) {
     using Sy = helm::Symbolic;
     TL_SCOPE(w, 2);
     int grp = blockIdx.x * WPB + (threadIdx.x >> 5);
@@ -848,7 +888,7 @@ __global__ void __launch_bounds__(WPB * 32, 5) k_solve_flat(PlanDev p, WorkDev w
     for (int r = lane; r < p.n_rows_nol; r += 32) xb[r] = rhs[r];
     const double2 zero = make_double2(0.0, 0.0);
     double2 xg = zero, bs = zero, xgn = zero, bsn = zero;
-    double2 carry = zero, cd0 = zero, cd1 = zero;
+    double2 carry = zero;
     bool early = false;
     for (int w0 = 0; w0 < nw; w0 += FLAT_NST) {
 #pragma unroll
@@ -861,9 +901,10 @@ __global__ void __launch_bounds__(WPB * 32, 5) k_solve_flat(PlanDev p, WorkDev w
                     if (S.info & Sy::WAVE_SYNC) __syncwarp();
                     flat_gather(S, rhs, xb, xg, bs);
                 }
+                // stage of wave wv-1 is free: fetch wave wv + NST - 1 into it
+                flat_prefetch(p, lu, st[(s + FLAT_NST - 1) % FLAT_NST], wv + FLAT_NST - 1, lane, wt, wtn);
                 const bool nxt_early = (wv + 1 < nw) && !(Sn.info & Sy::WAVE_SYNC);
                 if (nxt_early) flat_gather(Sn, rhs, xb, xgn, bsn);
-                flat_prefetch(p, lu, st[(s + FLAT_NST - 1) % FLAT_NST], wv + FLAT_NST - 1, lane, wt, wtn);
                 // ---- reduce wave wv
                 const int meta = S.meta, info = S.info;
                 double2 v = make_double2(S.m0.x * xg.x + S.m0.y * xg.y, S.m1.x * xg.x + S.m1.y * xg.y);
@@ -876,13 +917,17 @@ __global__ void __launch_bounds__(WPB * 32, 5) k_solve_flat(PlanDev p, WorkDev w
                 double2 acc = zero;
                 const bool head = (meta & Sy::META_HEAD) != 0;
                 if (head) {
-                    const double2 b = (meta & Sy::META_ROWSTART) ? bs : carry;
+                    const bool rs = (meta & Sy::META_ROWSTART) != 0;
+                    const double2 b = rs ? bs : carry;
                     acc = make_double2(b.x - v.x, b.y - v.y);
                     if (meta & Sy::META_ROWEND) {
                         double2 out = acc;
                         if (info & Sy::WAVE_ISU) {
-                            const double2 d0 = (meta & Sy::META_ROWSTART) ? S.m0 : cd0;
-                            const double2 d1 = (meta & Sy::META_ROWSTART) ? S.m1 : cd1;
+                            double2 d0 = S.m0, d1 = S.m1;
+                            if (!rs) {                       // row longer than a wave: its pivot came earlier
+                                const size_t ds = (size_t)__ldg(p.dslot + (meta >> 9));
+                                d0 = lu[2 * ds]; d1 = lu[2 * ds + 1];
+                            }
                             out = make_double2(d0.x * acc.x + d0.y * acc.y, d1.x * acc.x + d1.y * acc.y);
                         }
                         xb[meta >> 9] = out;
@@ -893,18 +938,179 @@ __global__ void __launch_bounds__(WPB * 32, 5) k_solve_flat(PlanDev p, WorkDev w
                     const int src = __ffs(bal) - 1;
                     carry.x = __shfl_sync(0xFFFFFFFFu, acc.x, src);
                     carry.y = __shfl_sync(0xFFFFFFFFu, acc.y, src);
-                    if (info & Sy::WAVE_ISU) {
-                        const double2 d0 = (meta & Sy::META_ROWSTART) ? S.m0 : cd0;
-                        const double2 d1 = (meta & Sy::META_ROWSTART) ? S.m1 : cd1;
-                        cd0.x = __shfl_sync(0xFFFFFFFFu, d0.x, src); cd0.y = __shfl_sync(0xFFFFFFFFu, d0.y, src);
-                        cd1.x = __shfl_sync(0xFFFFFFFFu, d1.x, src); cd1.y = __shfl_sync(0xFFFFFFFFu, d1.y, src);
-                    }
                 }
                 early = nxt_early;
                 xg = xgn; bs = bsn;
             }
         }
     }
+}
+
+// ---- K2 (G = 1), shared-memory wave solve --------------------------------------------------------
+// One CTA per scenario; same wave schedule as k_solve_flat, but the solution vector lives in
+// shared memory, so a dependent level costs a block barrier and a shared-memory gather instead of an
+// L2/HBM round trip.  The factor blocks and the {column, meta} table are consumed strictly in
+// storage order, so they are streamed in chunks of <= 128 slots into a shared-memory ring with bulk
+// asynchronous copies (cp.async.bulk, completion on an mbarrier) issued CS_NST chunks ahead by one
+// thread: the dependency chain never waits for HBM.  Waves of one level are spread over the warps.
+constexpr int CS_T = 128;
+constexpr int CS_NWARP = CS_T / 32;
+constexpr int CS_NST = 3;
+constexpr int CS_CH = helm::Symbolic::SOLVE_CHUNK_SLOTS;
+constexpr int CS_STAGE_BYTES = (CS_CH * 32 + (CS_CH + 2) * 8 + 127) / 128 * 128;
+
+struct CtaSolveLayout { size_t off_x, off_wave, off_chunk, off_ring, off_carry, total; };
+__host__ __device__ inline CtaSolveLayout cta_solve_layout(int N, int nwaves, int nchunks) {
+    CtaSolveLayout L;
+    size_t o = 128;                                          // mbarriers
+    L.off_carry = o; o += 128;                               // carry of a row continued in the next wave
+    L.off_x = o; o += ((size_t)N * 16 + 127) / 128 * 128;
+    L.off_wave = o; o += ((size_t)(nwaves + 1) / 2 * 16 + 127) / 128 * 128;
+    L.off_chunk = o; o += ((size_t)nchunks * 16 + 127) / 128 * 128;
+    L.off_ring = o; o += (size_t)CS_NST * CS_STAGE_BYTES;
+    L.total = o;
+    return L;
+}
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void *bar, unsigned parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, unsigned bytes, void *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void cta_issue_chunk(const PlanDev &p, const double2 *lu, unsigned char *ring,
+                                                unsigned long long *bars, int c, int4 ch) {
+    const int stage = c % CS_NST;
+    unsigned char *sb = ring + (size_t)stage * CS_STAGE_BYTES;
+    const int s0 = ch.z, ns = ch.w;
+    const int t0 = s0 & ~1, tn = ((s0 + ns + 1) & ~1) - t0;
+    mbar_expect_tx(bars + stage, (unsigned)(ns * 32 + tn * 8));
+    bulk_g2s(sb, lu + (size_t)s0 * 2, (unsigned)(ns * 32), bars + stage);
+    bulk_g2s(sb + CS_CH * 32, p.scm + (size_t)t0 * 2, (unsigned)(tn * 8), bars + stage);
+}
+
+__global__ void __launch_bounds__(CS_T) k_solve_cta(PlanDev p, WorkDev w, int side) {
+    using Sy = helm::Symbolic;
+    TL_SCOPE(w, 2);
+    extern __shared__ __align__(128) unsigned char smem_c[];
+    const int grp = blockIdx.x;                              // G = 1: one scenario per CTA
+    {
+        int gfl = w.g_flags[grp];
+        if (side ? !(gfl & GF_FACTORING) : (gfl & (GF_DONE | GF_FACTORING)) != 0) return;
+    }
+    if (w.s_status[grp] != ST_ACTIVE) return;
+    const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+    const int N = p.N, nchunks = p.nschunks;
+    const CtaSolveLayout L = cta_solve_layout(N, p.nwaves, nchunks);
+    unsigned long long *bars = (unsigned long long *)smem_c;           // [0..NST-1] ring stages, [NST] x + tables
+    double2 *carry_s = (double2 *)(smem_c + L.off_carry);              // [0] acc, [1..2] inverted pivot
+    double2 *xs = (double2 *)(smem_c + L.off_x);
+    const int2 *swave = (const int2 *)(smem_c + L.off_wave);
+    const int4 *schunk = (const int4 *)(smem_c + L.off_chunk);
+    unsigned char *ring = smem_c + L.off_ring;
+    const double2 *lu = w.lu + (size_t)grp * p.nslots * 2;
+    const double2 *rhs = w.rhs + (size_t)grp * N;
+    double2 *xb = w.xb + (size_t)grp * N;
+    if (tid == 0) {
+        for (int i = 0; i <= CS_NST; ++i) mbar_init(bars + i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned wbytes = (unsigned)((p.nwaves + 1) / 2 * 16), cbytes = (unsigned)(nchunks * 16);
+        mbar_expect_tx(bars + CS_NST, (unsigned)(N * 16) + wbytes + cbytes);
+        bulk_g2s(xs, rhs, (unsigned)(N * 16), bars + CS_NST);
+        bulk_g2s((void *)swave, p.wave_tab, wbytes, bars + CS_NST);
+        bulk_g2s((void *)schunk, p.solve_chunks, cbytes, bars + CS_NST);
+        for (int c = 0; c < CS_NST && c < nchunks; ++c) cta_issue_chunk(p, lu, ring, bars, c, __ldg(p.solve_chunks + c));
+    }
+    TL_CLK_DECL;
+    mbar_wait(bars + CS_NST, 0);
+    TL_CLK_ADD(w, 1);
+    const double2 zero = make_double2(0.0, 0.0);
+    for (int c = 0; c < nchunks; ++c) {
+        const int stage = c % CS_NST;
+        const int4 ch = schunk[c];
+        mbar_wait(bars + stage, (unsigned)((c / CS_NST) & 1));
+        TL_CLK_ADD(w, 2);
+        const unsigned char *sb = ring + (size_t)stage * CS_STAGE_BYTES;
+        const double2 *slu = (const double2 *)sb;
+        const int2 *stab = (const int2 *)(sb + CS_CH * 32);
+        const int tab0 = ch.z & ~1;
+        int wv = ch.x;
+        const int wend = ch.x + ch.y;
+        bool fresh = true;                                   // a block barrier has just been passed
+        while (wv < wend) {
+            int r = wv + 1;
+            while (r < wend && !(swave[r].y & Sy::WAVE_SYNC)) ++r;
+            if ((swave[wv].y & Sy::WAVE_SYNC) && !fresh) __syncthreads();
+            fresh = false;
+            for (int k = wv + wp; k < r; k += CS_NWARP) {
+                const int2 wi = swave[k];
+                const int info = wi.y, n = info & 63;
+                double2 m0 = zero, m1 = zero;
+                int col = 0, meta = Sy::META_DIAG;
+                if (lane < n) {
+                    const int idx = wi.x - ch.z + lane;
+                    m0 = slu[2 * idx];
+                    m1 = slu[2 * idx + 1];
+                    const int2 t = stab[wi.x + lane - tab0];
+                    col = t.x; meta = t.y;
+                }
+                double2 xg = zero;
+                if (!(meta & Sy::META_DIAG)) xg = xs[col];
+                double2 v = make_double2(m0.x * xg.x + m0.y * xg.y, m1.x * xg.x + m1.y * xg.y);
+                const int span = meta & 31, maxspan = (info >> 9) & 31;
+                for (int o = 1; o <= maxspan; o <<= 1) {
+                    double tx = __shfl_down_sync(0xFFFFFFFFu, v.x, o);
+                    double ty = __shfl_down_sync(0xFFFFFFFFu, v.y, o);
+                    if (o <= span) { v.x += tx; v.y += ty; }
+                }
+                if (meta & Sy::META_HEAD) {
+                    const int row = meta >> 9;
+                    const bool rs = (meta & Sy::META_ROWSTART) != 0;
+                    const double2 b = rs ? xs[row] : carry_s[0];
+                    const double2 acc = make_double2(b.x - v.x, b.y - v.y);
+                    if (meta & Sy::META_ROWEND) {
+                        double2 out = acc;
+                        if (info & Sy::WAVE_ISU) {
+                            const double2 d0 = rs ? m0 : carry_s[1];
+                            const double2 d1 = rs ? m1 : carry_s[2];
+                            out = make_double2(d0.x * acc.x + d0.y * acc.y, d1.x * acc.x + d1.y * acc.y);
+                        }
+                        xs[row] = out;
+                    } else {                                 // continued in the next wave (which is SYNC)
+                        carry_s[0] = acc;
+                        if ((info & Sy::WAVE_ISU) && rs) { carry_s[1] = m0; carry_s[2] = m1; }
+                    }
+                }
+            }
+            wv = r;
+        }
+        TL_CLK_ADD(w, 3);
+        __syncthreads();                                     // the stage is free; also a level boundary
+        if (tid == 0 && c + CS_NST < nchunks) cta_issue_chunk(p, lu, ring, bars, c + CS_NST, schunk[c + CS_NST]);
+        TL_CLK_ADD(w, 4);
+    }
+    for (int i = tid; i < N; i += CS_T) xb[i] = xs[i];
+    TL_CLK_ADD(w, 5);
 }
 
 // ---- K2 (G = 1, N*16 B fits in shared memory): shared-memory solve ------------------------------
@@ -1168,19 +1374,19 @@ __device__ __forceinline__ void eps2_step(Eps2State &st, int t, int j, double2 v
 }
 
 // O(j) loop of a PQ bus at order j: W recurrence (+ two epsilon anti-diagonals when EPS).
-template <bool EPS>
+template <bool EPS, int KU>
 __device__ __forceinline__ double2 conv_loop_pq(int j, double2 v, double2 vjm1, const double2 *Vb, const double2 *Hb,
                                                 double2 *Eb, size_t plane, Eps2State &es) {
     const double2 zero = make_double2(0.0, 0.0);
     double2 aux = zero;
     for (int t0 = 1; t0 <= j; t0 += KU) {
-        double2 vr[KU], eo[KU], hh[KU];
+        double2 vr[KU], eo[EPS ? KU : 1], hh[KU];
 #pragma unroll
         for (int u = 0; u < KU; ++u) {
             int t = t0 + u;
             if (t <= j) {
                 vr[u] = (t == 1) ? v : Vb[(size_t)(j + 1 - t) * plane];
-                if (EPS) eo[u] = (t < j - 1) ? Eb[(size_t)t * plane] : zero;
+                if (EPS) eo[EPS ? u : 0] = (t < j - 1) ? Eb[(size_t)t * plane] : zero;
                 hh[u] = Hb[(size_t)(t - 1) * plane];                              // W[t-1]
             }
         }
@@ -1188,7 +1394,7 @@ __device__ __forceinline__ double2 conv_loop_pq(int j, double2 v, double2 vjm1, 
         for (int u = 0; u < KU; ++u) {
             int t = t0 + u;
             if (t <= j) {
-                if (EPS) eps2_step(es, t, j, vjm1, v, eo[u], Eb, plane);
+                if (EPS) eps2_step(es, t, j, vjm1, v, eo[EPS ? u : 0], Eb, plane);
                 aux = cadd(aux, cmul(hh[u], vr[u]));                              // helm.py:430-432
             }
         }
@@ -1197,19 +1403,19 @@ __device__ __forceinline__ double2 conv_loop_pq(int j, double2 v, double2 vjm1, 
 }
 
 // O(j) loop of a PV bus (model 2) at order j: P-row convolution, |V|^2 convolution (+ epsilon).
-template <bool EPS>
+template <bool EPS, int KU>
 __device__ __forceinline__ void conv_loop_pv(int j, double2 v, double2 vjm1, double2 PP, const double2 *Vb,
                                              const double2 *Hb, double2 *Eb, size_t plane, Eps2State &es,
                                              double2 &ppp, double &vvre) {
     const double2 zero = make_double2(0.0, 0.0);
     for (int t0 = 1; t0 <= j; t0 += KU) {
-        double2 vr[KU], eo[KU], hh[KU], vf[KU];
+        double2 vr[KU], eo[EPS ? KU : 1], hh[KU], vf[KU];
 #pragma unroll
         for (int u = 0; u < KU; ++u) {
             int t = t0 + u;
             if (t <= j) {
                 vr[u] = (t == 1) ? v : Vb[(size_t)(j + 1 - t) * plane];
-                if (EPS) eo[u] = (t < j - 1) ? Eb[(size_t)t * plane] : zero;
+                if (EPS) eo[EPS ? u : 0] = (t < j - 1) ? Eb[(size_t)t * plane] : zero;
                 hh[u] = (t < j) ? Hb[(size_t)t * plane] : PP;                     // CC[t]
                 vf[u] = (t < j) ? Vb[(size_t)t * plane] : v;                      // V[t]
             }
@@ -1218,7 +1424,7 @@ __device__ __forceinline__ void conv_loop_pv(int j, double2 v, double2 vjm1, dou
         for (int u = 0; u < KU; ++u) {
             int t = t0 + u;
             if (t <= j) {
-                if (EPS) eps2_step(es, t, j, vjm1, v, eo[u], Eb, plane);
+                if (EPS) eps2_step(es, t, j, vjm1, v, eo[EPS ? u : 0], Eb, plane);
                 ppp = cadd(ppp, cmulc(hh[u], vr[u]));                             // helm.py:306-314
                 vvre += vf[u].x * vr[u].x + vf[u].y * vr[u].y;                    // helm.py:356-361
             }
@@ -1231,8 +1437,15 @@ __device__ __forceinline__ void conv_loop_pv(int j, double2 v, double2 vjm1, dou
 #ifndef RHS_MINB
 #define RHS_MINB 4
 #endif
-template <int G>
-__global__ void __launch_bounds__(128, RHS_MINB) k_rhs_conv(PlanDev p, WorkDev w) {
+// FUSED = false: the epsilon table and the Pade check run in their own kernel (k_eps); this one
+// then only carries the convolution state and runs with twice the loads in flight per thread.
+#ifndef CONV_MINB
+#define CONV_MINB 6
+#define CONV_KU_PQ 6
+#define CONV_KU_PV 4
+#endif
+template <int G, bool FUSED>
+__global__ void __launch_bounds__(128, FUSED ? RHS_MINB : CONV_MINB) k_rhs_conv(PlanDev p, WorkDev w) {
     TL_SCOPE(w, 3);
     const int grp = blockIdx.y;
     const int flat = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1240,7 +1453,7 @@ __global__ void __launch_bounds__(128, RHS_MINB) k_rhs_conv(PlanDev p, WorkDev w
     if (i >= p.N) return;
     const int N = p.N;
     const int sg = grp * G + s;
-    const size_t plane = (size_t)N * G;
+    const size_t plane = hplane<G>();
     const size_t bi = ix<G>(grp, N, i, s);
     const size_t h0 = hx<G>(w, N, grp, 0, i, s);
     double2 *Vb = w.Vh + h0, *Hb = w.Hh + h0, *Eb = w.Eh + h0;
@@ -1278,7 +1491,7 @@ __global__ void __launch_bounds__(128, RHS_MINB) k_rhs_conv(PlanDev p, WorkDev w
     const double2 zero = make_double2(0.0, 0.0);
     // The epsilon table advances by two anti-diagonals at every even order (the orders at which
     // the Pade value is needed, helm.py:611); odd orders do not touch it.
-    const bool even = (j & 1) == 0;
+    const bool even = FUSED && (j & 1) == 0;
     Eps2State es;
     es.o1 = e_old0;                                        // eps_0^(j-2) = S_{j-2}
     es.o2 = zero;                                          // eps_{-1} = 0
@@ -1288,8 +1501,10 @@ __global__ void __launch_bounds__(128, RHS_MINB) k_rhs_conv(PlanDev p, WorkDev w
     if (even) Eb[0] = es.b1;
     double2 out;
     if (bt == HELM_BUS_PQ) {
-        double2 aux = even ? conv_loop_pq<true>(j, v, vjm1, Vb, Hb, Eb, plane, es)
-                           : conv_loop_pq<false>(j, v, vjm1, Vb, Hb, Eb, plane, es);
+        double2 aux;
+        if (FUSED) aux = even ? conv_loop_pq<true, KU>(j, v, vjm1, Vb, Hb, Eb, plane, es)
+                              : conv_loop_pq<false, KU>(j, v, vjm1, Vb, Hb, Eb, plane, es);
+        else aux = conv_loop_pq<false, CONV_KU_PQ>(j, v, vjm1, Vb, Hb, Eb, plane, es);
         double2 wj = make_double2(-aux.x, -aux.y);
         Hb[(size_t)j * plane] = wj;                                               // W[j]
         // RHS of order j+1 (helm.py:367-385)
@@ -1309,8 +1524,12 @@ __global__ void __launch_bounds__(128, RHS_MINB) k_rhs_conv(PlanDev p, WorkDev w
         Hb[(size_t)j * plane] = PP;                                               // barras_CC[i][n-1]
         double2 ppp = zero;
         double vvre = 0.0;
-        if (even) conv_loop_pv<true>(j, v, vjm1, PP, Vb, Hb, Eb, plane, es, ppp, vvre);
-        else conv_loop_pv<false>(j, v, vjm1, PP, Vb, Hb, Eb, plane, es, ppp, vvre);
+        if (FUSED) {
+            if (even) conv_loop_pv<true, KU>(j, v, vjm1, PP, Vb, Hb, Eb, plane, es, ppp, vvre);
+            else conv_loop_pv<false, KU>(j, v, vjm1, PP, Vb, Hb, Eb, plane, es, ppp, vvre);
+        } else {
+            conv_loop_pv<false, CONV_KU_PV>(j, v, vjm1, PP, Vb, Hb, Eb, plane, es, ppp, vvre);
+        }
         double cc_ = 0.0 - ppp.x;
         if (ysh.x != 0.0) {                                                      // conduc_buses
             if (j >= 2) cc_ -= ysh.x * (w.VVant[bi] + 2.0 * v.x);                // helm.py:317-318
@@ -1346,6 +1565,68 @@ __global__ void __launch_bounds__(128, RHS_MINB) k_rhs_conv(PlanDev p, WorkDev w
         }
         w.Pcur[bi] = cur;
     }
+}
+
+// ---- K3: epsilon table + Pade check on their own (even orders only) ---------------------------
+// Thread per (bus, scenario).  Reads the stored anti-diagonal j-2, appends the anti-diagonals j-1 and
+// j (eps2_step) and compares the new Pade value with the previous one (helm.py:608-641).  Runs
+// beside k_rhs_conv<G, false>: both only read x and the V history.
+#ifndef EPS_MINB
+#define EPS_MINB 8
+#define EPS_KE 6
+#endif
+constexpr int KE = EPS_KE;
+template <int G>
+__global__ void __launch_bounds__(128, EPS_MINB) k_eps(PlanDev p, WorkDev w) {
+    TL_SCOPE(w, 3);
+    const int grp = blockIdx.y;
+    const int gf = w.g_flags[grp];
+    const int j = w.g_n[grp] + 1;                          // order just solved
+    if ((j & 1) || (gf & (GF_DONE | GF_PASSEND | GF_FACTORING))) return;   // uniform per CTA (G scenarios share j)
+    const int flat = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = flat / G, s = flat % G;
+    if (i >= p.N) return;
+    const int N = p.N;
+    const int sg = grp * G + s;
+    const size_t plane = hplane<G>();
+    const size_t bi = ix<G>(grp, N, i, s);
+    const size_t h0 = hx<G>(w, N, grp, 0, i, s);
+    const double2 *Vb = w.Vh + h0;
+    double2 *Eb = w.Eh + h0;
+    const int status = w.s_status[sg];
+    const unsigned char bt = w.btype[bi];
+    const double2 v = w.xb[(size_t)grp * N * G + (size_t)i * G + s];
+    const double2 e_old0 = Eb[0];
+    const double2 vjm1 = Vb[(size_t)(j - 1) * plane];
+    const double2 pold = w.Pcur[bi];
+    if (status != ST_ACTIVE || bt == HELM_BUS_SLACK) return;
+    const double2 zero = make_double2(0.0, 0.0);
+    Eps2State es;
+    es.o1 = e_old0; es.o2 = zero;
+    es.a1 = cadd(e_old0, vjm1); es.a2 = zero;
+    es.b1 = cadd(es.a1, v);
+    Eb[0] = es.b1;
+    for (int t0 = 1; t0 <= j; t0 += KE) {
+        double2 eo[KE];
+#pragma unroll
+        for (int u = 0; u < KE; ++u) {
+            int t = t0 + u;
+            eo[u] = (t < j - 1) ? Eb[(size_t)t * plane] : zero;
+        }
+#pragma unroll
+        for (int u = 0; u < KE; ++u) {
+            int t = t0 + u;
+            if (t <= j) eps2_step(es, t, j, vjm1, v, eo[u], Eb, plane);
+        }
+    }
+    const double2 cur = es.b1;                             // [j/2 / j/2] Pade at s = 1
+    if (j >= 4) {                                          // helm.py:611: m > 3
+        double mag1 = hypot(pold.x, pold.y), rad1 = atan2(pold.y, pold.x);
+        double mag2 = hypot(cur.x, cur.y), rad2 = atan2(cur.y, cur.x);
+        bool ok = (fabs(mag1 - mag2) <= w.mismatch) && (fabs(rad1 - rad2) <= w.mismatch);  // helm.py:618
+        if (!ok) w.s_fail[sg] = 1;
+    }
+    w.Pcur[bi] = cur;
 }
 
 // ---- K_adv: per-group bookkeeping after an order (helm.py:608-657 control flow) ----------
@@ -1493,11 +1774,16 @@ __global__ void k_step_begin(WorkDev w) {
 #endif
     int grp = blockIdx.x * blockDim.x + threadIdx.x;
     if (grp >= w.ngroups) return;
-    if (grp == 0) w.fact_count[w.parity ^ 1] = 0;          // the list of the next step starts empty
+    // the list of the next step starts empty (its previous user, depth + 1 steps ago, has been joined)
+    if (grp == 0) w.fact_count[(w.parity + 1) % (w.depth + 1)] = 0;
     int gf = w.g_flags[grp];
-    if (gf & GF_FACTORING) gf &= ~(GF_FACTORING | GF_NEWSCEN);
-    else if (gf & GF_PENDING) {
+    if (gf & GF_FACTORING) {
+        int age = w.g_fage[grp] - 1;
+        w.g_fage[grp] = age;
+        if (age <= 0) gf &= ~(GF_FACTORING | GF_NEWSCEN);
+    } else if (gf & GF_PENDING) {
         gf = (gf & ~GF_PENDING) | GF_FACTORING;
+        w.g_fage[grp] = w.depth;
         int pos = atomicAdd(&w.fact_count[w.parity], 1);
         w.fact_list[(size_t)w.parity * w.ngroups + pos] = grp;
     }
@@ -1533,7 +1819,7 @@ __global__ void k_setup(PlanDev p, WorkDev w, const double *scale_in) {
         if (grp == 0) {
             *w.active_groups = w.ngroups;
             *w.queue_next = w.ngroups * G;      // slots 0..Bp-1 start with scenarios 0..Bp-1
-            w.fact_count[0] = 0; w.fact_count[1] = 0;
+            for (int k = 0; k <= MAX_SIDE_DEPTH; ++k) w.fact_count[k] = 0;
         }
     }
 }
@@ -1575,8 +1861,8 @@ struct helm_plan {
     double *h_vout_pinned = nullptr;
     size_t h_vout_bytes = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t side = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t side[MAX_SIDE_DEPTH] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[MAX_SIDE_DEPTH] = {nullptr, nullptr, nullptr};
     unsigned long long *tl = nullptr;
     int *d_outage = nullptr;      // pending N-1 list for the next solve (helm_plan_set_outages)
     int outage_n = 0;
@@ -1627,7 +1913,7 @@ WsLayout layout(const helm_plan *pl, int B, const helm_params *prm) {
     auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes); return r; };
     L.off_scale = take(sizeof(double) * L.Bp);
     L.off_sint = take(sizeof(int) * L.Bp * (8 + HELM_MAX_PASSES));
-    L.off_gint = take(sizeof(int) * (4 * L.ngroups + 8));
+    L.off_gint = take(sizeof(int) * ((4 + MAX_SIDE_DEPTH) * L.ngroups + 16));
     L.off_btype = take(per);
     L.off_Qg = take(per * sizeof(double));
     L.off_VVant = take(per * sizeof(double));
@@ -1635,9 +1921,10 @@ WsLayout layout(const helm_plan *pl, int B, const helm_params *prm) {
     L.off_rhs = take(per * sizeof(double2));
     L.off_xb = take(per * sizeof(double2));
     L.off_lu = take((size_t)L.Bp * pl->S.nslots * 2 * sizeof(double2));
-    L.off_Vh = take(per * L.K * sizeof(double2));
-    L.off_Hh = take(per * L.K * sizeof(double2));
-    L.off_Eh = take(per * L.K * sizeof(double2));
+    const size_t per_h = (size_t)L.Bp * ((N + HT - 1) / HT * HT);   // histories are tiled by HT buses
+    L.off_Vh = take(per_h * L.K * sizeof(double2));
+    L.off_Hh = take(per_h * L.K * sizeof(double2));
+    L.off_Eh = take(per_h * L.K * sizeof(double2));
     L.off_var_s = L.off_ploss = L.off_zb = L.off_Qh = L.off_vre = L.off_qcur = 0;
     if (prm->dsb_method) {
         L.off_var_s = take(sizeof(double) * 4 * L.Bp);
@@ -1664,7 +1951,8 @@ WorkDev bind(const helm_plan *pl, const WsLayout &L, int B, const helm_params *p
     w.s_npass = si + 4 * L.Bp; w.s_nswitch = si + 5 * L.Bp; w.slot_scen = si + 6 * L.Bp; w.o_b = si + 7 * L.Bp; w.s_ncoef = si + 8 * L.Bp;
     int *gi = (int *)(b + L.off_gint);
     w.g_n = gi; w.g_flags = gi + L.ngroups; w.active_groups = gi + 2 * L.ngroups; w.queue_next = gi + 2 * L.ngroups + 1;
-    w.fact_count = gi + 2 * L.ngroups + 2; w.fact_list = gi + 2 * L.ngroups + 8; w.parity = 0;
+    w.fact_count = gi + 2 * L.ngroups + 2; w.g_fage = gi + 2 * L.ngroups + 16; w.fact_list = gi + 3 * L.ngroups + 16; w.parity = 0;
+    w.depth = 1;
     w.scale_in = nullptr; w.outage_in = nullptr; w.out_status = nullptr; w.out_ncoef = nullptr; w.out_nswitch = nullptr;
     w.btype = (unsigned char *)(b + L.off_btype);
     w.Qg = (double *)(b + L.off_Qg);
@@ -1728,13 +2016,16 @@ void launch_kernel(int which, const PlanDev &p, const WorkDev &w, cudaStream_t s
         case KI_PV1C_MAIN: k_pv1_correct<<<gridBus, T_ELEM, 0, st>>>(p, w, 0); break;
         case KI_PV1C_SIDE: k_pv1_correct<<<gridBus, T_ELEM, 0, st>>>(p, w, 1); break;
         case KI_SOLVE_SIDE:
-            if (p.use_flat_solve) k_solve_flat<FLAT_WPB><<<(w.ngroups + FLAT_WPB - 1) / FLAT_WPB, FLAT_WPB * 32, 0, st>>>(p, w, 1);
+            if (p.use_cta_solve) k_solve_cta<<<w.ngroups, CS_T, cta_solve_layout(p.N, p.nwaves, p.nschunks).total, st>>>(p, w, 1);
+            else if (p.use_flat_solve) k_solve_flat<FLAT_WPB><<<(w.ngroups + FLAT_WPB - 1) / FLAT_WPB, FLAT_WPB * 32, 0, st>>>(p, w, 1);
             else k_solve_warp<WPB_SOLVE><<<(w.ngroups + WPB_SOLVE - 1) / WPB_SOLVE, WPB_SOLVE * 32, 0, st>>>(p, w, 1);
             break;
         case KI_SOLVE:
             // shared-memory solve for small batches (<= ~3 CTAs per SM of concurrency is enough);
             // large batches keep more scenarios in flight with the warp-per-scenario kernel
-            if (G == 1 && p.use_smem_solve && w.ngroups <= p.smem_solve_max_groups) {
+            if (G == 1 && p.use_cta_solve && w.ngroups <= p.cta_solve_max_groups) {
+                k_solve_cta<<<w.ngroups, CS_T, cta_solve_layout(p.N, p.nwaves, p.nschunks).total, st>>>(p, w, 0);
+            } else if (G == 1 && p.use_smem_solve && w.ngroups <= p.smem_solve_max_groups) {
                 k_solve_smem<<<w.ngroups, SM_T, solve_smem_bytes(p.N, p.nring, p.nsteps), st>>>(p, w);
             } else if (G == 1 && p.use_flat_solve) {
                 k_solve_flat<FLAT_WPB><<<(w.ngroups + FLAT_WPB - 1) / FLAT_WPB, FLAT_WPB * 32, 0, st>>>(p, w, 0);
@@ -1746,7 +2037,10 @@ void launch_kernel(int which, const PlanDev &p, const WorkDev &w, cudaStream_t s
             break;
         case KI_RHS:
             if (w.pv_model == 1 || w.dsb_method) k_rhs_conv_var<<<gridBus, T_ELEM, 0, st>>>(p, w);
-            else k_rhs_conv<G><<<dim3((p.N * G + 127) / 128, w.ngroups), 128, 0, st>>>(p, w);
+            else if (p.split_eps) {
+                k_eps<G><<<dim3((p.N * G + 127) / 128, w.ngroups), 128, 0, st>>>(p, w);
+                k_rhs_conv<G, false><<<dim3((p.N * G + 127) / 128, w.ngroups), 128, 0, st>>>(p, w);
+            } else k_rhs_conv<G, true><<<dim3((p.N * G + 127) / 128, w.ngroups), 128, 0, st>>>(p, w);
             break;
         case KI_ADV: k_advance<<<gridGrp, 128, 0, st>>>(w); break;
         case KI_QLIM: k_qlimit<G><<<gridBus, T_ELEM, 0, st>>>(p, w); break;
@@ -1794,10 +2088,10 @@ struct StepSeq {
 };
 // default: main = solve, rhs_conv, advance, qlimit, pass_end; side = assemble, factor, init.
 // Variants (helm_variants.cuh) add the bordered-system kernels and the PV-model-1 fix-ups.
-StepSeq make_seq(const WorkDev &w) {
+StepSeq make_seq(const WorkDev &w, bool fused_asm) {
     StepSeq q;
     const bool dsb = w.dsb_method != 0, pv1 = w.pv_model == 1;
-    q.side_seq[q.side_len++] = KI_ASM;
+    if (!fused_asm) q.side_seq[q.side_len++] = KI_ASM;     // k_factor_coop assembles A itself
     q.side_seq[q.side_len++] = KI_FACTOR;
     if (dsb) { q.side_seq[q.side_len++] = KI_BPREP; q.side_seq[q.side_len++] = KI_SOLVE_SIDE; q.side_seq[q.side_len++] = KI_BFIN; }
     q.side_seq[q.side_len++] = KI_INIT;
@@ -1815,13 +2109,18 @@ StepSeq make_seq(const WorkDev &w) {
 constexpr int STEP_LEN_MAX = 1 + 2 * SEQ_MAX;
 
 struct StepCtx {
-    cudaStream_t st, side;
-    cudaEvent_t fork, join;
+    cudaStream_t st;
+    const cudaStream_t *side;      // [depth]
+    cudaEvent_t fork;
+    const cudaEvent_t *join;       // [depth]
+    int depth;
 };
 
-void launch_step(int G, const PlanDev &p, const WorkDev &w_in, const StepCtx &c, const StepSeq &q, int parity) {
+void launch_step(int G, const PlanDev &p, const WorkDev &w_in, const StepCtx &c, const StepSeq &q, long step,
+                 bool last_of_batch) {
     WorkDev w = w_in;
-    w.parity = parity & 1;
+    const int D = c.depth;
+    w.parity = (int)(step % (D + 1));
     static const bool nofork = getenv("HELM_B200_NOFORK") != nullptr;   // A/B switch: serial step
     if (nofork) {
         launch_any(G, KI_BEGIN, p, w, c.st);
@@ -1829,20 +2128,27 @@ void launch_step(int G, const PlanDev &p, const WorkDev &w_in, const StepCtx &c,
         for (int k = 0; k < q.main_len; ++k) launch_any(G, q.main_seq[k], p, w, c.st);
         return;
     }
+    // The side branch of step k has `depth` steps to finish: it is joined at the end of step
+    // k + depth - 1, and the groups it factorizes rejoin at the k_step_begin of step k + depth.
+    const int sl = (int)(step % D);
     launch_any(G, KI_BEGIN, p, w, c.st);
     cudaEventRecord(c.fork, c.st);
-    cudaStreamWaitEvent(c.side, c.fork, 0);
-    for (int k = 0; k < q.side_len; ++k) launch_any(G, q.side_seq[k], p, w, c.side);
-    cudaEventRecord(c.join, c.side);
+    cudaStreamWaitEvent(c.side[sl], c.fork, 0);
+    for (int k = 0; k < q.side_len; ++k) launch_any(G, q.side_seq[k], p, w, c.side[sl]);
+    cudaEventRecord(c.join[sl], c.side[sl]);
     for (int k = 0; k < q.main_len; ++k) launch_any(G, q.main_seq[k], p, w, c.st);
-    cudaStreamWaitEvent(c.st, c.join, 0);
+    if (last_of_batch) {             // end of a graph / of a polled batch of steps: join everything
+        for (long k = std::max(0L, step - (D - 1)); k <= step; ++k) cudaStreamWaitEvent(c.st, c.join[k % D], 0);
+    } else if (step - (D - 1) >= 0) {
+        cudaStreamWaitEvent(c.st, c.join[(step - (D - 1)) % D], 0);
+    }
 }
 
 // serial variant with an event around every kernel (profile mode)
 void launch_step_profiled(int G, const PlanDev &p, const WorkDev &w_in, cudaStream_t st,
-                          std::vector<cudaEvent_t> &ev, helm_stats &acc, const StepSeq &q, int parity) {
+                          std::vector<cudaEvent_t> &ev, helm_stats &acc, const StepSeq &q, long step) {
     WorkDev w = w_in;
-    w.parity = parity & 1;
+    w.parity = (int)(step % (w.depth + 1));
     int seq[STEP_LEN_MAX];
     int n = 0;
     seq[n++] = KI_BEGIN;
@@ -1958,8 +2264,16 @@ int helm_plan_create(const helm_grid_host *g, helm_plan **out) {
         if ((rc = upload(pl, S.wave_tab, &wt)) != HELM_OK) { helm_plan_destroy(pl); return rc; }
         d.wave_tab = (const int2 *)wt;
     }
-    d.nwaves = (int)S.wave_tab.size() / 2; d.n_rows_nol = S.n_rows_nol;
-    d.use_flat_solve = (S.n_rows_nol >= 0) && getenv("HELM_B200_FLAT_SOLVE") != nullptr;   // experimental (A/B)
+    d.nwaves = S.n_waves; d.n_rows_nol = S.n_rows_nol;
+    UP(S.scm, scm)
+    {
+        const int *ct = nullptr;
+        if ((rc = upload(pl, S.solve_chunks, &ct)) != HELM_OK) { helm_plan_destroy(pl); return rc; }
+        d.solve_chunks = (const int4 *)ct;
+    }
+    d.nschunks = (int)S.solve_chunks.size() / 4;
+    d.split_eps = getenv("HELM_B200_FUSED_EPS") == nullptr;
+    d.use_flat_solve = (S.n_rows_nol >= 0) && getenv("HELM_B200_NO_FLAT_SOLVE") == nullptr;
     d.nsteps = (int)S.sstep_kind.size(); d.nring = (int)S.sring_desc.size() / 8;
     d.max_row_blocks = S.max_row_blocks;
     d.nfchunks = (int)S.fchunk_lpr.size(); d.cap_upd = S.cap_upd; d.cap_ent = S.cap_ent; d.cap_rowblk = S.cap_rowblk;
@@ -1968,6 +2282,9 @@ int helm_plan_create(const helm_grid_host *g, helm_plan **out) {
         size_t smem = WPB_FACTOR * factor_smem_per_warp(pl->d.cap_upd, pl->d.cap_ent, pl->d.cap_rowblk);
         // staged factorization needs its chunk operands in shared memory; grids whose longest row
         // does not fit fall back to the unstaged warp-per-group kernel
+        if (getenv("HELM_B200_VERBOSE"))
+            fprintf(stderr, "[helm_b200] factor staging: cap_upd %d cap_ent %d cap_rowblk %d chunks %d -> %zu B per warp, %d warps per CTA\n",
+                    pl->d.cap_upd, pl->d.cap_ent, pl->d.cap_rowblk, pl->d.nfchunks, smem / WPB_FACTOR, WPB_FACTOR);
         pl->d.use_coop_factor = (smem <= 200 * 1024) && getenv("HELM_B200_NO_COOP_FACTOR") == nullptr;
         if (!pl->d.use_coop_factor) smem = 0;
         // shared-memory solve: usable when x (16 B per bus) plus the ring leaves room for >= 2 CTAs per SM
@@ -1978,6 +2295,17 @@ int helm_plan_create(const helm_grid_host *g, helm_plan **out) {
         if (pl->d.use_smem_solve && ssm > ssm_set) {
             CUDA_TRY(cudaFuncSetAttribute(k_solve_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
             ssm_set = ssm;
+        }
+        // shared-memory wave solve: x, the wave/chunk tables and the ring must fit one CTA
+        {
+            size_t csm = cta_solve_layout(pl->d.N, pl->d.nwaves, pl->d.nschunks).total;
+            static size_t csm_set = 48 * 1024;
+            pl->d.use_cta_solve = (S.n_rows_nol >= 0) && (csm <= 225 * 1024) && getenv("HELM_B200_NO_CTA_SOLVE") == nullptr;
+            pl->d.cta_solve_max_groups = getenv("HELM_B200_CTA_SOLVE_MAX") ? atoi(getenv("HELM_B200_CTA_SOLVE_MAX")) : 888;
+            if (pl->d.use_cta_solve && csm > csm_set) {
+                CUDA_TRY(cudaFuncSetAttribute(k_solve_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
+                csm_set = csm;
+            }
         }
         // the attribute is per function, not per plan: only ever raise it
         static size_t smem_set = 48 * 1024;
@@ -2004,9 +2332,11 @@ void helm_plan_destroy(helm_plan *pl) {
     if (pl->h_vout_pinned) cudaFreeHost(pl->h_vout_pinned);
     if (pl->d_outage) cudaFree(pl->d_outage);
     if (pl->stream) cudaStreamDestroy(pl->stream);
-    if (pl->side) cudaStreamDestroy(pl->side);
+    for (int k = 0; k < MAX_SIDE_DEPTH; ++k) {
+        if (pl->side[k]) cudaStreamDestroy(pl->side[k]);
+        if (pl->ev_join[k]) cudaEventDestroy(pl->ev_join[k]);
+    }
     if (pl->ev_fork) cudaEventDestroy(pl->ev_fork);
-    if (pl->ev_join) cudaEventDestroy(pl->ev_join);
     delete pl;
 }
 
@@ -2070,8 +2400,19 @@ int helm_solve_batch_device(helm_plan *pl, int32_t B, const double *d_scale, con
     const PlanDev &p = pl->d;
     const bool profile = getenv("HELM_B200_PROFILE") != nullptr;
     const bool use_graph = prm->use_graph && !profile;
-    int poll_every = prm->poll_every > 0 ? prm->poll_every : 4;
-    poll_every += poll_every & 1;      // even: the step parity of a captured graph must repeat
+    // Depth of the factorization pipeline: with depth 2 a numeric factorization (2-3 ms of dependent
+    // chunks for one warp) has two steps to finish and is never the critical path of a step; the
+    // price is one more idle step per pass for the scenario being factorized.  Kernels that select
+    // their groups by flag instead of by list (variants, generic G > 1) need depth 1.
+    int depth = 2;
+    if (getenv("HELM_B200_SIDE_DEPTH")) depth = std::max(1, std::min(MAX_SIDE_DEPTH, atoi(getenv("HELM_B200_SIDE_DEPTH"))));
+    if (!(L.G == 1 && p.use_coop_factor) || prm->dsb_method || prm->pv_bus_model == 1) depth = 1;
+    w.depth = depth;
+    // steps per graph launch / per poll: a multiple of depth * (depth + 1) so that list and stream
+    // indices repeat from one graph launch to the next
+    const int cyc = depth * (depth + 1);
+    int poll_every = prm->poll_every > 0 ? prm->poll_every : 12;
+    poll_every = (poll_every + cyc - 1) / cyc * cyc;
     if (!pl->h_pinned) CUDA_TRY(cudaMallocHost((void **)&pl->h_pinned, 64));
 
 #ifdef HELM_TIMELINE
@@ -2097,23 +2438,26 @@ int helm_solve_batch_device(helm_plan *pl, int32_t B, const double *d_scale, con
     memset(&local, 0, sizeof(local));
     local.kernel_launches = 1;
 
-    if (!pl->side) {
-        // No stream priority for the side branch: measured (profiles/, timeline r1) that pending
-        // high-priority CTAs that do not fit (shared-memory limit) block the main branch's CTAs.
-        CUDA_TRY(cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking));
-    }
-    if (!pl->ev_fork) {
+    if (!pl->side[0]) {
+        // The side branch has few, long-running CTAs: with the higher priority they take a free slot
+        // before the next CTA of the (much larger) main-branch grids does.  HELM_B200_SIDE_PRIO=0: A/B.
+        int lo = 0, hi = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        const char *sp = getenv("HELM_B200_SIDE_PRIO");
+        for (int k = 0; k < MAX_SIDE_DEPTH; ++k) {
+            CUDA_TRY(cudaStreamCreateWithPriority(&pl->side[k], cudaStreamNonBlocking, (sp && atoi(sp) == 0) ? lo : hi));
+            CUDA_TRY(cudaEventCreateWithFlags(&pl->ev_join[k], cudaEventDisableTiming));
+        }
         CUDA_TRY(cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&pl->ev_join, cudaEventDisableTiming));
     }
-    StepCtx ctx{st, pl->side, pl->ev_fork, pl->ev_join};
-    const StepSeq seq = make_seq(w);
+    StepCtx ctx{st, pl->side, pl->ev_fork, pl->ev_join, depth};
+    const StepSeq seq = make_seq(w, L.G == 1 && p.use_coop_factor);
     const int STEP_LEN = 1 + seq.main_len + seq.side_len;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t gexec = nullptr;
     if (use_graph) {
         CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        for (int rep = 0; rep < poll_every; ++rep) launch_step(L.G, p, w, ctx, seq, rep);
+        for (int rep = 0; rep < poll_every; ++rep) launch_step(L.G, p, w, ctx, seq, rep, rep == poll_every - 1);
         CUDA_TRY(cudaStreamEndCapture(st, &graph));
         CUDA_TRY(cudaGraphInstantiate(&gexec, graph, 0));
     }
@@ -2133,8 +2477,8 @@ int helm_solve_batch_device(helm_plan *pl, int32_t B, const double *d_scale, con
             steps += poll_every;
         } else {
             for (int rep = 0; rep < poll_every; ++rep) {
-                if (profile) launch_step_profiled(L.G, p, w, st, pev, local, seq, (int)steps);
-                else launch_step(L.G, p, w, ctx, seq, (int)steps);
+                if (profile) launch_step_profiled(L.G, p, w, st, pev, local, seq, steps);
+                else launch_step(L.G, p, w, ctx, seq, steps, rep == poll_every - 1);
                 local.kernel_launches += STEP_LEN;
                 steps++;
             }

@@ -390,7 +390,13 @@ bool build_symbolic(int N, const int32_t *adj_ptr, const int32_t *adj_idx, const
                 if (first_of_level && w_n == 0) { w_flags |= Symbolic::WAVE_SYNC; first_of_level = false; }
                 put(s0 + done, take, row, done == 0, done + take == n, isU && done == 0);
                 done += take;
-                if (done < n) { w_flags |= Symbolic::WAVE_CONT; flush(); }
+                if (done < n) {                 // the continuation is ordered after this wave; a wave that
+                                                // hands on a carry is ordered after the previous one, so
+                                                // the single carry slot of k_solve_cta is never contended
+                    w_flags |= Symbolic::WAVE_CONT | Symbolic::WAVE_SYNC;
+                    flush();
+                    w_flags |= Symbolic::WAVE_SYNC;
+                }
             }
         };
         for (int l = 0; l < nLlev; ++l) {
@@ -408,6 +414,38 @@ bool build_symbolic(int N, const int32_t *adj_ptr, const int32_t *adj_idx, const
             for (int q = S.ulev_ptr[l]; q < S.ulev_ptr[l + 1]; ++q)
                 add_row(S.slotD(q), 1 + (S.uptr[q + 1] - S.uptr[q]), S.urow[q], true, first);
             flush();
+        }
+        // chunks of the shared-memory solve (k_solve_cta): consecutive waves covering at most
+        // SOLVE_CHUNK_SLOTS slots, copied into a shared-memory ring with one bulk copy each for the
+        // factor blocks and for the {column, meta} table
+        S.scm.resize((size_t)S.nslots * 2 + 2, 0);
+        for (int e = 0; e < S.nslots; ++e) {
+            int col;
+            if (e < S.nL) col = S.lcol[e];
+            else col = -1;
+            S.scm[2 * e] = col;
+            S.scm[2 * e + 1] = S.smeta[e];
+        }
+        for (int q = 0; q < N; ++q) {
+            S.scm[2 * S.slotD(q)] = S.urow[q];
+            for (int t = 0; t < S.uptr[q + 1] - S.uptr[q]; ++t) S.scm[2 * S.slotU(q, t)] = S.ucol[S.uptr[q] + t];
+        }
+        {
+            const int nwv = (int)S.wave_tab.size() / 2;
+            S.n_waves = nwv;
+            int wv = 0;
+            while (wv < nwv) {
+                int w0 = wv, s0 = S.wave_tab[2 * wv], ns = 0;
+                while (wv < nwv && ns + (S.wave_tab[2 * wv + 1] & 63) <= Symbolic::SOLVE_CHUNK_SLOTS) {
+                    ns += S.wave_tab[2 * wv + 1] & 63;
+                    ++wv;
+                }
+                S.solve_chunks.push_back(w0);
+                S.solve_chunks.push_back(wv - w0);
+                S.solve_chunks.push_back(s0);
+                S.solve_chunks.push_back(ns);
+            }
+            if (nwv & 1) { S.wave_tab.push_back(0); S.wave_tab.push_back(0); }   // 16-byte multiple
         }
         // rows without L entries get x = rhs directly; they must form a prefix of the numbering
         S.n_rows_nol = 0;

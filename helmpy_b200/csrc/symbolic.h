@@ -53,6 +53,10 @@ struct Symbolic {
     // consecutive slots.  wave_tab: 2 ints per wave {first slot, n | flags | maxspan << 9};
     // smeta[slot]: span (lanes after this one in its row piece) | flags | row << 9.
     std::vector<int> wave_tab, smeta;
+    // k_solve_cta: scm = {column, meta} per slot; solve_chunks = 4 ints per chunk {first wave, waves, first slot, slots}
+    std::vector<int> scm, solve_chunks;
+    int n_waves = 0;                             // waves (wave_tab may carry one padding entry)
+    static constexpr int SOLVE_CHUNK_SLOTS = 128;
     int n_waves_l = 0;                           // waves of the forward solve (the rest is backward)
     int n_rows_nol = 0;                          // rows [0, n_rows_nol) have no L entries (-1: not a prefix)
     static constexpr int WAVE_SYNC = 64, WAVE_CONT = 128, WAVE_ISU = 256;          // n in bits 0-5

@@ -174,19 +174,34 @@ def test_non_islanding_branches():
         assert (ncomp == 1) == (b in safe), b
 
 
-@pytest.mark.parametrize('name', ['case9', 'case118', 'case1354pegase', 'case2869pegase'])
+@pytest.mark.parametrize('name', ['case9', 'case118', 'case1354pegase', 'case2869pegase', 'tiled'])
 def test_flat_wave_schedule_solves(name):
     """The wave tables of k_solve_flat (symbolic.cpp 4b-flat), emulated lane by lane on the host,
     give the same x as the plain row-by-row block solve."""
-    case = load_case(name)
+    if name == 'tiled':         # several elimination subtrees side by side: long rows share levels
+        import synth
+        case = synth.tiled_case(['case1354pegase', 'case2869pegase', 'case118'])
+    else:
+        case = load_case(name)
     S = _lib.symbolic_arrays(case.adj_ptr, case.adj_idx, case.bus_types_code())
     N = case.N
     lptr, lcol, uptr, ucol, urow, dslot = S['lptr'], S['lcol'], S['uptr'], S['ucol'], S['urow'], S['dslot']
     nL = int(lptr[-1])
     nslots = nL + int(uptr[-1]) + N
     wt = S['wave_tab'].reshape(-1, 2)
+    if (wt[-1, 1] & 63) == 0:       # padding entry (16-byte multiple for the bulk copy)
+        wt = wt[:-1]
     meta, col = S['smeta'], S['slot_col']
     assert len(meta) == nslots and len(col) == nslots
+    # tables of the shared-memory solve: {column, meta} per slot, chunks of consecutive waves
+    scm = S['scm'].reshape(-1, 2)[:nslots]
+    assert (scm[:, 0] == col).all() and (scm[:, 1] == meta).all()
+    ch = S['solve_chunks'].reshape(-1, 4)
+    assert ch[0, 0] == 0 and ch[0, 2] == 0 and (ch[:, 3] <= 128).all() and (ch[:, 3] >= 1).all()
+    assert (ch[1:, 0] == ch[:-1, 0] + ch[:-1, 1]).all() and ch[-1, 0] + ch[-1, 1] == len(wt)
+    assert (ch[1:, 2] == ch[:-1, 2] + ch[:-1, 3]).all() and ch[-1, 2] + ch[-1, 3] == nslots
+    for w0, nwv, s0, ns in ch:
+        assert wt[w0, 0] == s0 and int((wt[w0:w0 + nwv, 1] & 63).sum()) == ns
     rng = np.random.default_rng(3)
     lu = rng.standard_normal((nslots, 2, 2))
     rhs = rng.standard_normal((N, 2))
@@ -213,12 +228,17 @@ def test_flat_wave_schedule_solves(name):
     carry_d = None
     final_u = np.zeros(N, dtype=bool)
     this_level = set()          # rows written since the last SYNC wave: must not be gathered
+    cont_pending = False
     for e0, info in wt:
         n = info & 63
         is_u = bool(info & 256)
         assert 1 <= n <= 32
+        assert (info & 64) or not (info & 128), 'a wave that hands on a carry must be ordered (SYNC)'
         if info & 64:
             this_level = set()
+        else:
+            assert not cont_pending, 'the wave after a continued row must be ordered after it'
+        cont_pending = False
         covered[e0:e0 + n] += 1
         lane = 0
         while lane < n:
@@ -251,6 +271,7 @@ def test_flat_wave_schedule_solves(name):
             else:
                 assert info & 128 and lane + span == n - 1
                 carry, carry_d = acc, d
+                cont_pending = True
             lane += span + 1
     assert (covered == 1).all()
     assert np.allclose(y, x, rtol=1e-9, atol=1e-9)
