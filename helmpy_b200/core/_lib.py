@@ -53,11 +53,11 @@ class PlanInfo(C.Structure):
 class Stats(C.Structure):
     _fields_ = [
         ("steps", C.c_int64), ("kernel_launches", C.c_int64), ("graph_launches", C.c_int64),
-        ("ms_total", C.c_double), ("ms_kernel", C.c_double * 8),
+        ("ms_total", C.c_double), ("ms_kernel", C.c_double * 12),
     ]
 
 
-KERNEL_NAMES = ("assemble", "factor", "solve", "rhs_conv", "advance", "qlimit", "pass_end", "init")
+KERNEL_NAMES = ("assemble", "factor", "solve", "rhs_conv", "advance", "qlimit", "pass_end", "init", "eps")
 
 EXPORTED_SYMBOLS = (
     "helm_last_error", "helm_plan_create", "helm_plan_destroy", "helm_plan_get_info",
@@ -141,7 +141,6 @@ def symbolic_arrays(adj_ptr, adj_idx, bus_type=None):
         for name in ("perm", "iperm", "adj_ptr", "adj_idx", "adj_src", "adj_slot", "lptr", "lcol",
                      "llev_ptr", "urow", "qof", "ulev_ptr", "uptr", "ucol", "dslot", "fptr",
                      "fsrc", "fdst", "fdst_local", "fchunk_row", "fchunk_lpr", "frow_off",
-                     "sstep_kind", "sstep_a", "sstep_b", "sring_desc",
                      "slot_src", "slot_row", "slot_col", "wave_tab", "smeta", "scm", "solve_chunks"):
             data = C.c_void_p()
             n = C.c_int32()
@@ -294,7 +293,7 @@ def stats_dict(stats):
     return {
         "steps": int(stats.steps), "kernel_launches": int(stats.kernel_launches),
         "graph_launches": int(stats.graph_launches), "ms_total": float(stats.ms_total),
-        "ms_kernel": {KERNEL_NAMES[i]: float(stats.ms_kernel[i]) for i in range(8)},
+        "ms_kernel": {KERNEL_NAMES[i]: float(stats.ms_kernel[i]) for i in range(len(KERNEL_NAMES))},
     }
 
 

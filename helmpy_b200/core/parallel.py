@@ -51,7 +51,7 @@ def gather_blocks(local, n_total, world_size, dist, device=None):
 def helm_batch_sharded(case, scales, solve_fn=None, device=None, **kw):
     """Solve ``scales`` across all ranks of the default process group.
 
-    Every rank passes the same ``scales``; each solves its block with
+    Every rank passes the same ``scales`` (and ``outages``, if any); each solves its block with
     ``helm_batch`` (or ``solve_fn(case, scales_block, **kw)`` returning an object
     with ``V``, ``status``, ``ncoef``, ``nswitch``) and all ranks return the
     full (V, status, ncoef, nswitch).
@@ -59,9 +59,14 @@ def helm_batch_sharded(case, scales, solve_fn=None, device=None, **kw):
     import torch.distributed as dist
     from .helm import helm_batch
     world, rank = dist.get_world_size(), dist.get_rank()
+    outages = kw.pop('outages', None)
+    if scales is None:
+        scales = np.ones(len(outages))
     scales = np.asarray(scales, dtype=np.float64)
     lo, hi = shard_bounds(len(scales), world, rank)
     fn = solve_fn or helm_batch
+    if outages is not None:                      # N-1 scenarios are sharded with their scales
+        kw['outages'] = np.asarray(outages, dtype=np.int32)[lo:hi]
     res = fn(case, scales[lo:hi], **kw)
     n = len(scales)
     V = gather_blocks(res.V, n, world, dist, device)

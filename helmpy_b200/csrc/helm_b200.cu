@@ -66,12 +66,11 @@ struct PlanDev {
     const double *br_val;                   // [10b..]: y, sh_f, sh_t, ph_ft, ph_tf (complex)
     const int *fptr, *fsrc, *fdst, *fdstl, *qof;
     const int *fchunk_row, *fchunk_lpr, *frow_off;
-    const int *sstep_kind, *sstep_a, *sstep_b, *sring_desc;
-    int nsteps, nring, use_smem_solve, smem_solve_max_groups, use_coop_factor;
+    int use_coop_factor;
     int max_row_blocks, nfchunks, cap_upd, cap_ent, cap_rowblk;
     const int2 *wave_tab;
     const int *smeta;
-    int nwaves, n_rows_nol, use_flat_solve;
+    int nwaves, n_rows_nol;
     const int *scm;
     const int4 *solve_chunks;
     int nschunks, use_cta_solve, cta_solve_max_groups;
@@ -104,6 +103,9 @@ struct WorkDev {
     double2 *Pcur;                    // [group][N][G]
     double2 *rhs, *xb;                // [group][N][G]
     double2 *lu;                      // [group][nslots][G][2]
+    // factors of the first pass, shared by every scenario without an outage: the matrix of a pass depends
+    // on the topology and the bus types only (helm.py:46-60), not on the load scale.  null: not used.
+    const double2 *lu_shared;
     double2 *Vh, *Hh, *Eh;            // [group][K][N][G]
     double2 *vout;                    // [B][N] original order
     unsigned long long *tl;           // timeline buffer (HELM_TIMELINE builds only), else null
@@ -192,6 +194,14 @@ __device__ __forceinline__ size_t hx(const WorkDev &w, int N, int grp, int k, in
 }
 template <int G>
 __device__ __forceinline__ size_t hplane() { return (size_t)HT * G; }
+
+// G = 1: does the scenario in slot `grp` run on the shared first-pass factors?
+__device__ __forceinline__ bool uses_shared_lu(const WorkDev &w, int grp) {
+    return w.lu_shared != nullptr && w.s_npass[grp] == 0 && w.o_b[grp] < 0;
+}
+__device__ __forceinline__ const double2 *lu_of(const PlanDev &p, const WorkDev &w, int grp) {
+    return uses_shared_lu(w, grp) ? w.lu_shared : w.lu + (size_t)grp * p.nslots * 2;
+}
 
 __device__ __forceinline__ OutageRef load_outage(const PlanDev &p, const WorkDev &w, int sg) {
     OutageRef o{w.o_b[sg], -1, -1};
@@ -447,6 +457,7 @@ __global__ void __launch_bounds__(WPB * 32) k_factor_coop(PlanDev p, WorkDev w) 
         asm_reset<1>(p, w, grp, lane, 32);
         __syncwarp();
     }
+    if (uses_shared_lu(w, grp)) continue;                   // first pass: the shared factors are used
     for (int slot = lane; slot < p.nslots; slot += 32) asm_slot<1>(p, w, grp, slot, 0);
     __syncwarp();
     double2 *lu = w.lu + (size_t)grp * p.nslots * 2;
@@ -681,135 +692,6 @@ __global__ void __launch_bounds__(WPB * 32) k_solve(PlanDev p, WorkDev w) {
     }
 }
 
-// ---- K2 (G = 1), warp per scenario with cooperative thin levels ---------------------------------
-// Same data flow as k_solve<1>, but levels with fewer than 16 rows (the long tail near the root of
-// the elimination tree: 1-8 rows of 20-60 entries each) give each row to a sub-warp whose lanes
-// split the row's entries and combine with shuffles, instead of leaving 31 lanes idle while one
-// lane walks a 57-entry row.  Cuts the executed warp instructions per solve ~4x (ncu, profiles/).
-// side = 1: solve for the scenarios being factorized in the side branch (z = A^-1 c of the
-// distributed-slack border, helm_variants.cuh) instead of the ones advancing in the main branch.
-template <int WPB>
-__global__ void __launch_bounds__(WPB * 32, 8) k_solve_warp(PlanDev p, WorkDev w, int side) {
-    TL_SCOPE(w, 2);
-    int grp = blockIdx.x * WPB + (threadIdx.x >> 5);
-    if (grp >= w.ngroups) return;
-    {
-        int gfl = w.g_flags[grp];
-        if (side ? !(gfl & GF_FACTORING) : (gfl & (GF_DONE | GF_FACTORING)) != 0) return;
-    }
-    if (w.s_status[grp] != ST_ACTIVE) return;
-    const int lane = threadIdx.x & 31;
-    const double2 *lu = w.lu + (size_t)grp * p.nslots * 2;
-    const double2 *rhs = w.rhs + (size_t)grp * p.N;
-    double2 *xb = w.xb + (size_t)grp * p.N;
-    for (int l = 0; l < p.nLlev; ++l) {
-        const int r0 = __ldg(p.llev_ptr + l), r1 = __ldg(p.llev_ptr + l + 1);
-        const int width = r1 - r0;
-        if (width >= 16) {
-            int r = r0 + lane;
-            for (; r + 32 < r1; r += 64) {
-                int rb = r + 32;
-                int e0a = __ldg(p.lptr + r), e1a = __ldg(p.lptr + r + 1);
-                int e0b = __ldg(p.lptr + rb), e1b = __ldg(p.lptr + rb + 1);
-                double2 acc_a = rhs[r], acc_b = rhs[rb];
-                row_accumulate2<1>(lu, xb, p.lcol + e0a, (size_t)e0a, e1a - e0a, acc_a,
-                                   p.lcol + e0b, (size_t)e0b, e1b - e0b, acc_b, 0);
-                xb[r] = acc_a;
-                xb[rb] = acc_b;
-            }
-            if (r < r1) {
-                int e0 = __ldg(p.lptr + r), e1 = __ldg(p.lptr + r + 1);
-                double2 acc = rhs[r];
-                row_accumulate<1>(lu, xb, p.lcol + e0, (size_t)e0, e1 - e0, 0, acc);
-                xb[r] = acc;
-            }
-        } else {
-            const int lpr = (width <= 1) ? 32 : (width <= 2) ? 16 : (width <= 4) ? 8 : (width <= 8) ? 4 : 2;
-            const int rs = lane / lpr, sl = lane % lpr;
-            const int r = r0 + rs;
-            double2 sum = make_double2(0.0, 0.0);
-            if (r < r1) {
-                int e0 = __ldg(p.lptr + r), e1 = __ldg(p.lptr + r + 1);
-                for (int e = e0 + sl; e < e1; e += lpr) {
-                    int c = __ldg(p.lcol + e);
-                    Blk m = ldblk_stream(lu, (size_t)e);
-                    double2 x = xb[c];
-                    sum.x += m.a * x.x + m.b * x.y;
-                    sum.y += m.c * x.x + m.d * x.y;
-                }
-            }
-            for (int o = lpr >> 1; o > 0; o >>= 1) {
-                sum.x += __shfl_xor_sync(0xFFFFFFFFu, sum.x, o);
-                sum.y += __shfl_xor_sync(0xFFFFFFFFu, sum.y, o);
-            }
-            if (r < r1 && sl == 0) {
-                double2 b = rhs[r];
-                xb[r] = make_double2(b.x - sum.x, b.y - sum.y);
-            }
-        }
-        __syncwarp();
-    }
-    for (int l = 0; l < p.nUlev; ++l) {
-        const int q0 = __ldg(p.ulev_ptr + l), q1 = __ldg(p.ulev_ptr + l + 1);
-        const int width = q1 - q0;
-        if (width >= 16) {
-            int q = q0 + lane;
-            for (; q + 32 < q1; q += 64) {
-                int qb = q + 32;
-                int ra = __ldg(p.urow + q), rb = __ldg(p.urow + qb);
-                int u0a = __ldg(p.uptr + q), nua = __ldg(p.uptr + q + 1) - u0a;
-                int u0b = __ldg(p.uptr + qb), nub = __ldg(p.uptr + qb + 1) - u0b;
-                size_t base_a = (size_t)(p.nL + u0a + q), base_b = (size_t)(p.nL + u0b + qb);
-                Blk da = ldblk_stream(lu, base_a), db = ldblk_stream(lu, base_b);
-                double2 acc_a = xb[ra], acc_b = xb[rb];
-                row_accumulate2<1>(lu, xb, p.ucol + u0a, base_a + 1, nua, acc_a,
-                                   p.ucol + u0b, base_b + 1, nub, acc_b, 0);
-                xb[ra] = make_double2(da.a * acc_a.x + da.b * acc_a.y, da.c * acc_a.x + da.d * acc_a.y);
-                xb[rb] = make_double2(db.a * acc_b.x + db.b * acc_b.y, db.c * acc_b.x + db.d * acc_b.y);
-            }
-            if (q < q1) {
-                int r = __ldg(p.urow + q);
-                int u0 = __ldg(p.uptr + q), nu = __ldg(p.uptr + q + 1) - u0;
-                size_t base = (size_t)(p.nL + u0 + q);
-                Blk d = ldblk_stream(lu, base);
-                double2 acc = xb[r];
-                row_accumulate<1>(lu, xb, p.ucol + u0, base + 1, nu, 0, acc);
-                xb[r] = make_double2(d.a * acc.x + d.b * acc.y, d.c * acc.x + d.d * acc.y);
-            }
-        } else {
-            const int lpr = (width <= 1) ? 32 : (width <= 2) ? 16 : (width <= 4) ? 8 : (width <= 8) ? 4 : 2;
-            const int rs = lane / lpr, sl = lane % lpr;
-            const int q = q0 + rs;
-            double2 sum = make_double2(0.0, 0.0);
-            size_t base = 0;
-            int r = 0;
-            if (q < q1) {
-                r = __ldg(p.urow + q);
-                int u0 = __ldg(p.uptr + q), nu = __ldg(p.uptr + q + 1) - u0;
-                base = (size_t)(p.nL + u0 + q);
-                for (int t = sl; t < nu; t += lpr) {
-                    int c = __ldg(p.ucol + u0 + t);
-                    Blk m = ldblk_stream(lu, base + 1 + t);
-                    double2 x = xb[c];
-                    sum.x += m.a * x.x + m.b * x.y;
-                    sum.y += m.c * x.x + m.d * x.y;
-                }
-            }
-            for (int o = lpr >> 1; o > 0; o >>= 1) {
-                sum.x += __shfl_xor_sync(0xFFFFFFFFu, sum.x, o);
-                sum.y += __shfl_xor_sync(0xFFFFFFFFu, sum.y, o);
-            }
-            if (q < q1 && sl == 0) {
-                Blk d = ldblk_stream(lu, base);
-                double2 cur = xb[r];
-                double ax = cur.x - sum.x, ay = cur.y - sum.y;
-                xb[r] = make_double2(d.a * ax + d.b * ay, d.c * ax + d.d * ay);
-            }
-        }
-        __syncwarp();
-    }
-}
-
 // ---- K2 (G = 1), flat wave solve ----------------------------------------------------------------
 // One warp per scenario.  The blocks of L and of [D|U], in storage (= consumption) order, are cut on
 // the host into waves of <= 32 consecutive slots (symbolic.cpp 4b-flat): one block per lane, so the
@@ -875,7 +757,7 @@ __global__ void __maxnreg__(64) k_solve_flat(PlanDev p, WorkDev w, int side) {
     }
     if (w.s_status[grp] != ST_ACTIVE) return;
     const int lane = threadIdx.x & 31;
-    const double2 *lu = w.lu + (size_t)grp * p.nslots * 2;
+    const double2 *lu = lu_of(p, w, grp);
     const double2 *rhs = w.rhs + (size_t)grp * p.N;
     double2 *xb = w.xb + (size_t)grp * p.N;
     const int nw = p.nwaves;
@@ -1025,7 +907,7 @@ __global__ void __launch_bounds__(CS_T) k_solve_cta(PlanDev p, WorkDev w, int si
     const int2 *swave = (const int2 *)(smem_c + L.off_wave);
     const int4 *schunk = (const int4 *)(smem_c + L.off_chunk);
     unsigned char *ring = smem_c + L.off_ring;
-    const double2 *lu = w.lu + (size_t)grp * p.nslots * 2;
+    const double2 *lu = lu_of(p, w, grp);
     const double2 *rhs = w.rhs + (size_t)grp * N;
     double2 *xb = w.xb + (size_t)grp * N;
     if (tid == 0) {
@@ -1111,176 +993,6 @@ __global__ void __launch_bounds__(CS_T) k_solve_cta(PlanDev p, WorkDev w, int si
     }
     for (int i = tid; i < N; i += CS_T) xb[i] = xs[i];
     TL_CLK_ADD(w, 5);
-}
-
-// ---- K2 (G = 1, N*16 B fits in shared memory): shared-memory solve ------------------------------
-// One CTA per scenario.  The solution vector lives in shared memory, so a dependent level costs a
-// barrier and a shared-memory round trip instead of an L2 one.  The levels near the root of the
-// elimination tree (few, long rows — they make up most of the 172-step dependency chain) are
-// "ring" steps: their factor blocks, column indices and row pointers are contiguous in storage, and
-// are prefetched RING_D steps ahead into a shared-memory ring with cp.async (LDGSTS), so the chain
-// never waits for HBM; there one warp takes one row and its lanes split the row's entries.  The
-// wide levels near the leaves have thousands of independent rows and read their factors straight
-// from global memory, one row per thread.
-constexpr int SM_T = 256;                      // threads per CTA
-constexpr int SM_NW = SM_T / 32;
-constexpr int RING_D = 4;                      // prefetch distance (ring slots)
-constexpr int RING_BLK = helm::Symbolic::RING_BLOCKS;
-constexpr int RING_ROWS = helm::Symbolic::RING_ROWS;
-// slot layout (bytes): [vals RING_BLK*32][cols RING_BLK*4][rowptr (RING_ROWS+4)*4][rows (RING_ROWS+4)*4]
-constexpr int RING_SLOT_BYTES = RING_BLK * 32 + RING_BLK * 4 + 2 * (RING_ROWS + 4) * 4;
-
-// shared memory: [x: N double2][ring: RING_D slots][ring descriptors: nring*8 ints][steps: nsteps*3 ints]
-__host__ __device__ inline size_t solve_smem_bytes(int N, int nring, int nsteps) {
-    return (size_t)N * sizeof(double2) + (size_t)RING_D * RING_SLOT_BYTES +
-           (size_t)((nring * 8 + nsteps * 3 + 3) / 4 * 4) * sizeof(int);
-}
-
-// issue the copies of ring step kk (descriptor in shared memory) into its slot; every thread
-// commits one group
-__device__ __forceinline__ void ring_issue(const PlanDev &p, const double2 *lu, char *ring, const int *sdesc,
-                                           int kk, int tid) {
-    if (kk < p.nring) {
-        const int *d = sdesc + kk * 8;
-        int kind = d[0], row0 = d[1], nrows = d[2], slot0 = d[3];
-        int nblk = d[4], col0 = d[5], ncol = d[6];
-        char *slot = ring + (size_t)(kk % RING_D) * RING_SLOT_BYTES;
-        const char *gv = (const char *)(lu + (size_t)slot0 * 2);
-        for (int i = tid; i < nblk * 2; i += SM_T) cp_async16(slot + (size_t)i * 16, gv + (size_t)i * 16);
-        int *sc = (int *)(slot + RING_BLK * 32);
-        const int *gc = (kind == 1 ? p.lcol : p.ucol) + col0;
-        for (int i = tid; i < ncol; i += SM_T) cp_async4(sc + i, gc + i);
-        int *sp = sc + RING_BLK;
-        const int *gp = (kind == 1 ? p.lptr : p.uptr) + row0;
-        for (int i = tid; i <= nrows; i += SM_T) cp_async4(sp + i, gp + i);
-        if (kind == 3) {
-            int *sr = sp + RING_ROWS + 4;
-            for (int i = tid; i < nrows; i += SM_T) cp_async4(sr + i, p.urow + row0 + i);
-        }
-    }
-    cp_async_commit();
-}
-
-__device__ __forceinline__ double2 warp_sum2(double2 v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        v.x += __shfl_xor_sync(0xFFFFFFFFu, v.x, o);
-        v.y += __shfl_xor_sync(0xFFFFFFFFu, v.y, o);
-    }
-    return v;
-}
-
-__global__ void __launch_bounds__(SM_T) k_solve_smem(PlanDev p, WorkDev w) {
-    TL_SCOPE(w, 2);
-    extern __shared__ double2 smem_s[];
-    const int grp = blockIdx.x;                              // G = 1: one scenario per CTA
-    if (w.g_flags[grp] & (GF_DONE | GF_FACTORING)) return;
-    if (w.s_status[grp] != ST_ACTIVE) return;
-    const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
-    const int N = p.N;
-    double2 *xs = smem_s;
-    char *ring = (char *)(smem_s + N);
-    const double2 *lu = w.lu + (size_t)grp * p.nslots * 2;
-    const double2 *rhs = w.rhs + (size_t)grp * N;
-    double2 *xb = w.xb + (size_t)grp * N;
-    int *sdesc = (int *)(ring + (size_t)RING_D * RING_SLOT_BYTES);
-    int *ssteps = sdesc + p.nring * 8;
-    for (int i = tid; i < p.nring * 8; i += SM_T) sdesc[i] = __ldg(p.sring_desc + i);
-    for (int i = tid; i < p.nsteps; i += SM_T) {
-        ssteps[3 * i] = __ldg(p.sstep_kind + i);
-        ssteps[3 * i + 1] = __ldg(p.sstep_a + i);
-        ssteps[3 * i + 2] = __ldg(p.sstep_b + i);
-    }
-    TL_CLK_DECL;
-    for (int i = tid; i < N; i += SM_T) xs[i] = rhs[i];
-    __syncthreads();
-    TL_CLK_ADD(w, 1);
-    // prologue: first RING_D-1 ring steps in flight
-    for (int kk = 0; kk < RING_D - 1; ++kk) ring_issue(p, lu, ring, sdesc, kk, tid);
-    int k = 0;                                               // ring steps consumed so far
-    for (int st = 0; st < p.nsteps; ++st) {
-        const int kind = ssteps[3 * st];
-        const int a = ssteps[3 * st + 1], b = ssteps[3 * st + 2];
-        if (kind == 4) continue;
-        if (kind == 1 || kind == 3) {
-            TL_CLK_ADD(w, 7);
-            cp_async_wait<RING_D - 2>();                     // this step's group has landed (this thread)
-            __syncthreads();                                 // ... for every thread; previous step's x visible
-            TL_CLK_ADD(w, 2);
-            ring_issue(p, lu, ring, sdesc, k + RING_D - 1, tid);   // refill the slot the previous ring step used
-            const char *slot = ring + (size_t)(k % RING_D) * RING_SLOT_BYTES;
-            const double2 *V = (const double2 *)slot;
-            const int *C = (const int *)(slot + RING_BLK * 32);
-            const int *P = C + RING_BLK;
-            const int *R = P + RING_ROWS + 4;
-            const int nrows = b - a;
-            const int p0 = P[0];
-            if (kind == 1) {
-                for (int rr = wp; rr < nrows; rr += SM_NW) {
-                    int ea = P[rr] - p0, eb = P[rr + 1] - p0;
-                    double2 sum = make_double2(0.0, 0.0);
-                    for (int t = ea + lane; t < eb; t += 32) {
-                        double2 r0 = V[2 * t], r1 = V[2 * t + 1];
-                        double2 x = xs[C[t]];
-                        sum.x += r0.x * x.x + r0.y * x.y;
-                        sum.y += r1.x * x.x + r1.y * x.y;
-                    }
-                    sum = warp_sum2(sum);
-                    if (lane == 0) {
-                        double2 cur = xs[a + rr];
-                        xs[a + rr] = make_double2(cur.x - sum.x, cur.y - sum.y);
-                    }
-                }
-            } else {
-                for (int rr = wp; rr < nrows; rr += SM_NW) {
-                    int ua = P[rr] - p0, ub = P[rr + 1] - p0;
-                    int bi = ua + rr;                        // the row's inverted pivot block
-                    double2 sum = make_double2(0.0, 0.0);
-                    for (int t = lane; t < ub - ua; t += 32) {
-                        double2 r0 = V[2 * (bi + 1 + t)], r1 = V[2 * (bi + 1 + t) + 1];
-                        double2 x = xs[C[ua + t]];
-                        sum.x += r0.x * x.x + r0.y * x.y;
-                        sum.y += r1.x * x.x + r1.y * x.y;
-                    }
-                    sum = warp_sum2(sum);
-                    if (lane == 0) {
-                        int r = R[rr];
-                        double2 cur = xs[r];
-                        double ax = cur.x - sum.x, ay = cur.y - sum.y;
-                        double2 d0 = V[2 * bi], d1 = V[2 * bi + 1];
-                        xs[r] = make_double2(d0.x * ax + d0.y * ay, d1.x * ax + d1.y * ay);
-                    }
-                }
-            }
-            ++k;
-            TL_CLK_ADD(w, 3);
-        } else if (kind == 0) {
-            __syncthreads();
-            for (int r = a + tid; r < b; r += SM_T) {
-                int e0 = __ldg(p.lptr + r), e1 = __ldg(p.lptr + r + 1);
-                double2 acc = xs[r];
-                row_accumulate<1>(lu, xs, p.lcol + e0, (size_t)e0, e1 - e0, 0, acc);
-                xs[r] = acc;
-            }
-            TL_CLK_ADD(w, 4);
-        } else {  // kind == 2
-            __syncthreads();
-            for (int q = a + tid; q < b; q += SM_T) {
-                int r = __ldg(p.urow + q);
-                int u0 = __ldg(p.uptr + q), nu = __ldg(p.uptr + q + 1) - u0;
-                size_t base = (size_t)(p.nL + u0 + q);
-                Blk d = ldblk_stream(lu, base);
-                double2 acc = xs[r];
-                row_accumulate<1>(lu, xs, p.ucol + u0, base + 1, nu, 0, acc);
-                xs[r] = make_double2(d.a * acc.x + d.b * acc.y, d.c * acc.x + d.d * acc.y);
-            }
-            TL_CLK_ADD(w, 5);
-        }
-    }
-    cp_async_wait<0>();
-    __syncthreads();
-    for (int i = tid; i < N; i += SM_T) xb[i] = xs[i];
-    TL_CLK_ADD(w, 6);
 }
 
 // ---- K_init: order-0 germ and RHS of order 1 (helm.py:110-139, 551-556, n == 1 branches) ---
@@ -1790,6 +1502,14 @@ __global__ void k_step_begin(WorkDev w) {
     w.g_flags[grp] = gf;
 }
 
+// ---- shared first-pass factors: scratch control block for factorizing the base matrix once -----
+// ints[0..3] = 1 (list length for any list index), ints[4] = 0 (the list: pseudo-group 0),
+// ints[8] = -1 (no outage), ints[9] = status (ST_ACTIVE; ST_SINGULAR afterwards if A is singular),
+// ints[10] = 0 (flags), ints[11] = 0 (passes)
+__global__ void k_shared_prep(int *ints) {
+    if (threadIdx.x < 16) ints[threadIdx.x] = (threadIdx.x < 4) ? 1 : (threadIdx.x == 8 ? -1 : 0);
+}
+
 // ---- K_setup: initial per-scenario state ---------------------------------------------------
 template <int G>
 __global__ void k_setup(PlanDev p, WorkDev w, const double *scale_in) {
@@ -1894,7 +1614,7 @@ int pick_group(int n_scen, int requested) {
 struct WsLayout {
     size_t total = 0;
     size_t off_scale, off_sint, off_gint, off_btype, off_Qg, off_VVant, off_Pcur, off_rhs, off_xb, off_lu, off_Vh, off_Hh, off_Eh;
-    size_t off_var_s, off_ploss, off_zb, off_Qh, off_vre, off_qcur;
+    size_t off_var_s, off_ploss, off_zb, off_Qh, off_vre, off_qcur, off_lu_shared, off_shprep;
     int G, ngroups, Bp, K;
 };
 
@@ -1921,6 +1641,8 @@ WsLayout layout(const helm_plan *pl, int B, const helm_params *prm) {
     L.off_rhs = take(per * sizeof(double2));
     L.off_xb = take(per * sizeof(double2));
     L.off_lu = take((size_t)L.Bp * pl->S.nslots * 2 * sizeof(double2));
+    L.off_lu_shared = take((size_t)pl->S.nslots * 2 * sizeof(double2));
+    L.off_shprep = take(sizeof(int) * 16);
     const size_t per_h = (size_t)L.Bp * ((N + HT - 1) / HT * HT);   // histories are tiled by HT buses
     L.off_Vh = take(per_h * L.K * sizeof(double2));
     L.off_Hh = take(per_h * L.K * sizeof(double2));
@@ -1961,6 +1683,7 @@ WorkDev bind(const helm_plan *pl, const WsLayout &L, int B, const helm_params *p
     w.rhs = (double2 *)(b + L.off_rhs);
     w.xb = (double2 *)(b + L.off_xb);
     w.lu = (double2 *)(b + L.off_lu);
+    w.lu_shared = nullptr;
     w.Vh = (double2 *)(b + L.off_Vh);
     w.Hh = (double2 *)(b + L.off_Hh);
     w.Eh = (double2 *)(b + L.off_Eh);
@@ -1988,7 +1711,9 @@ constexpr int T_ELEM = 256;   // threads per CTA of the per-(item, scenario) ker
 constexpr int WPB_SOLVE = 4;  // warps (= scenario groups) per CTA of the factor / solve kernels
 
 enum { KI_ASM = 0, KI_FACTOR, KI_SOLVE, KI_RHS, KI_ADV, KI_QLIM, KI_PEND, KI_INIT, KI_BEGIN,
-       KI_SOLVE_SIDE, KI_BPREP, KI_BFIN, KI_BP, KI_VPRE, KI_PV1C_MAIN, KI_PV1C_SIDE, KI_COUNT };
+       KI_SOLVE_SIDE, KI_BPREP, KI_BFIN, KI_BP, KI_VPRE, KI_PV1C_MAIN, KI_PV1C_SIDE, KI_EPS, KI_COUNT };
+// slot of helm_stats.ms_kernel a kernel is accounted under in profile mode (-1: not accounted)
+inline int stat_slot(int ki) { return ki < 8 ? ki : (ki == KI_EPS ? 8 : -1); }
 
 template <int G>
 void launch_kernel(int which, const PlanDev &p, const WorkDev &w, cudaStream_t st) {
@@ -2017,31 +1742,25 @@ void launch_kernel(int which, const PlanDev &p, const WorkDev &w, cudaStream_t s
         case KI_PV1C_SIDE: k_pv1_correct<<<gridBus, T_ELEM, 0, st>>>(p, w, 1); break;
         case KI_SOLVE_SIDE:
             if (p.use_cta_solve) k_solve_cta<<<w.ngroups, CS_T, cta_solve_layout(p.N, p.nwaves, p.nschunks).total, st>>>(p, w, 1);
-            else if (p.use_flat_solve) k_solve_flat<FLAT_WPB><<<(w.ngroups + FLAT_WPB - 1) / FLAT_WPB, FLAT_WPB * 32, 0, st>>>(p, w, 1);
-            else k_solve_warp<WPB_SOLVE><<<(w.ngroups + WPB_SOLVE - 1) / WPB_SOLVE, WPB_SOLVE * 32, 0, st>>>(p, w, 1);
+            else k_solve_flat<FLAT_WPB><<<(w.ngroups + FLAT_WPB - 1) / FLAT_WPB, FLAT_WPB * 32, 0, st>>>(p, w, 1);
             break;
         case KI_SOLVE:
-            // shared-memory solve for small batches (<= ~3 CTAs per SM of concurrency is enough);
-            // large batches keep more scenarios in flight with the warp-per-scenario kernel
+            // small batches: CTA per scenario with x in shared memory (shortest dependency chain);
+            // large batches: warp per scenario, all resident scenarios in one round
             if (G == 1 && p.use_cta_solve && w.ngroups <= p.cta_solve_max_groups) {
                 k_solve_cta<<<w.ngroups, CS_T, cta_solve_layout(p.N, p.nwaves, p.nschunks).total, st>>>(p, w, 0);
-            } else if (G == 1 && p.use_smem_solve && w.ngroups <= p.smem_solve_max_groups) {
-                k_solve_smem<<<w.ngroups, SM_T, solve_smem_bytes(p.N, p.nring, p.nsteps), st>>>(p, w);
-            } else if (G == 1 && p.use_flat_solve) {
-                k_solve_flat<FLAT_WPB><<<(w.ngroups + FLAT_WPB - 1) / FLAT_WPB, FLAT_WPB * 32, 0, st>>>(p, w, 0);
             } else if (G == 1) {
-                k_solve_warp<WPB_SOLVE><<<(w.ngroups + WPB_SOLVE - 1) / WPB_SOLVE, WPB_SOLVE * 32, 0, st>>>(p, w, 0);
+                k_solve_flat<FLAT_WPB><<<(w.ngroups + FLAT_WPB - 1) / FLAT_WPB, FLAT_WPB * 32, 0, st>>>(p, w, 0);
             } else {
                 k_solve<G, WPB_SOLVE><<<(w.ngroups + WPB_SOLVE - 1) / WPB_SOLVE, WPB_SOLVE * 32, 0, st>>>(p, w);
             }
             break;
         case KI_RHS:
             if (w.pv_model == 1 || w.dsb_method) k_rhs_conv_var<<<gridBus, T_ELEM, 0, st>>>(p, w);
-            else if (p.split_eps) {
-                k_eps<G><<<dim3((p.N * G + 127) / 128, w.ngroups), 128, 0, st>>>(p, w);
-                k_rhs_conv<G, false><<<dim3((p.N * G + 127) / 128, w.ngroups), 128, 0, st>>>(p, w);
-            } else k_rhs_conv<G, true><<<dim3((p.N * G + 127) / 128, w.ngroups), 128, 0, st>>>(p, w);
+            else if (p.split_eps) k_rhs_conv<G, false><<<dim3((p.N * G + 127) / 128, w.ngroups), 128, 0, st>>>(p, w);
+            else k_rhs_conv<G, true><<<dim3((p.N * G + 127) / 128, w.ngroups), 128, 0, st>>>(p, w);
             break;
+        case KI_EPS: k_eps<G><<<dim3((p.N * G + 127) / 128, w.ngroups), 128, 0, st>>>(p, w); break;
         case KI_ADV: k_advance<<<gridGrp, 128, 0, st>>>(w); break;
         case KI_QLIM: k_qlimit<G><<<gridBus, T_ELEM, 0, st>>>(p, w); break;
         case KI_PEND: k_pass_end<<<gridGrp, 128, 0, st>>>(w); break;
@@ -2088,7 +1807,7 @@ struct StepSeq {
 };
 // default: main = solve, rhs_conv, advance, qlimit, pass_end; side = assemble, factor, init.
 // Variants (helm_variants.cuh) add the bordered-system kernels and the PV-model-1 fix-ups.
-StepSeq make_seq(const WorkDev &w, bool fused_asm) {
+StepSeq make_seq(const WorkDev &w, bool fused_asm, bool split_eps) {
     StepSeq q;
     const bool dsb = w.dsb_method != 0, pv1 = w.pv_model == 1;
     if (!fused_asm) q.side_seq[q.side_len++] = KI_ASM;     // k_factor_coop assembles A itself
@@ -2099,6 +1818,7 @@ StepSeq make_seq(const WorkDev &w, bool fused_asm) {
     q.main_seq[q.main_len++] = KI_SOLVE;
     if (dsb) q.main_seq[q.main_len++] = KI_BP;
     if (dsb || pv1) q.main_seq[q.main_len++] = KI_VPRE;
+    if (split_eps && !dsb && !pv1) q.main_seq[q.main_len++] = KI_EPS;   // epsilon table + Pade check (k_eps)
     q.main_seq[q.main_len++] = KI_RHS;
     if (pv1) q.main_seq[q.main_len++] = KI_PV1C_MAIN;
     q.main_seq[q.main_len++] = KI_ADV;
@@ -2163,7 +1883,7 @@ void launch_step_profiled(int G, const PlanDev &p, const WorkDev &w_in, cudaStre
     for (int k = 0; k < n; ++k) {
         float ms = 0;
         cudaEventElapsedTime(&ms, ev[k], ev[k + 1]);
-        if (seq[k] < 8) acc.ms_kernel[seq[k]] += ms;
+        if (stat_slot(seq[k]) >= 0) acc.ms_kernel[stat_slot(seq[k])] += ms;
     }
 }
 
@@ -2257,7 +1977,6 @@ int helm_plan_create(const helm_grid_host *g, helm_plan **out) {
     UP(br_f, br_f) UP(br_t, br_t) UP(br_a, br_a) UP(br_p, br_p) UP(br_val, br_val)
     UP(S.fptr, fptr) UP(S.fsrc, fsrc) UP(S.fdst, fdst) UP(S.fdst_local, fdstl) UP(S.qof, qof)
     UP(S.fchunk_row, fchunk_row) UP(S.fchunk_lpr, fchunk_lpr) UP(S.frow_off, frow_off)
-    UP(S.sstep_kind, sstep_kind) UP(S.sstep_a, sstep_a) UP(S.sstep_b, sstep_b) UP(S.sring_desc, sring_desc)
     UP(S.smeta, smeta)
     {
         const int *wt = nullptr;
@@ -2273,8 +1992,6 @@ int helm_plan_create(const helm_grid_host *g, helm_plan **out) {
     }
     d.nschunks = (int)S.solve_chunks.size() / 4;
     d.split_eps = getenv("HELM_B200_FUSED_EPS") == nullptr;
-    d.use_flat_solve = (S.n_rows_nol >= 0) && getenv("HELM_B200_NO_FLAT_SOLVE") == nullptr;
-    d.nsteps = (int)S.sstep_kind.size(); d.nring = (int)S.sring_desc.size() / 8;
     d.max_row_blocks = S.max_row_blocks;
     d.nfchunks = (int)S.fchunk_lpr.size(); d.cap_upd = S.cap_upd; d.cap_ent = S.cap_ent; d.cap_rowblk = S.cap_rowblk;
 #undef UP
@@ -2287,20 +2004,11 @@ int helm_plan_create(const helm_grid_host *g, helm_plan **out) {
                     pl->d.cap_upd, pl->d.cap_ent, pl->d.cap_rowblk, pl->d.nfchunks, smem / WPB_FACTOR, WPB_FACTOR);
         pl->d.use_coop_factor = (smem <= 200 * 1024) && getenv("HELM_B200_NO_COOP_FACTOR") == nullptr;
         if (!pl->d.use_coop_factor) smem = 0;
-        // shared-memory solve: usable when x (16 B per bus) plus the ring leaves room for >= 2 CTAs per SM
-        size_t ssm = solve_smem_bytes(pl->d.N, pl->d.nring, pl->d.nsteps);
-        static size_t ssm_set = 48 * 1024;
-        pl->d.use_smem_solve = (ssm <= 110 * 1024) && getenv("HELM_B200_NO_SMEM_SOLVE") == nullptr;
-        pl->d.smem_solve_max_groups = getenv("HELM_B200_SMEM_SOLVE_MAX") ? atoi(getenv("HELM_B200_SMEM_SOLVE_MAX")) : 1024;
-        if (pl->d.use_smem_solve && ssm > ssm_set) {
-            CUDA_TRY(cudaFuncSetAttribute(k_solve_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
-            ssm_set = ssm;
-        }
         // shared-memory wave solve: x, the wave/chunk tables and the ring must fit one CTA
         {
             size_t csm = cta_solve_layout(pl->d.N, pl->d.nwaves, pl->d.nschunks).total;
             static size_t csm_set = 48 * 1024;
-            pl->d.use_cta_solve = (S.n_rows_nol >= 0) && (csm <= 225 * 1024) && getenv("HELM_B200_NO_CTA_SOLVE") == nullptr;
+            pl->d.use_cta_solve = (csm <= 225 * 1024) && getenv("HELM_B200_NO_CTA_SOLVE") == nullptr;
             pl->d.cta_solve_max_groups = getenv("HELM_B200_CTA_SOLVE_MAX") ? atoi(getenv("HELM_B200_CTA_SOLVE_MAX")) : 888;
             if (pl->d.use_cta_solve && csm > csm_set) {
                 CUDA_TRY(cudaFuncSetAttribute(k_solve_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
@@ -2404,14 +2112,14 @@ int helm_solve_batch_device(helm_plan *pl, int32_t B, const double *d_scale, con
     // chunks for one warp) has two steps to finish and is never the critical path of a step; the
     // price is one more idle step per pass for the scenario being factorized.  Kernels that select
     // their groups by flag instead of by list (variants, generic G > 1) need depth 1.
-    int depth = 2;
+    int depth = (L.Bp < 256) ? 1 : 2;     // a handful of scenarios: nothing to hide the factorization behind
     if (getenv("HELM_B200_SIDE_DEPTH")) depth = std::max(1, std::min(MAX_SIDE_DEPTH, atoi(getenv("HELM_B200_SIDE_DEPTH"))));
     if (!(L.G == 1 && p.use_coop_factor) || prm->dsb_method || prm->pv_bus_model == 1) depth = 1;
     w.depth = depth;
     // steps per graph launch / per poll: a multiple of depth * (depth + 1) so that list and stream
     // indices repeat from one graph launch to the next
     const int cyc = depth * (depth + 1);
-    int poll_every = prm->poll_every > 0 ? prm->poll_every : 12;
+    int poll_every = prm->poll_every > 0 ? prm->poll_every : (L.Bp < 256 ? 4 : 12);
     poll_every = (poll_every + cyc - 1) / cyc * cyc;
     if (!pl->h_pinned) CUDA_TRY(cudaMallocHost((void **)&pl->h_pinned, 64));
 
@@ -2434,6 +2142,25 @@ int helm_solve_batch_device(helm_plan *pl, int32_t B, const double *d_scale, con
     if (d_nswitch) CUDA_TRY(cudaMemsetAsync(d_nswitch, 0, sizeof(int) * B, st));
     launch_setup(L.G, p, w, d_scale, st);
 
+    // Shared first-pass factors (default variant, staged factorization): assemble and factorize the
+    // base matrix once, as pseudo-group 0 of a control block that points at the base bus types.
+    if (L.G == 1 && p.use_coop_factor && !prm->dsb_method && prm->pv_bus_model != 1 &&
+        getenv("HELM_B200_NO_SHARED_LU") == nullptr) {
+        int *ints = (int *)((char *)d_ws + L.off_shprep);
+        WorkDev w2 = w;
+        w2.lu = (double2 *)((char *)d_ws + L.off_lu_shared);
+        w2.btype = const_cast<unsigned char *>(p.btype0);
+        w2.fact_count = ints; w2.fact_list = ints + 4; w2.parity = 0;
+        w2.o_b = ints + 8; w2.s_status = ints + 9; w2.g_flags = ints + 10; w2.s_npass = ints + 11;
+        w2.ngroups = 1;
+        k_shared_prep<<<1, 32, 0, st>>>(ints);
+        launch_any(1, KI_FACTOR, p, w2, st);
+        if (!pl->h_pinned) CUDA_TRY(cudaMallocHost((void **)&pl->h_pinned, 64));
+        CUDA_TRY(cudaMemcpyAsync(pl->h_pinned, ints + 9, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (pl->h_pinned[0] == ST_ACTIVE) w.lu_shared = w2.lu;      // singular base matrix: every scenario factorizes (and fails) itself
+    }
+
     helm_stats local;
     memset(&local, 0, sizeof(local));
     local.kernel_launches = 1;
@@ -2451,7 +2178,7 @@ int helm_solve_batch_device(helm_plan *pl, int32_t B, const double *d_scale, con
         CUDA_TRY(cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming));
     }
     StepCtx ctx{st, pl->side, pl->ev_fork, pl->ev_join, depth};
-    const StepSeq seq = make_seq(w, L.G == 1 && p.use_coop_factor);
+    const StepSeq seq = make_seq(w, L.G == 1 && p.use_coop_factor, p.split_eps != 0);
     const int STEP_LEN = 1 + seq.main_len + seq.side_len;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t gexec = nullptr;

@@ -320,38 +320,6 @@ bool build_symbolic(int N, const int32_t *adj_ptr, const int32_t *adj_idx, const
         S.fchunk_row.push_back(N);
     }
 
-    // ---- 4b''. solve schedule ----------------------------------------------------------------
-    {
-        for (int l = 0; l < nLlev; ++l) {
-            int r0 = S.llev_ptr[l], r1 = S.llev_ptr[l + 1];
-            int ent = S.lptr[r1] - S.lptr[r0];
-            int kind = 0;
-            if (ent == 0) kind = 4;
-            else if (ent <= Symbolic::RING_BLOCKS && r1 - r0 <= Symbolic::RING_ROWS) kind = 1;
-            S.sstep_kind.push_back(kind);
-            S.sstep_a.push_back(r0);
-            S.sstep_b.push_back(r1);
-            if (kind == 1) {
-                int d[8] = {1, r0, r1 - r0, S.lptr[r0], ent, S.lptr[r0], ent, 0};
-                S.sring_desc.insert(S.sring_desc.end(), d, d + 8);
-            }
-        }
-        for (int l = 0; l < nUlev; ++l) {
-            int q0 = S.ulev_ptr[l], q1 = S.ulev_ptr[l + 1];
-            int ncol = S.uptr[q1] - S.uptr[q0];
-            int nblk = ncol + (q1 - q0);
-            int kind = 2;
-            if (nblk <= Symbolic::RING_BLOCKS && q1 - q0 <= Symbolic::RING_ROWS) kind = 3;
-            S.sstep_kind.push_back(kind);
-            S.sstep_a.push_back(q0);
-            S.sstep_b.push_back(q1);
-            if (kind == 3) {
-                int d[8] = {3, q0, q1 - q0, S.nL + S.uptr[q0] + q0, nblk, S.uptr[q0], ncol, 0};
-                S.sring_desc.insert(S.sring_desc.end(), d, d + 8);
-            }
-        }
-    }
-
     // ---- 4b-flat. flat solve schedule ---------------------------------------------------------
     // The blocks of both triangular solves, in storage (= consumption) order, are cut into
     // "waves" of at most 32 consecutive slots that one warp handles with one block per lane.
@@ -447,11 +415,15 @@ bool build_symbolic(int N, const int32_t *adj_ptr, const int32_t *adj_idx, const
             }
             if (nwv & 1) { S.wave_tab.push_back(0); S.wave_tab.push_back(0); }   // 16-byte multiple
         }
-        // rows without L entries get x = rhs directly; they must form a prefix of the numbering
+        // rows without L entries get x = rhs directly: they are the rows of forward level 0 and
+        // come first in the numbering
         S.n_rows_nol = 0;
         while (S.n_rows_nol < N && S.lptr[S.n_rows_nol + 1] == S.lptr[S.n_rows_nol]) S.n_rows_nol++;
         for (int r = S.n_rows_nol; r < N; ++r)
-            if (S.lptr[r + 1] == S.lptr[r]) { S.n_rows_nol = -1; break; }   // not a prefix: flat solve unusable
+            if (S.lptr[r + 1] == S.lptr[r]) {
+                err = "internal: rows without L entries are not a prefix of the numbering";
+                return false;
+            }
     }
 
     // ---- 4c. adjacency in the new numbering + assembly map -------------------------

@@ -38,17 +38,6 @@ struct Symbolic {
     // assembly map: slot -> adjacency entry (or -1 for fill), slot -> row
     std::vector<int> slot_src, slot_row, slot_col;
 
-    // triangular-solve schedule for the shared-memory solve kernel: steps in execution order
-    // (forward levels, then backward levels).  kind: 0 = forward level, rows from global memory;
-    // 1 = forward level prefetched through the shared-memory ring; 2 / 3 = same for backward
-    // levels; 4 = nothing to do.  a, b = row range [a, b) (forward) or position range (backward).
-    std::vector<int> sstep_kind, sstep_a, sstep_b;
-    // ring descriptors, 8 ints per ring step in execution order:
-    // {kind, row0, nrows, slot0, nblk, col0, ncol, 0}
-    std::vector<int> sring_desc;
-    static constexpr int RING_BLOCKS = 128;      // 2x2 blocks per ring slot
-    static constexpr int RING_ROWS = 32;         // rows per ring slot
-
     // flat solve schedule (k_solve_flat): the slots in consumption order cut into waves of <= 32
     // consecutive slots.  wave_tab: 2 ints per wave {first slot, n | flags | maxspan << 9};
     // smeta[slot]: span (lanes after this one in its row piece) | flags | row << 9.
@@ -58,7 +47,7 @@ struct Symbolic {
     int n_waves = 0;                             // waves (wave_tab may carry one padding entry)
     static constexpr int SOLVE_CHUNK_SLOTS = 128;
     int n_waves_l = 0;                           // waves of the forward solve (the rest is backward)
-    int n_rows_nol = 0;                          // rows [0, n_rows_nol) have no L entries (-1: not a prefix)
+    int n_rows_nol = 0;                          // rows [0, n_rows_nol) have no L entries (forward level 0)
     static constexpr int WAVE_SYNC = 64, WAVE_CONT = 128, WAVE_ISU = 256;          // n in bits 0-5
     static constexpr int META_HEAD = 32, META_ROWSTART = 64, META_ROWEND = 128, META_DIAG = 256;  // span in bits 0-4
 

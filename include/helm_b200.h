@@ -116,7 +116,7 @@ typedef struct helm_stats {
     int64_t kernel_launches;    /* kernels launched (graph nodes count)         */
     int64_t graph_launches;
     double ms_total;            /* device time of the whole solve (CUDA events) */
-    double ms_kernel[8];        /* per-kernel accumulated ms when profile=1: assemble, factor, solve, rhs_conv, advance, qlimit, pass_end, init */
+    double ms_kernel[12];       /* per-kernel accumulated ms when profile=1: assemble, factor, solve, rhs_conv, advance, qlimit, pass_end, init, eps, (reserved x3) */
 } helm_stats;
 
 const char *helm_last_error(void);

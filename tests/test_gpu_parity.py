@@ -185,7 +185,7 @@ def test_unstaged_kernels_agree(hb, monkeypatch):
         "print(json.dumps([r.V.real.tolist(), r.V.imag.tolist(), r.ncoef.tolist()]))"
     ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
     outs = []
-    for env_extra in ({}, {'HELM_B200_NO_COOP_FACTOR': '1', 'HELM_B200_NO_SMEM_SOLVE': '1'}):
+    for env_extra in ({}, {'HELM_B200_NO_COOP_FACTOR': '1', 'HELM_B200_NO_CTA_SOLVE': '1'}):
         env = dict(os.environ, **env_extra)
         out = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=300)
         assert out.returncode == 0, out.stderr[-2000:]
