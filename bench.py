@@ -373,11 +373,23 @@ def roofline_model(info, ncoef, stats, N):
     steps = max(1, stats['steps'])
     # K2 solve: LU blocks (32 B each) once + rhs read + x write (16 B each per bus)
     b_solve = orders * (32.0 * nslots + 32.0 * N)
-    # K1 k_rhs_conv at order j, per bus: histories V, W|CC (read j each) + x read, V[j], H[j], rhs
-    #   written: 16 B each.  K3 k_eps, even orders only: epsilon anti-diagonal read j-1, write j+1,
-    #   + x, V[j-1], Pade value read and written: 16 B each.
+    # K1 k_rhs_conv at order j, per bus (x read, V[j], H[j], rhs written: 64 B at every order):
+    #   PV bus: histories V and CC, read j each (32 j).  PQ bus, blocked W recurrence (block 4):
+    #   j < 4 or j % 4 == 0: histories V and W read j each (32 j), at a block start also three
+    #   partial sums written (48); j % 4 == i > 0: one partial read (16) and 4 i - 4 history values (16 each).
+    # K3 k_eps, even orders only: epsilon anti-diagonal read j-1, write j+1, + x, V[j-1], Pade value
+    #   read and written: 16 B each.
+    def conv_bytes_pq(mm):
+        j = np.arange(1, int(mm))
+        i = j & 3
+        walk = (j < 4) | (i == 0)
+        b = np.where(walk, 32.0 * j + np.where(j >= 4, 48.0, 0.0), 16.0 + 16.0 * (4 * i - 4))
+        return float(np.sum(b + 64.0))
     orders_even = float(np.sum(half))
-    b_rhs = (32.0 * sum_j + 64.0 * orders) * N
+    n_pv = float(info.get('n_pv', 0))
+    um, cnt = np.unique(m, return_counts=True)
+    b_pq = float(sum(c * conv_bytes_pq(v) for v, c in zip(um, cnt)))
+    b_rhs = b_pq * (N - n_pv) + (32.0 * sum_j + 64.0 * orders) * n_pv
     b_eps = (32.0 * sum_j_even + 64.0 * orders_even) * N
     # K2f factor: read A blocks + write LU blocks (32 B per slot each way), per pass
     b_fac = passes * (64.0 + 32.0) * nslots       # assembly (write) + factorization (read, write)
