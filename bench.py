@@ -193,7 +193,8 @@ def run_cuda(args):
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
-            os.environ['NCCL_DEBUG'] = 'WARN'      # keep stdout to the one JSON line
+            os.environ['NCCL_DEBUG'] = 'WARN'
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')   # keep stdout to the one JSON line
         dist.init_process_group('nccl', device_id=dev)
     B = args.batch
     case = load_case(CASE)

@@ -275,3 +275,42 @@ def test_flat_wave_schedule_solves(name):
             lane += span + 1
     assert (covered == 1).all()
     assert np.allclose(y, x, rtol=1e-9, atol=1e-9)
+
+
+def _write_matpower(path, name, buses, branches, gens, base=100.0):
+    def mat(a):
+        return '\n'.join('\t' + '\t'.join(repr(float(v)) for v in row) + ';' for row in a)
+    with open(path, 'w') as f:
+        f.write('function mpc = %s\n%% test case\nmpc.version = \'2\';\nmpc.baseMVA = %r;\n' % (name, base))
+        f.write('%% bus data\nmpc.bus = [\n%s\n];\n' % mat(buses))
+        f.write('mpc.gen = [\n%s\n];\n' % mat(gens))
+        f.write('mpc.branch = [ %% fbus tbus r x b ...\n%s\n];\n' % mat(branches))
+
+
+@pytest.mark.parametrize('name', ['case9', 'case118'])
+def test_matpower_reader(name, tmp_path):
+    """A MATPOWER .m case loads to the same CaseData as the reference-format tables, also from a
+    file on another MVA base, and converts to the reference's .xlsx layout."""
+    from common import load_tables
+    from helmpy_b200.core.matpower import create_case_data_object_from_matpower, matpower_to_xlsx
+    from helmpy_b200.core.classes import create_case_data_object_from_xlsx
+    buses, branches, gens = load_tables(name)
+    ref = load_case(name)
+    m = str(tmp_path / (name + '.m'))
+    _write_matpower(m, name, buses, branches, gens)
+    c = create_case_data_object_from_matpower(m)
+    assert c.name == name and c.N == ref.N and c.slack == ref.slack
+    for attr in ('Pd', 'Qd', 'Pg', 'Qgmax', 'Qgmin', 'Yshunt', 'Ytrans_val', 'Y_val', 'adj_idx', 'phase_val'):
+        assert np.array_equal(getattr(c, attr), getattr(ref, attr)), attr
+    # the same grid written on a 50 MVA base (z halves, line charging doubles)
+    b2 = branches.copy()
+    b2[:, 2:4] *= 0.5
+    b2[:, 4] *= 2.0
+    m2 = str(tmp_path / (name + '_50.m'))
+    _write_matpower(m2, name, buses, b2, gens, base=50.0)
+    c2 = create_case_data_object_from_matpower(m2)
+    assert np.allclose(c2.Ytrans_val, ref.Ytrans_val, rtol=1e-14, atol=0) and np.allclose(c2.Y_val, ref.Y_val, rtol=1e-13)
+    x = str(tmp_path / (name + '.xlsx'))
+    matpower_to_xlsx(m, x)
+    c3 = create_case_data_object_from_xlsx(x)
+    assert np.array_equal(c3.Ytrans_val, ref.Ytrans_val) and np.array_equal(c3.Pd, ref.Pd)
