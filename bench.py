@@ -11,7 +11,7 @@ scale=s, max_coefficients=40) would (Q limits on).  Metric: converged power-flow
 cases per second, whole job (all ranks).  `value` is measured with the scenario
 scales and the grid already resident in HBM; `e2e` goes through the host-buffer
 C-ABI call (`helm_batch`): scales host->device and voltages device->host inside
-the timed region.  4096 scenarios are resident at a time (6.3 MB each, 26 GB:
+the timed region.  4096 scenarios are resident at a time (7 MB each, 28 GB:
 far beyond the 126 MB L2, so every step streams from HBM); the rest of the batch
 queues on the device and takes over slots as scenarios finish.
 """
@@ -408,7 +408,7 @@ def main():
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='cuda', choices=['cuda', 'reference'])
-    ap.add_argument('--batch', type=int, default=int(os.environ.get('HELM_BENCH_BATCH', '16384')),
+    ap.add_argument('--batch', type=int, default=int(os.environ.get('HELM_BENCH_BATCH', '32768')),
                     help='scenarios per GPU per step')
     ap.add_argument('--group', type=int, default=int(os.environ.get('HELM_BENCH_GROUP', '1')))
     ap.add_argument('--resident', type=int, default=int(os.environ.get('HELM_BENCH_RESIDENT', '4096')),

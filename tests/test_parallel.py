@@ -24,10 +24,13 @@ class _Res:
     pass
 
 
-def _stub_solver(case, scales, **kw):
+def _stub_solver(case, scales, outages=None, **kw):
     r = _Res()
     n = len(scales)
     r.V = (np.outer(scales, np.arange(1, 6)) + 1j * scales[:, None]).astype(np.complex128)
+    if outages is not None:                    # N-1 scenarios: the removed branch must travel with its scale
+        assert len(outages) == n
+        r.V = r.V + 1000.0 * np.asarray(outages, dtype=np.float64)[:, None]
     r.status = np.full(n, 2, dtype=np.int32)
     r.ncoef = np.tile(np.arange(16, dtype=np.int32), (n, 1)) * (1 + np.arange(n, dtype=np.int32))[:, None]
     r.nswitch = (scales * 100).astype(np.int32)
@@ -50,6 +53,10 @@ def _worker(rank, world, port, n, q):
         lo, hi = parallel.shard_bounds(n, world, r)
         exp.append(_stub_solver(None, scales[lo:hi]).ncoef)
     ok = ok and np.array_equal(ncoef, np.concatenate(exp))
+    # N-1 sweep: outages are sharded with the scales (scales=None means all ones)
+    outages = np.arange(n, dtype=np.int32)[::-1].copy()
+    V2, st2, _, _ = parallel.helm_batch_sharded(None, None, solve_fn=_stub_solver, outages=outages)
+    ok = ok and np.array_equal(V2, _stub_solver(None, np.ones(n), outages=outages).V)
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 

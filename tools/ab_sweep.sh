@@ -1,7 +1,4 @@
-export HELM_RESIDENT=4096
-run() { python tools/sweep.py case2869pegase 16384 1 2>&1 | grep case | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['cases_per_s'], d['ms'], d['steps'])"; }
-echo "two chains, solve prio"; run
-echo "two chains, no prio"; HELM_B200_NO_SOLVE_PRIO=1 run
-echo "one chain"; HELM_B200_NO_CHAINS=1 run
-echo "two chains prio R=8192"; HELM_RESIDENT=8192 run
-echo "two chains prio R=5600"; HELM_RESIDENT=5600 run
+run() { python tools/sweep.py case2869pegase $1 1 2>&1 | grep case | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['cases_per_s'], d['ms'], d['steps'])"; }
+for R in 4096 8192 8800 9100 12288; do echo "R=$R B=32768"; HELM_RESIDENT=$R run 32768; done
+echo "R=4096 B=16384"; HELM_RESIDENT=4096 run 16384
+echo "R=8800 B=16384"; HELM_RESIDENT=8800 run 16384
