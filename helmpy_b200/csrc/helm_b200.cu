@@ -718,23 +718,27 @@ struct FlatStage { double2 m0, m1; int col, meta, info; };
 constexpr int FLAT_WPB = 7;
 constexpr int FLAT_NST = 2;
 
-__device__ __forceinline__ void flat_prefetch(const PlanDev &p, const double2 *lu, FlatStage &S, int wp, int lane,
-                                              int2 &wt, int2 &wtn) {
+// opaque copy of a pointer: keeps the 64-bit base in a register pair so that every access is one
+// IMAD.WIDE + load instead of a recomputation from the kernel parameters
+template <typename T>
+__device__ __forceinline__ T *pin_ptr(T *ptr) {
+    asm volatile("" : "+l"(ptr));
+    return ptr;
+}
+
+__device__ __forceinline__ void flat_prefetch(const int2 *wave_tab, const int2 *scm, int nwaves, const double2 *lu,
+                                              FlatStage &S, int wp, int lane, int2 &wnext) {
     S.info = 0;
     S.meta = helm::Symbolic::META_DIAG;
-    if (wp < p.nwaves) {
-        if ((wp & 31) == 0 && wp > 0) {          // next chunk of the wave table (loaded 32 waves ago)
-            wt = wtn;
-            int idx = wp + 32 + lane;
-            wtn = (idx < p.nwaves) ? __ldg(p.wave_tab + idx) : make_int2(0, 0);
-        }
-        const int e0 = __shfl_sync(0xFFFFFFFFu, wt.x, wp & 31);
-        S.info = __shfl_sync(0xFFFFFFFFu, wt.y, wp & 31);
-        const int n = S.info & 63;
-        const int e = e0 + min(lane, n - 1);     // idle lanes repeat the last block (and contribute 0)
-        S.m0 = __ldcs(lu + 2 * (size_t)e);
-        S.m1 = __ldcs(lu + 2 * (size_t)e + 1);
-        const int2 cm = __ldg((const int2 *)p.scm + e);
+    if (wp < nwaves) {
+        const int2 wi = wnext;                                   // entry of wave wp, loaded one call ago
+        wnext = __ldg(wave_tab + min(wp + 1, nwaves - 1));
+        S.info = wi.y;
+        const int n = wi.y & 63;
+        const int e = wi.x + min(lane, n - 1);                   // idle lanes repeat the last block (and contribute 0)
+        S.m0 = __ldcs(lu + 2 * e);
+        S.m1 = __ldcs(lu + 2 * e + 1);
+        const int2 cm = __ldg(scm + e);
         S.col = cm.x;
         S.meta = (lane < n) ? cm.y : helm::Symbolic::META_DIAG;
     }
@@ -748,9 +752,15 @@ __device__ __forceinline__ void flat_gather(const FlatStage &S, const double2 *r
     xg = make_double2(0.0, 0.0);
     if (!(S.meta & Sy::META_DIAG)) xg = xb[S.col];
     if ((S.meta & (Sy::META_HEAD | Sy::META_ROWSTART)) == (Sy::META_HEAD | Sy::META_ROWSTART)) {
-        const int r = S.meta >> 9;
-        bs = (S.info & Sy::WAVE_ISU) ? xb[r] : rhs[r];
+        const double2 *base = (S.info & Sy::WAVE_ISU) ? xb : rhs;
+        bs = base[S.meta >> 9];
     }
+}
+
+// v += t on the lanes with o <= span (predicated adds, no selects)
+__device__ __forceinline__ void add_if_le(double2 &v, double tx, double ty, int o, int span) {
+    asm("{\n\t.reg .pred p;\n\tsetp.le.s32 p, %4, %5;\n\t@p add.f64 %0, %0, %2;\n\t@p add.f64 %1, %1, %3;\n\t}"
+        : "+d"(v.x), "+d"(v.y) : "d"(tx), "d"(ty), "r"(o), "r"(span));
 }
 
 template <int WPB>
@@ -766,15 +776,16 @@ __global__ void __maxnreg__(64) k_solve_flat(PlanDev p, WorkDev w, int side) {
     }
     if (w.s_status[grp] != ST_ACTIVE) return;
     const int lane = threadIdx.x & 31;
-    const double2 *lu = lu_of(p, w, grp);
-    const double2 *rhs = w.rhs + (size_t)grp * p.N;
-    double2 *xb = w.xb + (size_t)grp * p.N;
+    const double2 *lu = pin_ptr(lu_of(p, w, grp));
+    const double2 *rhs = pin_ptr(w.rhs + (size_t)grp * p.N);
+    double2 *xb = pin_ptr(w.xb + (size_t)grp * p.N);
+    const int2 *wave_tab = pin_ptr(p.wave_tab);
+    const int2 *scm = pin_ptr((const int2 *)p.scm);
     const int nw = p.nwaves;
-    int2 wt = (lane < nw) ? __ldg(p.wave_tab + lane) : make_int2(0, 0);
-    int2 wtn = (32 + lane < nw) ? __ldg(p.wave_tab + 32 + lane) : make_int2(0, 0);
+    int2 wnext = __ldg(wave_tab);
     FlatStage st[FLAT_NST];
 #pragma unroll
-    for (int s = 0; s < FLAT_NST - 1; ++s) flat_prefetch(p, lu, st[s], s, lane, wt, wtn);
+    for (int s = 0; s < FLAT_NST - 1; ++s) flat_prefetch(wave_tab, scm, nw, lu, st[s], s, lane, wnext);
     // rows without L entries: y = rhs
     for (int r = lane; r < p.n_rows_nol; r += 32) xb[r] = rhs[r];
     const double2 zero = make_double2(0.0, 0.0);
@@ -793,7 +804,7 @@ __global__ void __maxnreg__(64) k_solve_flat(PlanDev p, WorkDev w, int side) {
                     flat_gather(S, rhs, xb, xg, bs);
                 }
                 // stage of wave wv-1 is free: fetch wave wv + NST - 1 into it
-                flat_prefetch(p, lu, st[(s + FLAT_NST - 1) % FLAT_NST], wv + FLAT_NST - 1, lane, wt, wtn);
+                flat_prefetch(wave_tab, scm, nw, lu, st[(s + FLAT_NST - 1) % FLAT_NST], wv + FLAT_NST - 1, lane, wnext);
                 const bool nxt_early = (wv + 1 < nw) && !(Sn.info & Sy::WAVE_SYNC);
                 if (nxt_early) flat_gather(Sn, rhs, xb, xgn, bsn);
                 // ---- reduce wave wv
@@ -803,7 +814,7 @@ __global__ void __maxnreg__(64) k_solve_flat(PlanDev p, WorkDev w, int side) {
                 for (int o = 1; o <= maxspan; o <<= 1) {
                     double tx = __shfl_down_sync(0xFFFFFFFFu, v.x, o);
                     double ty = __shfl_down_sync(0xFFFFFFFFu, v.y, o);
-                    if (o <= span) { v.x += tx; v.y += ty; }
+                    add_if_le(v, tx, ty, o, span);
                 }
                 double2 acc = zero;
                 const bool head = (meta & Sy::META_HEAD) != 0;
@@ -816,7 +827,7 @@ __global__ void __maxnreg__(64) k_solve_flat(PlanDev p, WorkDev w, int side) {
                         if (info & Sy::WAVE_ISU) {
                             double2 d0 = S.m0, d1 = S.m1;
                             if (!rs) {                       // row longer than a wave: its pivot came earlier
-                                const size_t ds = (size_t)__ldg(p.dslot + (meta >> 9));
+                                const int ds = __ldg(p.dslot + (meta >> 9));
                                 d0 = lu[2 * ds]; d1 = lu[2 * ds + 1];
                             }
                             out = make_double2(d0.x * acc.x + d0.y * acc.y, d1.x * acc.x + d1.y * acc.y);
