@@ -91,7 +91,7 @@ def run_reference(args):
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': workload_config(per_step, 1),
+        'config': workload_config(args.batch, args.gpus),      # the CUDA arm's workload; each step times a bounded sample of it
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                          'sample': '%d scenarios per step over %d processes (numpy/scipy oracle port of '
                                    'the reference algorithm; the reference itself is pure Python and is '
@@ -107,7 +107,7 @@ def workload_config(batch_per_gpu, n_gpus):
                     'max_coefficients 40, scale~U[%.2f,%.2f]' % (CASE, SCALE_LO, SCALE_HI),
         'grid': CASE, 'n_bus': 2869, 'scenarios_per_gpu': batch_per_gpu,
         'scenarios_total': batch_per_gpu * n_gpus, 'parallelism': 'scenario-sharded x%d' % n_gpus,
-        'l2': 'working set >> 126 MB L2 (6.3 MB per resident scenario), no flush needed',
+        'l2': 'working set >> 126 MB L2 (7 MB per resident scenario), no flush needed',
         'resident_scenarios_per_gpu': RESIDENT[0],
     }
 
