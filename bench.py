@@ -268,8 +268,10 @@ def run_cuda(args):
 
     # ---- e2e: host buffers through the public API, H2D + D2H inside the timed region -------
     host_scales = [scenario_scales(B, 5000 + 1000 * rank + it) for it in range(2)]
-    helmpy_b200.helm_batch(case, host_scales[0], mismatch=MISMATCH, max_coefficients=MAX_COEF, group=args.group,
-                           max_resident=args.resident)
+    res = None
+    for it in range(2):     # warm-up: plan workspace, and the two page-locked result blocks a `res = helm_batch(...)` loop alternates between
+        res = helmpy_b200.helm_batch(case, host_scales[it], mismatch=MISMATCH, max_coefficients=MAX_COEF, group=args.group,
+                                     max_resident=args.resident)
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()

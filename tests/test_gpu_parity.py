@@ -285,7 +285,7 @@ VARIANTS = [(1, False, None), (2, False, 1), (2, False, 2), (1, False, 1), (1, F
             (2, True, 1), (2, True, 2), (1, True, 1), (1, True, 2)]        # test/test_helmpy.py:111-122
 
 
-@pytest.mark.parametrize('name', ['case9', 'case118', 'case1354pegase'])
+@pytest.mark.parametrize('name', CASES)             # the reference's full 10-variant x 4-case matrix (test/test_helmpy.py:111-156)
 @pytest.mark.parametrize('variant', VARIANTS)
 def test_helm_variants_match_reference_golden_xlsx(hb, name, variant):
     """The rest of the reference's own test matrix: PV model 1 and the distributed-slack
