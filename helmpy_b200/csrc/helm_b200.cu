@@ -908,6 +908,63 @@ __device__ __forceinline__ void cta_issue_chunk(const PlanDev &p, const double2 
     bulk_g2s(sb + CS_CH * 32, p.scm + (size_t)t0 * 2, (unsigned)(tn * 8), bars + stage);
 }
 
+struct CtaOps { double2 m0, m1; int col, meta, info; };
+__device__ __forceinline__ void cta_load_ops(CtaOps &o, const int2 *swave, const double2 *slu, const int2 *stab,
+                                             int slot0, int tab0, int k, int lane) {
+    const int2 wi = swave[k];
+    o.info = wi.y;
+    o.m0 = o.m1 = make_double2(0.0, 0.0);
+    o.col = 0; o.meta = helm::Symbolic::META_DIAG;
+    if (lane < (wi.y & 63)) {
+        const int idx = wi.x - slot0 + lane;
+        o.m0 = slu[2 * idx];
+        o.m1 = slu[2 * idx + 1];
+        const int2 t = stab[wi.x + lane - tab0];
+        o.col = t.x; o.meta = t.y;
+    }
+}
+
+// waves [a, e): each a level of its own, processed in order by one warp
+__device__ __forceinline__ void cta_thin_run(const int2 *swave, const double2 *slu, const int2 *stab, int slot0,
+                                             int tab0, double2 *xs, double2 *carry_s, int a, int e, int lane) {
+    using Sy = helm::Symbolic;
+    const double2 zero = make_double2(0.0, 0.0);
+    CtaOps nx;
+    cta_load_ops(nx, swave, slu, stab, slot0, tab0, a, lane);
+    for (int k = a; k < e; ++k) {
+        const CtaOps o = nx;
+        if (k + 1 < e) cta_load_ops(nx, swave, slu, stab, slot0, tab0, k + 1, lane);
+        if (k > a) __syncwarp();                             // x of the previous level is in shared memory
+        const int meta = o.meta, info = o.info;
+        double2 xg = zero, b = zero;
+        if (!(meta & Sy::META_DIAG)) xg = xs[o.col];
+        const bool head = (meta & Sy::META_HEAD) != 0, rs = (meta & Sy::META_ROWSTART) != 0;
+        if (head) b = rs ? xs[meta >> 9] : carry_s[0];
+        double2 v = make_double2(o.m0.x * xg.x + o.m0.y * xg.y, o.m1.x * xg.x + o.m1.y * xg.y);
+        const int span = meta & 31, maxspan = (info >> 9) & 31;
+        for (int s = 1; s <= maxspan; s <<= 1) {
+            double tx = __shfl_down_sync(0xFFFFFFFFu, v.x, s);
+            double ty = __shfl_down_sync(0xFFFFFFFFu, v.y, s);
+            if (s <= span) { v.x += tx; v.y += ty; }
+        }
+        if (head) {
+            const double2 acc = make_double2(b.x - v.x, b.y - v.y);
+            if (meta & Sy::META_ROWEND) {
+                double2 out = acc;
+                if (info & Sy::WAVE_ISU) {
+                    const double2 d0 = rs ? o.m0 : carry_s[1];
+                    const double2 d1 = rs ? o.m1 : carry_s[2];
+                    out = make_double2(d0.x * acc.x + d0.y * acc.y, d1.x * acc.x + d1.y * acc.y);
+                }
+                xs[meta >> 9] = out;
+            } else {
+                carry_s[0] = acc;
+                if ((info & Sy::WAVE_ISU) && rs) { carry_s[1] = o.m0; carry_s[2] = o.m1; }
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(CS_T) k_solve_cta(PlanDev p, WorkDev w, int side) {
     using Sy = helm::Symbolic;
     TL_SCOPE(w, 2);
@@ -960,6 +1017,19 @@ __global__ void __launch_bounds__(CS_T) k_solve_cta(PlanDev p, WorkDev w, int si
         const int wend = ch.x + ch.y;
         bool fresh = true;                                   // a block barrier has just been passed
         while (wv < wend) {
+            if (swave[wv].y & Sy::WAVE_THIN) {
+                // chain of one-wave levels (the long tail near the root of the elimination tree):
+                // warp 0 runs it alone — warp barriers instead of block barriers, and the operands of
+                // the next wave (which do not depend on x) are fetched from the ring while this one
+                // is reduced; the other warps wait at the next block barrier
+                int e = wv + 1;
+                while (e < wend && (swave[e].y & Sy::WAVE_THIN)) ++e;
+                if (!fresh) __syncthreads();
+                fresh = false;
+                if (wp == 0) cta_thin_run(swave, slu, stab, ch.z, tab0, xs, carry_s, wv, e, lane);
+                wv = e;
+                continue;
+            }
             int r = wv + 1;
             while (r < wend && !(swave[r].y & Sy::WAVE_SYNC)) ++r;
             if ((swave[wv].y & Sy::WAVE_SYNC) && !fresh) __syncthreads();

@@ -401,6 +401,11 @@ bool build_symbolic(int N, const int32_t *adj_ptr, const int32_t *adj_idx, const
         {
             const int nwv = (int)S.wave_tab.size() / 2;
             S.n_waves = nwv;
+            for (int k = 0; k < nwv; ++k) {      // one-wave levels: k_solve_cta runs chains of them in one warp
+                bool sync_k = (S.wave_tab[2 * k + 1] & Symbolic::WAVE_SYNC) != 0;
+                bool sync_next = (k + 1 >= nwv) || (S.wave_tab[2 * (k + 1) + 1] & Symbolic::WAVE_SYNC) != 0;
+                if (sync_k && sync_next) S.wave_tab[2 * k + 1] |= Symbolic::WAVE_THIN;
+            }
             int wv = 0;
             while (wv < nwv) {
                 int w0 = wv, s0 = S.wave_tab[2 * wv], ns = 0;
