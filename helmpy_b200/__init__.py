@@ -6,4 +6,4 @@
 from helmpy_b200.core import *  # noqa: F401,F403
 from helmpy_b200.core import (helm, helm_batch, non_islanding_branches,  # noqa: F401
                               create_case_data_object_from_xlsx, nr, nr_ds,
-                              create_case_data_object_from_matpower, matpower_to_xlsx)
+                              create_case_data_object_from_matpower, matpower_to_xlsx, nr_batch)

@@ -62,7 +62,7 @@ KERNEL_NAMES = ("assemble", "factor", "solve", "rhs_conv", "advance", "qlimit", 
 EXPORTED_SYMBOLS = (
     "helm_last_error", "helm_plan_create", "helm_plan_destroy", "helm_plan_get_info",
     "helm_plan_get_perm", "helm_plan_set_outages", "helm_workspace_bytes", "helm_solve_batch_device",
-    "helm_solve_batch_host", "helm_last_state_host", "helm_last_ploss_host", "helm_debug_factor_solve", "helm_debug_timeline", "helm_measure_peaks",
+    "helm_solve_batch_host", "helm_nr_batch_host", "helm_last_state_host", "helm_last_ploss_host", "helm_debug_factor_solve", "helm_debug_timeline", "helm_measure_peaks",
     "helm_symbolic_create", "helm_symbolic_destroy", "helm_symbolic_array",
 )
 
@@ -99,6 +99,8 @@ def load():
     lib.helm_solve_batch_host.argtypes = [
         C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p,
         C.c_void_p, C.c_void_p, C.POINTER(Stats)]
+    lib.helm_nr_batch_host.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_double, C.c_int32, C.c_int32,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.helm_last_state_host.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     lib.helm_last_ploss_host.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     lib.helm_debug_factor_solve.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
@@ -268,6 +270,20 @@ class Plan:
                                         _ptr(status), _ptr(ncoef), _ptr(nswitch), C.byref(stats)),
               "helm_solve_batch_host")
         return vout, status, ncoef, nswitch, stats_dict(stats)
+
+    def nr_host(self, scales, mismatch, max_iterations, enforce_q_limits):
+        """Batched Newton-Raphson cross-check on the GPU: numpy in, numpy out."""
+        lib = load()
+        scales = np.ascontiguousarray(scales, dtype=np.float64)
+        B = len(scales)
+        vout = _result_array(B, self.N)
+        status = np.zeros(B, dtype=np.int32)
+        iters = np.zeros((B, HELM_MAX_PASSES), dtype=np.int32)
+        nswitch = np.zeros(B, dtype=np.int32)
+        check(lib.helm_nr_batch_host(self.handle, B, _ptr(scales), float(mismatch), int(max_iterations),
+                                     int(bool(enforce_q_limits)), _ptr(vout), _ptr(status), _ptr(iters),
+                                     _ptr(nswitch)), "helm_nr_batch_host")
+        return vout, status, iters, nswitch
 
     def solve_device(self, d_scale, params, workspace, d_vout, d_status, d_ncoef, d_nswitch,
                      stream_ptr):

@@ -180,3 +180,35 @@ def nr_ds(grid_data_file_path, Print_Details=False, Mismatch=1e-4, Scale=1, MaxI
         _report(case, V, 'NR DS', Scale, Mismatch, Enforce_Qlimits, Print_Details, Save_results,
                 Results_FileName or case.name)
     return V
+
+
+class NRBatchResult:
+    """Result of ``nr_batch``: ``V`` [B, N] complex128 (zeros where not converged), ``status``
+    (2 converged, 3 diverged, 4 singular Jacobian), ``iterations`` [B, 16] Newton steps per
+    Q-limit pass (the reference's ``list_iterations``), ``nswitch`` PV->PQ switches."""
+
+    def __init__(self, V, status, iterations, nswitch):
+        self.V, self.status, self.iterations, self.nswitch = V, status, iterations, nswitch
+
+    @property
+    def converged(self):
+        return self.status == 2
+
+    def list_iterations(self, b):
+        row = self.iterations[b]
+        return [int(x) - 1 for x in row[row > 0]]            # the C ABI stores steps + 1 (0 = pass not run)
+
+
+def nr_batch(case, scales, Mismatch=1e-4, MaxIterations=15, Enforce_Qlimits=True):
+    """Newton-Raphson cross-check for ``len(scales)`` load-scaling scenarios on the GPU.
+
+    Scenario b equals ``nr(case, Mismatch=..., Scale=scales[b], ...)`` (reference nr.py:506-598,
+    classic slack): same flat start, same update, same convergence test and Q-limit handling; the
+    Jacobian lives on the 2x2-block pattern of the HELM plan and is factorized and solved by the
+    same kernels (csrc/helm_nr.cuh).  ``case`` is not mutated.
+    """
+    from .helm import get_plan
+    plan = get_plan(case)
+    V, status, iters, nswitch = plan.nr_host(np.asarray(scales, dtype=np.float64), Mismatch, MaxIterations,
+                                             Enforce_Qlimits)
+    return NRBatchResult(V, status, iters, nswitch)

@@ -98,6 +98,7 @@ struct WorkDev {
     int *g_fage;                      // [ngroups] steps left until a group being factorized rejoins
     int parity;                       // list of the current step: step % (depth + 1) (host-set per launch)
     int depth;                        // steps a factorization may take (side-branch pipeline depth)
+    int skip_asm;                     // k_factor_coop: the LU slots already hold the matrix (Newton-Raphson Jacobian)
     int *out_status, *out_ncoef, *out_nswitch;   // per-scenario outputs, written when a scenario ends
     unsigned char *btype;             // [group][N][G]
     double *Qg, *VVant;               // [group][N][G]
@@ -461,13 +462,15 @@ __global__ void __launch_bounds__(WPB * 32) k_factor_coop(PlanDev p, WorkDev w) 
     if (w.s_status[grp] != ST_ACTIVE) continue;             // G = 1: warp-uniform
     // assembly of A by the same warp (no separate kernel in front: the factorization starts at the
     // beginning of the step, while the main branch's solve is being dispatched)
-    if (w.g_flags[grp] & GF_NEWSCEN) {
-        asm_reset<1>(p, w, grp, lane, 32);
+    if (!w.skip_asm) {
+        if (w.g_flags[grp] & GF_NEWSCEN) {
+            asm_reset<1>(p, w, grp, lane, 32);
+            __syncwarp();
+        }
+        if (uses_shared_lu(w, grp)) continue;               // first pass: the shared factors are used
+        for (int slot = lane; slot < p.nslots; slot += 32) asm_slot<1>(p, w, grp, slot, 0);
         __syncwarp();
     }
-    if (uses_shared_lu(w, grp)) continue;                   // first pass: the shared factors are used
-    for (int slot = lane; slot < p.nslots; slot += 32) asm_slot<1>(p, w, grp, slot, 0);
-    __syncwarp();
     double2 *lu = w.lu + (size_t)grp * p.nslots * 2;
     char *base = (char *)smem_f + (size_t)wib * factor_smem_per_warp(p.cap_upd, p.cap_ent, p.cap_rowblk);
     double2 *sSrc = (double2 *)base;
@@ -1635,6 +1638,7 @@ __global__ void k_pass_end(WorkDev w) {
 }
 
 #include "helm_variants.cuh"
+#include "helm_nr.cuh"
 
 // ---- K_begin: start of a step.  Groups factorized during the previous step rejoin the main
 // branch; groups whose pass ended in the previous step move to the factorization branch.
@@ -1837,7 +1841,7 @@ WorkDev bind(const helm_plan *pl, const WsLayout &L, int B, const helm_params *p
     int *gi = (int *)(b + L.off_gint);
     w.g_n = gi; w.g_flags = gi + L.ngroups; w.active_groups = gi + 2 * L.ngroups; w.queue_next = gi + 2 * L.ngroups + 1;
     w.fact_count = gi + 2 * L.ngroups + 2; w.g_fage = gi + 2 * L.ngroups + 16; w.fact_list = gi + 3 * L.ngroups + 16; w.parity = 0;
-    w.depth = 1;
+    w.depth = 1; w.skip_asm = 0;
     w.scale_in = nullptr; w.outage_in = nullptr; w.out_status = nullptr; w.out_ncoef = nullptr; w.out_nswitch = nullptr;
     w.btype = (unsigned char *)(b + L.off_btype);
     w.Qg = (double *)(b + L.off_Qg);
@@ -1905,7 +1909,7 @@ void launch_kernel(int which, const PlanDev &p, const WorkDev &w, cudaStream_t s
         case KI_PV1C_MAIN: k_pv1_correct<<<gridBus, T_ELEM, 0, st>>>(p, w, 0); break;
         case KI_PV1C_SIDE: k_pv1_correct<<<gridBus, T_ELEM, 0, st>>>(p, w, 1); break;
         case KI_SOLVE_SIDE:
-            if (p.use_cta_solve) k_solve_cta<<<w.ngroups, CS_T, cta_solve_layout(p.N, p.nwaves, p.nschunks).total, st>>>(p, w, 1);
+            if (p.use_cta_solve && w.ngroups <= p.cta_solve_max_groups) k_solve_cta<<<w.ngroups, CS_T, cta_solve_layout(p.N, p.nwaves, p.nschunks).total, st>>>(p, w, 1);
             else k_solve_flat<FLAT_WPB><<<(w.ngroups + FLAT_WPB - 1) / FLAT_WPB, FLAT_WPB * 32, 0, st>>>(p, w, 1);
             break;
         case KI_SOLVE:
@@ -2486,6 +2490,76 @@ int helm_solve_batch_host(helm_plan *pl, int32_t B, const double *h_scale, const
     if (h_nswitch) CUDA_TRY(cudaMemcpyAsync(h_nswitch, pl->d_nswitch, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return HELM_OK;
+}
+
+int helm_nr_batch_host(helm_plan *pl, int32_t B, const double *h_scale, double mismatch, int32_t max_iterations,
+                       int32_t enforce_q_limits, double *h_vout, int32_t *h_status, int32_t *h_iters,
+                       int32_t *h_nswitch) {
+    if (!pl || !h_scale || !h_vout || !h_status || B <= 0) { g_err = "null/invalid argument"; return HELM_E_ARG; }
+    if (!(mismatch > 0) || max_iterations < 1) { g_err = "mismatch must be positive and max_iterations >= 1"; return HELM_E_ARG; }
+    if (!pl->d.use_coop_factor) { g_err = "grid too large for the staged factorization used by the GPU Newton-Raphson"; return HELM_E_STRUCT; }
+    const PlanDev &p = pl->d;
+    const size_t N = pl->S.N;
+    if (!pl->stream) CUDA_TRY(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
+    cudaStream_t st = pl->stream;
+    if (!pl->h_pinned) CUDA_TRY(cudaMallocHost((void **)&pl->h_pinned, 64));
+    const int CH = 4096;                                    // scenarios per chunk (all resident)
+    helm_params prm;
+    memset(&prm, 0, sizeof(prm));
+    prm.mismatch = mismatch; prm.max_coefficients = 5; prm.group = 1; prm.max_resident = CH;
+    const int nmax = std::min<int>(B, CH);
+    WsLayout L = layout(pl, nmax, &prm);
+    if (pl->ws_bytes < L.total) {
+        if (pl->ws) cudaFree(pl->ws);
+        pl->ws = nullptr; pl->ws_bytes = 0;
+        CUDA_TRY(cudaMalloc(&pl->ws, L.total));
+        pl->ws_bytes = L.total;
+    }
+    pl->last_B = 0;                                         // the HELM state of the workspace is gone
+    double *d_scale = nullptr, *d_vout = nullptr;
+    int *d_int = nullptr;
+    CUDA_TRY(cudaMalloc((void **)&d_scale, sizeof(double) * nmax));
+    CUDA_TRY(cudaMalloc((void **)&d_vout, sizeof(double) * 2 * N * nmax));
+    CUDA_TRY(cudaMalloc((void **)&d_int, sizeof(int) * nmax * (2 + HELM_MAX_PASSES)));
+    int rc = HELM_OK;
+    for (int b0 = 0; b0 < B && rc == HELM_OK; b0 += CH) {
+        const int nb = std::min(CH, B - b0);
+        L = layout(pl, nb, &prm);
+        WorkDev w = bind(pl, L, nb, &prm, pl->ws, d_vout);
+        w.scale_in = d_scale;
+        w.skip_asm = 1;
+        int *d_status = d_int, *d_nsw = d_int + nb, *d_iters = d_int + 2 * nb;
+        cudaMemcpyAsync(d_scale, h_scale + b0, sizeof(double) * nb, cudaMemcpyHostToDevice, st);
+        dim3 gridBus((p.N + T_ELEM - 1) / T_ELEM, w.ngroups);
+        const int gridGrp = (w.ngroups + 127) / 128;
+        k_nr_init<<<gridBus, T_ELEM, 0, st>>>(p, w);
+        const long max_rounds = (long)(max_iterations + 2) * 4 * HELM_MAX_PASSES;
+        int active = 1;
+        for (long round = 0; round < max_rounds && active > 0; ++round) {
+            cudaMemsetAsync(w.active_groups, 0, sizeof(int), st);
+            cudaMemsetAsync(w.fact_count, 0, sizeof(int), st);
+            k_nr_eval<<<gridBus, T_ELEM, 0, st>>>(p, w);
+            k_nr_decide<<<gridGrp, 128, 0, st>>>(w, mismatch, max_iterations);
+            if (enforce_q_limits) k_nr_qlim<<<gridBus, T_ELEM, 0, st>>>(p, w);
+            k_nr_passend<<<gridGrp, 128, 0, st>>>(w, enforce_q_limits);
+            cudaMemcpyAsync(pl->h_pinned, w.active_groups, sizeof(int), cudaMemcpyDeviceToHost, st);
+            k_nr_assemble<<<std::min(w.ngroups, 592), 256, 0, st>>>(p, w);
+            launch_any(1, KI_FACTOR, p, w, st);
+            launch_any(1, KI_SOLVE_SIDE, p, w, st);
+            k_nr_update<<<gridBus, T_ELEM, 0, st>>>(p, w);
+            if (cudaStreamSynchronize(st) != cudaSuccess) { g_err = "CUDA failure in the Newton-Raphson step"; rc = HELM_E_CUDA; break; }
+            active = pl->h_pinned[0];
+        }
+        if (rc != HELM_OK) break;
+        k_nr_out<<<gridBus, T_ELEM, 0, st>>>(p, w, (double2 *)d_vout, d_status, h_iters ? d_iters : nullptr, h_nswitch ? d_nsw : nullptr);
+        cudaMemcpyAsync(h_vout + (size_t)b0 * N * 2, d_vout, sizeof(double) * 2 * N * nb, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(h_status + b0, d_status, sizeof(int) * nb, cudaMemcpyDeviceToHost, st);
+        if (h_iters) cudaMemcpyAsync(h_iters + (size_t)b0 * HELM_MAX_PASSES, d_iters, sizeof(int) * nb * HELM_MAX_PASSES, cudaMemcpyDeviceToHost, st);
+        if (h_nswitch) cudaMemcpyAsync(h_nswitch + b0, d_nsw, sizeof(int) * nb, cudaMemcpyDeviceToHost, st);
+        if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) { g_err = "CUDA failure in the Newton-Raphson batch"; rc = HELM_E_CUDA; }
+    }
+    cudaFree(d_scale); cudaFree(d_vout); cudaFree(d_int);
+    return rc;
 }
 
 int helm_last_state_host(helm_plan *pl, int32_t B, double *h_qg, uint8_t *h_bus_type) {

@@ -160,6 +160,17 @@ int helm_solve_batch_host(helm_plan *plan, int32_t n_scen, const double *h_scale
                           const helm_params *params, double *h_vout, int32_t *h_status,
                           int32_t *h_ncoef, int32_t *h_nswitch, helm_stats *stats);
 
+/* Newton-Raphson cross-check, batched (reference helmpy/core/nr.py:506-598 `nr`, classic slack; host
+ * restatement helmpy_b200/core/nr.py): polar NR from the flat start for n_scen load scales on the
+ * plan's LU pattern and kernels; converged when max|dP, dQ| <= mismatch; PVLIM buses that violate a
+ * Q limit after a converged pass become PQ at the limit and the iteration continues (nr.py:409-436).
+ * h_vout [n_scen*n_bus] complex (zeros unless converged), h_status HELM_ST_*, h_iters
+ * [n_scen*HELM_MAX_PASSES] Newton steps per pass PLUS ONE, 0 = pass not run (may be NULL), h_nswitch
+ * [n_scen] (may be NULL). */
+int helm_nr_batch_host(helm_plan *plan, int32_t n_scen, const double *h_scale, double mismatch,
+                       int32_t max_iterations, int32_t enforce_q_limits, double *h_vout,
+                       int32_t *h_status, int32_t *h_iters, int32_t *h_nswitch);
+
 /* Per-bus state at the end of the last helm_solve_batch_host call with the same n_scen
  * (reference run.Qg and run.Buses_type, classes.py:239, 252; needed by the result report,
  * helm.py:670-759).  h_qg [n_scen*n_bus] p.u., h_bus_type [n_scen*n_bus] HELM_BUS_*;

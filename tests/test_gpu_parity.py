@@ -412,3 +412,38 @@ def test_edge_cases_and_errors(hb):
         plan.solve_host(np.array([1.0]), _lib.Plan.make_params(1e-8, 40, True), outages=np.array([5]))
     with pytest.raises(_lib.HelmB200Error):
         plan.solve_host(np.array([1.0]), _lib.Plan.make_params(1e-8, 40, True, dsb_method=0, dsb_model=True))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', ['case9', 'case118', 'case1354pegase', 'case2869pegase'])
+def test_nr_batch_matches_host_nr_and_helm(hb, name):
+    """GPU Newton-Raphson (csrc/helm_nr.cuh) against the host restatement of the reference's NR
+    (same Newton steps per pass, same switches, voltages to 1e-9) and against HELM on the GPU
+    (NR stops on a 1e-8 power mismatch: 1e-6 p.u. / 1e-5 rad)."""
+    import contextlib, io, importlib
+    nrmod = importlib.import_module('helmpy_b200.core.nr')     # `helmpy_b200.core.nr` the attribute is the function
+    case = load_case(name)
+    scales = [1.0, 0.9, 1.04]
+    res = hb.nr_batch(case, scales, Mismatch=1e-8)
+    helm = hb.helm_batch(case, scales, mismatch=1e-8, max_coefficients=40)
+    for b, s in enumerate(scales):
+        with contextlib.redirect_stdout(io.StringIO()):
+            Vh = nrmod.nr(case, Mismatch=1e-8, Scale=float(s))
+        assert bool(res.converged[b]) == (Vh is not None)
+        if Vh is None:
+            continue
+        assert res.list_iterations(b) == nrmod.last_run['list_iterations'], (res.iterations[b], nrmod.last_run['list_iterations'])
+        dmag, dang = polar_err(res.V[b], Vh)
+        assert dmag <= 1e-9 and dang <= 1e-9, (dmag, dang)
+        if helm.converged[b]:
+            dmag, dang = polar_err(res.V[b], helm.V[b])
+            assert dmag <= 1e-6 and dang <= 1e-5, (dmag, dang)
+
+
+@pytest.mark.gpu
+def test_nr_batch_divergence_and_no_limits(hb):
+    case = load_case('case118')
+    res = hb.nr_batch(case, [1.0, 8.0], Mismatch=1e-8, MaxIterations=15)
+    assert res.converged[0] and not res.converged[1] and np.all(res.V[1] == 0)
+    free = hb.nr_batch(case, [1.0], Mismatch=1e-8, Enforce_Qlimits=False)
+    assert free.converged[0] and free.nswitch[0] == 0 and res.nswitch[0] > 0

@@ -122,6 +122,20 @@ def batch_config(num, what, names, nscen, seed, lo, hi, maxc, ncheck, nr_check=0
                 worst = (max(worst[0], e[0]), max(worst[1], e[1]))
             assert worst[0] <= 1e-6 and worst[1] <= 1e-5, worst
             res['nr_cross_check'] = {'scenarios_checked': nr_check, 'max_dmag_pu': worst[0], 'max_dang_rad': worst[1]}
+            # every scenario against the batched GPU Newton-Raphson (csrc/helm_nr.cuh)
+            import torch
+            helmpy_b200.nr_batch(case, scales[:8], Mismatch=1e-8)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            nrb = helmpy_b200.nr_batch(case, scales, Mismatch=1e-8)
+            dtn = time.perf_counter() - t0
+            both = nrb.converged & (st == 2)
+            dm = float(np.max(np.abs(np.abs(nrb.V[both]) - np.abs(V[both]))))
+            da = float(np.max(np.abs(np.angle(nrb.V[both]) - np.angle(V[both]))))
+            assert both.sum() == nscen and dm <= 1e-6 and da <= 1e-5, (int(both.sum()), dm, da)
+            res['nr_gpu_cross_check'] = {'scenarios_checked': int(both.sum()), 'max_dmag_pu': dm, 'max_dang_rad': da,
+                                         'nr_wall_s': dtn, 'nr_cases_per_s': float(nscen / dtn),
+                                         'mean_newton_steps': float(np.mean(np.maximum(nrb.iterations - 1, 0).sum(axis=1)))}
     return res
 
 
