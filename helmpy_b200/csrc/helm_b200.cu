@@ -3,14 +3,19 @@
 // (cited per kernel below).  sm_100a only; fp64 throughout; no tensor cores
 // (nothing on this path is a dense contraction).
 //
-// Data layout.  Scenarios are packed in lock-step groups of G (1..32).  Every
-// per-scenario array is stored [group][item][G], so the G scenarios of a group
-// sit in adjacent lanes and every access to a per-(item, scenario) value is a
-// contiguous run of G*16 B (values are double2 = complex or a 2-vector).  Series
-// histories are [group][order][bus][G].  LU block values are [group][slot][G]
-// with 4 doubles (one 2x2 block) per element, slots numbered in the order the
-// triangular solves consume them, so each CTA streams its group's factors front
-// to back.
+// Data layout.  Scenarios are packed in lock-step groups of G (1..32; G = 1 is the
+// default and the tuned path).  Every per-scenario array is stored [group][item][G],
+// so the G scenarios of a group sit in adjacent lanes and every access to a
+// per-(item, scenario) value is a contiguous run of G*16 B (values are double2 =
+// complex or a 2-vector).  Series histories are tiled, [group][tile of 128 buses]
+// [order][128][G] (hx()).  LU block values are [group][slot][G] with 4 doubles (one
+// 2x2 block) per element, slots numbered in the order the triangular solves consume
+// them, so a solve streams its scenario's factors front to back.
+//
+// File map: assembly + numeric LU (k_assemble, k_factor*), triangular solves
+// (k_solve<G>, k_solve_flat, k_solve_cta), per-order kernels (k_init, k_rhs_conv,
+// k_eps, k_advance, k_qlimit, k_pass_end, k_step_begin), variants (helm_variants.cuh),
+// Newton-Raphson cross-check (helm_nr.cuh), host side and the C ABI.
 #include <cuda_runtime.h>
 
 #include <algorithm>
