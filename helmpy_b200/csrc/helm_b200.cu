@@ -101,6 +101,11 @@ struct WorkDev {
     int *fact_list;                   // [MAX_SIDE_DEPTH + 1][ngroups]
     int *fact_count;                  // [MAX_SIDE_DEPTH + 1]
     int *g_fage;                      // [ngroups] steps left until a group being factorized rejoins
+    // groups that take a triangular solve in the current step, compacted by k_step_begin (same list
+    // index as fact_list): the solve launches one warp per ENTRY, so slots that are idle (being
+    // factorized, finished) do not occupy solve warps and more slots than solve warps can be resident
+    int *solve_list;                  // [MAX_SIDE_DEPTH + 1][ngroups]
+    int *solve_count;                 // [MAX_SIDE_DEPTH + 1]
     int parity;                       // list of the current step: step % (depth + 1) (host-set per launch)
     int depth;                        // steps a factorization may take (side-branch pipeline depth)
     int skip_asm;                     // k_factor_coop: the LU slots already hold the matrix (Newton-Raphson Jacobian)
@@ -776,11 +781,13 @@ __global__ void __maxnreg__(64) k_solve_flat(PlanDev p, WorkDev w, int side) {
     using Sy = helm::Symbolic;
     TL_SCOPE(w, 2);
     int grp = blockIdx.x * WPB + (threadIdx.x >> 5);
-    if (grp >= w.ngroups) return;
-    grp += w.grp_base;
-    {
-        int gfl = w.g_flags[grp];
-        if (side ? !(gfl & GF_FACTORING) : (gfl & (GF_DONE | GF_FACTORING)) != 0) return;
+    if (side) {                                              // scenarios being factorized (bordered-system / NR solves)
+        if (grp >= w.ngroups) return;
+        grp += w.grp_base;
+        if (!(w.g_flags[grp] & GF_FACTORING)) return;
+    } else {                                                 // one warp per entry of the step's solve list
+        if (grp >= w.solve_count[w.parity]) return;
+        grp = w.solve_list[(size_t)w.parity * w.ngroups + grp];
     }
     if (w.s_status[grp] != ST_ACTIVE) return;
     const int lane = threadIdx.x & 31;
@@ -1654,7 +1661,10 @@ __global__ void k_step_begin(WorkDev w) {
     int grp = blockIdx.x * blockDim.x + threadIdx.x;
     if (grp >= w.ngroups) return;
     // the list of the next step starts empty (its previous user, depth + 1 steps ago, has been joined)
-    if (grp == 0) w.fact_count[(w.parity + 1) % (w.depth + 1)] = 0;
+    if (grp == 0) {
+        w.fact_count[(w.parity + 1) % (w.depth + 1)] = 0;
+        w.solve_count[(w.parity + 1) % (w.depth + 1)] = 0;
+    }
     grp += w.grp_base;
     int gf = w.g_flags[grp];
     if (gf & GF_FACTORING) {
@@ -1668,6 +1678,10 @@ __global__ void k_step_begin(WorkDev w) {
         w.fact_list[(size_t)w.parity * w.ngroups + pos] = grp;
     }
     w.g_flags[grp] = gf;
+    if (!(gf & (GF_DONE | GF_FACTORING)) && (w.G > 1 || w.s_status[grp] == ST_ACTIVE)) {
+        int pos = atomicAdd(&w.solve_count[w.parity], 1);
+        w.solve_list[(size_t)w.parity * w.ngroups + pos] = grp;
+    }
 }
 
 // ---- shared first-pass factors: scratch control block for factorizing the base matrix once -----
@@ -1707,7 +1721,7 @@ __global__ void k_setup(PlanDev p, WorkDev w, const double *scale_in) {
         if (grp == 0) {
             *w.active_groups = w.ngroups;
             *w.queue_next = w.ngroups * G;      // slots 0..Bp-1 start with scenarios 0..Bp-1
-            for (int k = 0; k < 2 * (MAX_SIDE_DEPTH + 1); ++k) w.fact_count[k] = 0;   // both chains
+            for (int k = 0; k < 2 * (MAX_SIDE_DEPTH + 1); ++k) { w.fact_count[k] = 0; w.solve_count[k] = 0; }   // both chains
         }
     }
 }
@@ -1804,7 +1818,7 @@ WsLayout layout(const helm_plan *pl, int B, const helm_params *prm) {
     auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes); return r; };
     L.off_scale = take(sizeof(double) * L.Bp);
     L.off_sint = take(sizeof(int) * L.Bp * (8 + HELM_MAX_PASSES));
-    L.off_gint = take(sizeof(int) * ((4 + MAX_SIDE_DEPTH) * L.ngroups + 16));
+    L.off_gint = take(sizeof(int) * ((5 + 2 * MAX_SIDE_DEPTH) * L.ngroups + 32));
     L.off_btype = take(per);
     L.off_Qg = take(per * sizeof(double));
     L.off_VVant = take(per * sizeof(double));
@@ -1845,7 +1859,9 @@ WorkDev bind(const helm_plan *pl, const WsLayout &L, int B, const helm_params *p
     w.s_npass = si + 4 * L.Bp; w.s_nswitch = si + 5 * L.Bp; w.slot_scen = si + 6 * L.Bp; w.o_b = si + 7 * L.Bp; w.s_ncoef = si + 8 * L.Bp;
     int *gi = (int *)(b + L.off_gint);
     w.g_n = gi; w.g_flags = gi + L.ngroups; w.active_groups = gi + 2 * L.ngroups; w.queue_next = gi + 2 * L.ngroups + 1;
-    w.fact_count = gi + 2 * L.ngroups + 2; w.g_fage = gi + 2 * L.ngroups + 16; w.fact_list = gi + 3 * L.ngroups + 16; w.parity = 0;
+    w.fact_count = gi + 2 * L.ngroups + 2; w.solve_count = gi + 2 * L.ngroups + 16;
+    w.g_fage = gi + 2 * L.ngroups + 32; w.fact_list = gi + 3 * L.ngroups + 32;
+    w.solve_list = w.fact_list + (size_t)(MAX_SIDE_DEPTH + 1) * L.ngroups; w.parity = 0;
     w.depth = 1; w.skip_asm = 0;
     w.scale_in = nullptr; w.outage_in = nullptr; w.out_status = nullptr; w.out_ncoef = nullptr; w.out_nswitch = nullptr;
     w.btype = (unsigned char *)(b + L.off_btype);
@@ -2389,6 +2405,8 @@ int helm_solve_batch_device(helm_plan *pl, int32_t B, const double *d_scale, con
         wc[1].grp_base = nA; wc[1].ngroups = L.ngroups - nA;
         wc[1].fact_count = w.fact_count + (MAX_SIDE_DEPTH + 1);
         wc[1].fact_list = w.fact_list + (size_t)(MAX_SIDE_DEPTH + 1) * nA;
+        wc[1].solve_count = w.solve_count + (MAX_SIDE_DEPTH + 1);
+        wc[1].solve_list = w.solve_list + (size_t)(MAX_SIDE_DEPTH + 1) * nA;
     }
     const StepSeq seq = make_seq(w, L.G == 1 && p.use_coop_factor, p.split_eps != 0);
     const int STEP_LEN = 1 + seq.main_len + seq.side_len;
