@@ -447,3 +447,19 @@ def test_nr_batch_divergence_and_no_limits(hb):
     assert res.converged[0] and not res.converged[1] and np.all(res.V[1] == 0)
     free = hb.nr_batch(case, [1.0], Mismatch=1e-8, Enforce_Qlimits=False)
     assert free.converged[0] and free.nswitch[0] == 0 and res.nswitch[0] > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('kw', [dict(), dict(pv_bus_model=1), dict(DSB_model=True, DSB_model_method=2),
+                                dict(pv_bus_model=1, DSB_model=True, DSB_model_method=1)])
+def test_large_batch_kernels_agree_with_small_batch(hb, kw):
+    """More than 888 resident scenarios switch to the warp-per-scenario solve on the compacted list,
+    the side solves by flag and (default variant) the two-step factorization pipeline; a small batch
+    uses the CTA solve and a one-step pipeline.  Same passes, same voltages."""
+    case = load_case('case1354pegase')
+    scales = np.random.default_rng(5).uniform(0.9, 1.03, 1500)
+    big = hb.helm_batch(case, scales, mismatch=1e-8, max_coefficients=40, **kw)
+    small = hb.helm_batch(case, scales[:40], mismatch=1e-8, max_coefficients=40, **kw)
+    assert big.converged.all()
+    assert np.array_equal(big.status[:40], small.status) and np.array_equal(big.ncoef[:40], small.ncoef)
+    assert np.max(np.abs(big.V[:40] - small.V)) < 1e-10
