@@ -2481,6 +2481,19 @@ int helm_solve_batch_host(helm_plan *pl, int32_t B, const double *h_scale, const
     if (!pl || !h_scale || !h_vout || !h_status || B <= 0) { g_err = "null/invalid argument"; return HELM_E_ARG; }
     int rc = check_params(prm);
     if (rc) return rc;
+    helm_params prm_local = *prm;
+    if (prm_local.max_resident <= 0) {
+        // auto: 4096 resident scenarios, fewer if the workspace would not fit the free device memory
+        // (big grids / many coefficients: 40 MB per scenario at 13 656 buses and 60 coefficients)
+        prm_local.max_resident = 4096;
+        size_t free_b = 0, total_b = 0;
+        CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        free_b += pl->ws_bytes;                                  // the cached workspace is reused or replaced
+        const size_t out_b = (size_t)B * (pl->S.N * 16 + 64);    // d_vout etc. for the whole batch
+        const size_t budget = free_b > out_b ? (size_t)((free_b - out_b) * 0.9) : 0;
+        while (prm_local.max_resident > 64 && layout(pl, B, &prm_local).total > budget) prm_local.max_resident /= 2;
+    }
+    prm = &prm_local;
     WsLayout L = layout(pl, B, prm);
     if (!pl->stream) CUDA_TRY(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
     if (pl->ws_bytes < L.total) {

@@ -89,7 +89,9 @@ typedef struct helm_params {
     int32_t use_graph;          /* replay the per-order step as a CUDA graph    */
     int32_t poll_every;         /* steps between host polls of the done counter; 0 = auto */
     int32_t max_resident;       /* scenarios resident on the GPU at once (slots); the rest of the
-                                   batch queues and takes over slots as scenarios end; 0 = auto */
+                                   batch queues and takes over slots as scenarios end; 0 = auto
+                                   (4096, fewer when the workspace would not fit the free memory;
+                                   the device-pointer call sizes its workspace for 4096) */
     int32_t pv_bus_model;       /* helm(pv_bus_model=): 1 or 2; 0 = 2 (the reference default)   */
     int32_t dsb_method;         /* helm(DSB_model_method=): 0 = classic slack, 1 or 2            */
     int32_t dsb_model;          /* helm(DSB_model=): participation factors (needs dsb_method)    */
