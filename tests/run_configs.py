@@ -1,12 +1,12 @@
 """The five configurations of BASELINE.json, end to end through the public API (GPU box).
 
-    python tools/configs.py [1 2 3 4 5]                      # one GPU
-    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/configs.py 3 5
+    python tests/run_configs.py [1 2 3 4 5]                      # one GPU
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tests/run_configs.py 3 5
 
 Configs 3-5 name MATPOWER grids the reference does not ship (case2383wp, case9241pegase,
 case13659pegase): tests/synth.py builds stand-ins of the same size from the shipped grids
 (SURVEY 8d).  Every config is checked on sampled scenarios against the oracle
-(oracle/helm_oracle.py, test infrastructure) and, for config 4, against the Newton-Raphson
+(oracle/helm_oracle.py; this script lives under tests/ because only test code may use the oracle) and, for config 4, against the Newton-Raphson
 cross-check.  One JSON line per config; rank 0 appends them to gpurun_out/configs.jsonl.
 """
 import contextlib
