@@ -2342,8 +2342,8 @@ int helm_solve_batch_device(helm_plan *pl, int32_t B, const double *d_scale, con
 
     // Shared first-pass factors (default variant, staged factorization): assemble and factorize the
     // base matrix once, as pseudo-group 0 of a control block that points at the base bus types.
-    if (L.G == 1 && p.use_coop_factor && !prm->dsb_method && prm->pv_bus_model != 1 &&
-        getenv("HELM_B200_NO_SHARED_LU") == nullptr) {
+    if (L.G == 1 && p.use_coop_factor && !prm->dsb_method && prm->pv_bus_model != 1 && L.Bp >= 64 &&
+        getenv("HELM_B200_NO_SHARED_LU") == nullptr) {                 // (a handful of scenarios: not worth the extra factorization)
         int *ints = (int *)((char *)d_ws + L.off_shprep);
         WorkDev w2 = w;
         w2.lu = (double2 *)((char *)d_ws + L.off_lu_shared);
