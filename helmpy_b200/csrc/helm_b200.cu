@@ -79,7 +79,6 @@ struct PlanDev {
     const int *scm;
     const int4 *solve_chunks;
     int nschunks, use_cta_solve, cta_solve_max_groups;
-    int split_eps;
 };
 
 struct WorkDev {
@@ -1143,22 +1142,21 @@ __global__ void k_init(PlanDev p, WorkDev w) {
   }
 }
 
-// ---- K1: V/W update, epsilon-table column, Pade check, RHS of the next order ------------
-// One thread per (bus, scenario).  Replaces compute_complex_voltages (helm.py:402-420),
+// ---- K1 / K3: V and W update and the RHS of the next order (k_rhs_conv); epsilon table and Pade
+// check (k_eps).  One thread per (bus, scenario).  Replace compute_complex_voltages (helm.py:402-420),
 // calculate_inverse_voltages_w_array (423-433), the per-bus evaluators (293-398) and the
-// Pade/convergence test (608-641, analytic_continuation.py).  The Pade value is obtained
-// with Wynn's epsilon algorithm kept incrementally: each order appends one anti-diagonal
-// (the reference states the algorithm itself in analytic_continuation.py:9-26).
+// Pade/convergence test (608-641, analytic_continuation.py).  The Pade value is obtained with
+// Wynn's epsilon algorithm kept incrementally (the reference states the algorithm itself in
+// analytic_continuation.py:9-26).
 //
-// All O(j) work of one order is a single fused loop over the history index t = 1..j:
-//   PQ:  W_i[j]  = -sum_t W_i[t-1] V_i[j+1-t]
+// The O(j) work of one order is a loop over the history index t = 1..j:
+//   PQ:  W_i[j]  = -sum_t W_i[t-1] V_i[j+1-t]                  (blocked by four orders, conv_blocked_pq)
 //   PV:  PPP     =  sum_t conj(V_i[j+1-t]) CC_i[t]          (CC_i[j] = sum_k Ytrans_ik V_k[j])
 //        VV      =  sum_t V_i[t] conj(V_i[j+1-t])
-//   all: eps_t^(j-t) = eps_{t-2}^(j-t+1) + 1 / (eps_{t-1}^(j-t+1) - eps_{t-1}^(j-t))
-// The loop is blocked by KU: the loads of a block (histories are [order][bus][G], so
-// each one is a coalesced 16 B per lane) are issued together before the dependent
-// arithmetic, which is what gives the kernel its memory-level parallelism.
-constexpr int KU = 4;
+//   eps: eps_t^(j-t) = eps_{t-2}^(j-t+1) + 1 / (eps_{t-1}^(j-t+1) - eps_{t-1}^(j-t))
+// The loops are blocked: the loads of a block (one coalesced 16 B per lane each, histories are
+// tiled by 128 buses) are issued together before the dependent arithmetic, which is what gives
+// the kernels their memory-level parallelism.
 
 struct EpsState { double2 prev1, prev2, cur; };
 
@@ -1190,37 +1188,8 @@ __device__ __forceinline__ void eps2_step(Eps2State &st, int t, int j, double2 v
     st.b1 = b;
 }
 
-// O(j) loop of a PQ bus at order j: W recurrence (+ two epsilon anti-diagonals when EPS).
-template <bool EPS, int KU>
-__device__ __forceinline__ double2 conv_loop_pq(int j, double2 v, double2 vjm1, const double2 *Vb, const double2 *Hb,
-                                                double2 *Eb, size_t plane, Eps2State &es) {
-    const double2 zero = make_double2(0.0, 0.0);
-    double2 aux = zero;
-    for (int t0 = 1; t0 <= j; t0 += KU) {
-        double2 vr[KU], eo[EPS ? KU : 1], hh[KU];
-#pragma unroll
-        for (int u = 0; u < KU; ++u) {
-            int t = t0 + u;
-            if (t <= j) {
-                vr[u] = (t == 1) ? v : Vb[(size_t)(j + 1 - t) * plane];
-                if (EPS) eo[EPS ? u : 0] = (t < j - 1) ? Eb[(size_t)t * plane] : zero;
-                hh[u] = Hb[(size_t)(t - 1) * plane];                              // W[t-1]
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < KU; ++u) {
-            int t = t0 + u;
-            if (t <= j) {
-                if (EPS) eps2_step(es, t, j, vjm1, v, eo[EPS ? u : 0], Eb, plane);
-                aux = cadd(aux, cmul(hh[u], vr[u]));                              // helm.py:430-432
-            }
-        }
-    }
-    return aux;
-}
-
 // Blocked ("relaxed") form of the same convolution C[j] = sum_{a<j} W[a] V[j-a], block size 4.
-// At a block start j = T (T = 4, 8, ...) the history is walked once, as in conv_loop_pq, but next to
+// At a block start j = T (T = 4, 8, ...) the history is walked once, and next to
 // C[T] the loop also accumulates, through a three-deep window of the V just loaded, the parts of
 // C[T+1..T+3] whose operands are already known: P[T+i] = sum_{a=i..T} W[a] V[T+i-a].  The three
 // following orders read their partial and add the 2i-1 products with the operands that arrived
@@ -1285,20 +1254,17 @@ __device__ __forceinline__ double2 conv_blocked_pq(int j, double2 v, const doubl
     return acc0;
 }
 
-// O(j) loop of a PV bus (model 2) at order j: P-row convolution, |V|^2 convolution (+ epsilon).
-template <bool EPS, int KU>
-__device__ __forceinline__ void conv_loop_pv(int j, double2 v, double2 vjm1, double2 PP, const double2 *Vb,
-                                             const double2 *Hb, double2 *Eb, size_t plane, Eps2State &es,
-                                             double2 &ppp, double &vvre) {
-    const double2 zero = make_double2(0.0, 0.0);
+// O(j) loop of a PV bus (model 2) at order j: P-row convolution and |V|^2 convolution.
+template <int KU>
+__device__ __forceinline__ void conv_loop_pv(int j, double2 v, double2 PP, const double2 *Vb, const double2 *Hb,
+                                             size_t plane, double2 &ppp, double &vvre) {
     for (int t0 = 1; t0 <= j; t0 += KU) {
-        double2 vr[KU], eo[EPS ? KU : 1], hh[KU], vf[KU];
+        double2 vr[KU], hh[KU], vf[KU];
 #pragma unroll
         for (int u = 0; u < KU; ++u) {
             int t = t0 + u;
             if (t <= j) {
                 vr[u] = (t == 1) ? v : Vb[(size_t)(j + 1 - t) * plane];
-                if (EPS) eo[EPS ? u : 0] = (t < j - 1) ? Eb[(size_t)t * plane] : zero;
                 hh[u] = (t < j) ? Hb[(size_t)t * plane] : PP;                     // CC[t]
                 vf[u] = (t < j) ? Vb[(size_t)t * plane] : v;                      // V[t]
             }
@@ -1307,7 +1273,6 @@ __device__ __forceinline__ void conv_loop_pv(int j, double2 v, double2 vjm1, dou
         for (int u = 0; u < KU; ++u) {
             int t = t0 + u;
             if (t <= j) {
-                if (EPS) eps2_step(es, t, j, vjm1, v, eo[EPS ? u : 0], Eb, plane);
                 ppp = cadd(ppp, cmulc(hh[u], vr[u]));                             // helm.py:306-314
                 vvre += vf[u].x * vr[u].x + vf[u].y * vr[u].y;                    // helm.py:356-361
             }
@@ -1315,20 +1280,15 @@ __device__ __forceinline__ void conv_loop_pv(int j, double2 v, double2 vjm1, dou
     }
 }
 
-// 128-thread CTAs: a CTA is 16 K registers, so an SM that also hosts a factorization CTA of the
-// side branch loses a quarter of this kernel's occupancy instead of half (measured: timeline r1).
-#ifndef RHS_MINB
-#define RHS_MINB 4
-#endif
-// FUSED = false: the epsilon table and the Pade check run in their own kernel (k_eps); this one
-// then only carries the convolution state and runs with twice the loads in flight per thread.
+// 128-thread CTAs (= one history tile), 80 registers: six CTAs per SM.  The epsilon table and the
+// Pade check run in their own kernel (k_eps); this one only carries the convolution state.
 #ifndef CONV_MINB
 #define CONV_MINB 6
 #define CONV_KU_PQ 4
 #define CONV_KU_PV 4
 #endif
-template <int G, bool FUSED>
-__global__ void __launch_bounds__(128, FUSED ? RHS_MINB : CONV_MINB) k_rhs_conv(PlanDev p, WorkDev w) {
+template <int G>
+__global__ void __launch_bounds__(128, CONV_MINB) k_rhs_conv(PlanDev p, WorkDev w) {
     TL_SCOPE(w, 3);
     const int grp = blockIdx.y + w.grp_base;
     const int flat = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1339,7 +1299,7 @@ __global__ void __launch_bounds__(128, FUSED ? RHS_MINB : CONV_MINB) k_rhs_conv(
     const size_t plane = hplane<G>();
     const size_t bi = ix<G>(grp, N, i, s);
     const size_t h0 = hx<G>(w, N, grp, 0, i, s);
-    double2 *Vb = w.Vh + h0, *Hb = w.Hh + h0, *Eb = w.Eh + h0;
+    double2 *Vb = w.Vh + h0, *Hb = w.Hh + h0;
     const double2 *xb = w.xb + (size_t)grp * N * G;
     // Every operand of the prologue is loaded before the first branch: the addresses are valid for
     // any (bus, scenario), and issuing them together costs one memory round trip instead of six
@@ -1349,8 +1309,6 @@ __global__ void __launch_bounds__(128, FUSED ? RHS_MINB : CONV_MINB) k_rhs_conv(
     const int j = w.g_n[grp] + 1;  // order just solved
     const unsigned char bt = w.btype[bi];
     const double2 v = xb[(size_t)i * G + s];
-    const double2 e_old0 = Eb[0];
-    const double2 vjm1 = Vb[(size_t)(j - 1) * plane];       // V[j-1] (j >= 1)
     const double sc = w.scale[sg];
     const double qg = w.Qg[bi];
     const double pgi = p.pg[i], pdi = p.pd[i], qdi = p.qd[i];
@@ -1372,22 +1330,9 @@ __global__ void __launch_bounds__(128, FUSED ? RHS_MINB : CONV_MINB) k_rhs_conv(
         return;
     }
     const double2 zero = make_double2(0.0, 0.0);
-    // The epsilon table advances by two anti-diagonals at every even order (the orders at which
-    // the Pade value is needed, helm.py:611); odd orders do not touch it.
-    const bool even = FUSED && (j & 1) == 0;
-    Eps2State es;
-    es.o1 = e_old0;                                        // eps_0^(j-2) = S_{j-2}
-    es.o2 = zero;                                          // eps_{-1} = 0
-    es.a1 = cadd(e_old0, vjm1);                            // S_{j-1}
-    es.a2 = zero;
-    es.b1 = cadd(es.a1, v);                                // S_j
-    if (even) Eb[0] = es.b1;
     double2 out;
     if (bt == HELM_BUS_PQ) {
-        double2 aux;
-        if (FUSED) aux = even ? conv_loop_pq<true, KU>(j, v, vjm1, Vb, Hb, Eb, plane, es)
-                              : conv_loop_pq<false, KU>(j, v, vjm1, Vb, Hb, Eb, plane, es);
-        else aux = conv_blocked_pq<CONV_KU_PQ>(j, v, Vb, Hb, w.Pb + px<G>(N, grp, 0, i, s), plane);
+        const double2 aux = conv_blocked_pq<CONV_KU_PQ>(j, v, Vb, Hb, w.Pb + px<G>(N, grp, 0, i, s), plane);
         double2 wj = make_double2(-aux.x, -aux.y);
         Hb[(size_t)j * plane] = wj;                                               // W[j]
         // RHS of order j+1 (helm.py:367-385)
@@ -1407,12 +1352,7 @@ __global__ void __launch_bounds__(128, FUSED ? RHS_MINB : CONV_MINB) k_rhs_conv(
         Hb[(size_t)j * plane] = PP;                                               // barras_CC[i][n-1]
         double2 ppp = zero;
         double vvre = 0.0;
-        if (FUSED) {
-            if (even) conv_loop_pv<true, KU>(j, v, vjm1, PP, Vb, Hb, Eb, plane, es, ppp, vvre);
-            else conv_loop_pv<false, KU>(j, v, vjm1, PP, Vb, Hb, Eb, plane, es, ppp, vvre);
-        } else {
-            conv_loop_pv<false, CONV_KU_PV>(j, v, vjm1, PP, Vb, Hb, Eb, plane, es, ppp, vvre);
-        }
+        conv_loop_pv<CONV_KU_PV>(j, v, PP, Vb, Hb, plane, ppp, vvre);
         double cc_ = 0.0 - ppp.x;
         if (ysh.x != 0.0) {                                                      // conduc_buses
             if (j >= 2) cc_ -= ysh.x * (w.VVant[bi] + 2.0 * v.x);                // helm.py:317-318
@@ -1436,24 +1376,13 @@ __global__ void __launch_bounds__(128, FUSED ? RHS_MINB : CONV_MINB) k_rhs_conv(
         out = make_double2(cc_, -vvre * 0.5);
     }
     w.rhs[bi] = out;
-    // --- Pade value of m = j+1 terms and the convergence test (helm.py:608-641)
-    if (even) {                                            // m odd: es.b1 = [j/2 / j/2] Pade at s = 1
-        double2 cur = es.b1;
-        if (j >= 4) {                                      // helm.py:611: m > 3
-            double2 old = w.Pcur[bi];
-            double mag1 = hypot(old.x, old.y), rad1 = atan2(old.y, old.x);
-            double mag2 = hypot(cur.x, cur.y), rad2 = atan2(cur.y, cur.x);
-            bool ok = (fabs(mag1 - mag2) <= w.mismatch) && (fabs(rad1 - rad2) <= w.mismatch);  // helm.py:618
-            if (!ok) w.s_fail[sg] = 1;
-        }
-        w.Pcur[bi] = cur;
-    }
 }
 
-// ---- K3: epsilon table + Pade check on their own (even orders only) ---------------------------
+// ---- K3: epsilon table + Pade check (even orders only: the orders at which the Pade value is
+// needed, helm.py:611) -----------------------------------------------------------------------
 // Thread per (bus, scenario).  Reads the stored anti-diagonal j-2, appends the anti-diagonals j-1 and
-// j (eps2_step) and compares the new Pade value with the previous one (helm.py:608-641).  Runs
-// beside k_rhs_conv<G, false>: both only read x and the V history.
+// j (eps2_step) and compares the new Pade value with the previous one (helm.py:608-641).  Independent
+// of k_rhs_conv: both only read x and the V history.
 #ifndef EPS_MINB
 #define EPS_MINB 8
 #define EPS_KE 6
@@ -1946,8 +1875,7 @@ void launch_kernel(int which, const PlanDev &p, const WorkDev &w, cudaStream_t s
             break;
         case KI_RHS:
             if (w.pv_model == 1 || w.dsb_method) k_rhs_conv_var<<<gridBus, T_ELEM, 0, st>>>(p, w);
-            else if (p.split_eps) k_rhs_conv<G, false><<<dim3((p.N * G + 127) / 128, w.ngroups), 128, 0, st>>>(p, w);
-            else k_rhs_conv<G, true><<<dim3((p.N * G + 127) / 128, w.ngroups), 128, 0, st>>>(p, w);
+            else k_rhs_conv<G><<<dim3((p.N * G + 127) / 128, w.ngroups), 128, 0, st>>>(p, w);
             break;
         case KI_EPS: k_eps<G><<<dim3((p.N * G + 127) / 128, w.ngroups), 128, 0, st>>>(p, w); break;
         case KI_ADV: k_advance<<<gridGrp, 128, 0, st>>>(w); break;
@@ -1996,7 +1924,7 @@ struct StepSeq {
 };
 // default: main = solve, rhs_conv, advance, qlimit, pass_end; side = assemble, factor, init.
 // Variants (helm_variants.cuh) add the bordered-system kernels and the PV-model-1 fix-ups.
-StepSeq make_seq(const WorkDev &w, bool fused_asm, bool split_eps) {
+StepSeq make_seq(const WorkDev &w, bool fused_asm) {
     StepSeq q;
     const bool dsb = w.dsb_method != 0, pv1 = w.pv_model == 1;
     if (!fused_asm) q.side_seq[q.side_len++] = KI_ASM;     // k_factor_coop assembles A itself
@@ -2007,7 +1935,7 @@ StepSeq make_seq(const WorkDev &w, bool fused_asm, bool split_eps) {
     q.main_seq[q.main_len++] = KI_SOLVE;
     if (dsb) q.main_seq[q.main_len++] = KI_BP;
     if (dsb || pv1) q.main_seq[q.main_len++] = KI_VPRE;
-    if (split_eps && !dsb && !pv1) q.main_seq[q.main_len++] = KI_EPS;   // epsilon table + Pade check (k_eps)
+    if (!dsb && !pv1) q.main_seq[q.main_len++] = KI_EPS;   // epsilon table + Pade check (k_eps); the variants' kernel does both
     q.main_seq[q.main_len++] = KI_RHS;
     if (pv1) q.main_seq[q.main_len++] = KI_PV1C_MAIN;
     q.main_seq[q.main_len++] = KI_ADV;
@@ -2183,7 +2111,6 @@ int helm_plan_create(const helm_grid_host *g, helm_plan **out) {
         d.solve_chunks = (const int4 *)ct;
     }
     d.nschunks = (int)S.solve_chunks.size() / 4;
-    d.split_eps = getenv("HELM_B200_FUSED_EPS") == nullptr;
     d.max_row_blocks = S.max_row_blocks;
     d.nfchunks = (int)S.fchunk_lpr.size(); d.cap_upd = S.cap_upd; d.cap_ent = S.cap_ent; d.cap_rowblk = S.cap_rowblk;
 #undef UP
@@ -2408,7 +2335,7 @@ int helm_solve_batch_device(helm_plan *pl, int32_t B, const double *d_scale, con
         wc[1].solve_count = w.solve_count + (MAX_SIDE_DEPTH + 1);
         wc[1].solve_list = w.solve_list + (size_t)(MAX_SIDE_DEPTH + 1) * nA;
     }
-    const StepSeq seq = make_seq(w, L.G == 1 && p.use_coop_factor, p.split_eps != 0);
+    const StepSeq seq = make_seq(w, L.G == 1 && p.use_coop_factor);
     const int STEP_LEN = 1 + seq.main_len + seq.side_len;
     // `count` steps of every chain, starting at step index `first`; everything is joined back into st
     auto launch_batch = [&](long first, int count) {
