@@ -83,7 +83,6 @@ struct PlanDev {
 
 struct WorkDev {
     int B, G, ngroups, K;  // B = scenarios in the queue; K = history planes = max_coef + 1
-    int grp_base;          // first slot group of this launch: ngroups counts from here (a *chain*, see launch_chains)
     double mismatch;
     int max_coef, enforce_q;
     double *scale;                    // [Bp]
@@ -782,7 +781,6 @@ __global__ void __maxnreg__(64) k_solve_flat(PlanDev p, WorkDev w, int side) {
     int grp = blockIdx.x * WPB + (threadIdx.x >> 5);
     if (side) {                                              // scenarios being factorized (bordered-system / NR solves)
         if (grp >= w.ngroups) return;
-        grp += w.grp_base;
         if (!(w.g_flags[grp] & GF_FACTORING)) return;
     } else {                                                 // one warp per entry of the step's solve list
         if (grp >= w.solve_count[w.parity]) return;
@@ -983,7 +981,7 @@ __global__ void __launch_bounds__(CS_T) k_solve_cta(PlanDev p, WorkDev w, int si
     using Sy = helm::Symbolic;
     TL_SCOPE(w, 2);
     extern __shared__ __align__(128) unsigned char smem_c[];
-    const int grp = blockIdx.x + w.grp_base;                 // G = 1: one scenario per CTA
+    const int grp = blockIdx.x;                              // G = 1: one scenario per CTA
     {
         int gfl = w.g_flags[grp];
         if (side ? !(gfl & GF_FACTORING) : (gfl & (GF_DONE | GF_FACTORING)) != 0) return;
@@ -1290,7 +1288,7 @@ __device__ __forceinline__ void conv_loop_pv(int j, double2 v, double2 PP, const
 template <int G>
 __global__ void __launch_bounds__(128, CONV_MINB) k_rhs_conv(PlanDev p, WorkDev w) {
     TL_SCOPE(w, 3);
-    const int grp = blockIdx.y + w.grp_base;
+    const int grp = blockIdx.y;
     const int flat = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = flat / G, s = flat % G;
     if (i >= p.N) return;
@@ -1391,7 +1389,7 @@ constexpr int KE = EPS_KE;
 template <int G>
 __global__ void __launch_bounds__(128, EPS_MINB) k_eps(PlanDev p, WorkDev w) {
     TL_SCOPE(w, 3);
-    const int grp = blockIdx.y + w.grp_base;
+    const int grp = blockIdx.y;
     const int gf = w.g_flags[grp];
     const int j = w.g_n[grp] + 1;                          // order just solved
     if ((j & 1) || (gf & (GF_DONE | GF_PASSEND | GF_FACTORING))) return;   // uniform per CTA (G scenarios share j)
@@ -1446,7 +1444,6 @@ __global__ void k_advance(WorkDev w) {
     TL_SCOPE(w, 4);
     int grp = blockIdx.x * blockDim.x + threadIdx.x;
     if (grp >= w.ngroups) return;
-    grp += w.grp_base;
     int gf = w.g_flags[grp];
     if (gf & (GF_DONE | GF_PASSEND | GF_FACTORING)) return;
     int j = w.g_n[grp] + 1, m = j + 1;
@@ -1475,7 +1472,7 @@ __global__ void k_advance(WorkDev w) {
 template <int G>
 __global__ void k_qlimit(PlanDev p, WorkDev w) {
     TL_SCOPE(w, 5);
-    int grp = blockIdx.y + w.grp_base;
+    int grp = blockIdx.y;
     if (!(w.g_flags[grp] & GF_PASSEND)) return;
     int flat = blockIdx.x * blockDim.x + threadIdx.x;
     int i = flat / G, s = flat % G;
@@ -1513,7 +1510,6 @@ __global__ void k_pass_end(WorkDev w) {
     TL_SCOPE(w, 6);
     int grp = blockIdx.x * blockDim.x + threadIdx.x;
     if (grp >= w.ngroups) return;
-    grp += w.grp_base;
     int gf = w.g_flags[grp];
     if (!(gf & GF_PASSEND)) return;
     int any = 0;
@@ -1594,7 +1590,6 @@ __global__ void k_step_begin(WorkDev w) {
         w.fact_count[(w.parity + 1) % (w.depth + 1)] = 0;
         w.solve_count[(w.parity + 1) % (w.depth + 1)] = 0;
     }
-    grp += w.grp_base;
     int gf = w.g_flags[grp];
     if (gf & GF_FACTORING) {
         int age = w.g_fage[grp] - 1;
@@ -1650,7 +1645,7 @@ __global__ void k_setup(PlanDev p, WorkDev w, const double *scale_in) {
         if (grp == 0) {
             *w.active_groups = w.ngroups;
             *w.queue_next = w.ngroups * G;      // slots 0..Bp-1 start with scenarios 0..Bp-1
-            for (int k = 0; k < 2 * (MAX_SIDE_DEPTH + 1); ++k) { w.fact_count[k] = 0; w.solve_count[k] = 0; }   // both chains
+            for (int k = 0; k <= MAX_SIDE_DEPTH; ++k) { w.fact_count[k] = 0; w.solve_count[k] = 0; }
         }
     }
 }
@@ -1692,11 +1687,8 @@ struct helm_plan {
     double *h_vout_pinned = nullptr;
     size_t h_vout_bytes = 0;
     cudaStream_t stream = nullptr;
-    // per chain (see helm_solve_batch_device): side streams and fork/join events; chain 1 has its own main stream
-    cudaStream_t side[2][MAX_SIDE_DEPTH] = {};
-    cudaEvent_t ev_fork[2] = {}, ev_join[2][MAX_SIDE_DEPTH] = {};
-    cudaStream_t chain_stream = nullptr;
-    cudaEvent_t ev_chain_fork = nullptr, ev_chain_shift = nullptr, ev_chain_join = nullptr;
+    cudaStream_t side[MAX_SIDE_DEPTH] = {};          // side branches of consecutive steps (factorization pipeline)
+    cudaEvent_t ev_fork = nullptr, ev_join[MAX_SIDE_DEPTH] = {};
     unsigned long long *tl = nullptr;
     int *d_outage = nullptr;      // pending N-1 list for the next solve (helm_plan_set_outages)
     int outage_n = 0;
@@ -1780,7 +1772,7 @@ WsLayout layout(const helm_plan *pl, int B, const helm_params *prm) {
 WorkDev bind(const helm_plan *pl, const WsLayout &L, int B, const helm_params *prm, void *ws, double *vout) {
     WorkDev w;
     char *b = (char *)ws;
-    w.B = B; w.G = L.G; w.ngroups = L.ngroups; w.K = L.K; w.grp_base = 0;
+    w.B = B; w.G = L.G; w.ngroups = L.ngroups; w.K = L.K;
     w.mismatch = prm->mismatch; w.max_coef = prm->max_coefficients; w.enforce_q = prm->enforce_q_limits;
     w.scale = (double *)(b + L.off_scale);
     int *si = (int *)(b + L.off_sint);
@@ -1954,7 +1946,7 @@ struct StepCtx {
 };
 
 void launch_step(int G, const PlanDev &p, const WorkDev &w_in, const StepCtx &c, const StepSeq &q, long step,
-                 bool last_of_batch, cudaEvent_t after_solve = nullptr) {
+                 bool last_of_batch) {
     WorkDev w = w_in;
     const int D = c.depth;
     w.parity = (int)(step % (D + 1));
@@ -1973,10 +1965,7 @@ void launch_step(int G, const PlanDev &p, const WorkDev &w_in, const StepCtx &c,
     cudaStreamWaitEvent(c.side[sl], c.fork, 0);
     for (int k = 0; k < q.side_len; ++k) launch_any(G, q.side_seq[k], p, w, c.side[sl]);
     cudaEventRecord(c.join[sl], c.side[sl]);
-    for (int k = 0; k < q.main_len; ++k) {
-        launch_any(G, q.main_seq[k], p, w, c.st);
-        if (k == 0 && after_solve) cudaEventRecord(after_solve, c.st);
-    }
+    for (int k = 0; k < q.main_len; ++k) launch_any(G, q.main_seq[k], p, w, c.st);
     if (last_of_batch) {             // end of a graph / of a polled batch of steps: join everything
         for (long k = std::max(0L, step - (D - 1)); k <= step; ++k) cudaStreamWaitEvent(c.st, c.join[k % D], 0);
     } else if (step - (D - 1) >= 0) {
@@ -2159,17 +2148,11 @@ void helm_plan_destroy(helm_plan *pl) {
     if (pl->h_vout_pinned) cudaFreeHost(pl->h_vout_pinned);
     if (pl->d_outage) cudaFree(pl->d_outage);
     if (pl->stream) cudaStreamDestroy(pl->stream);
-    for (int c = 0; c < 2; ++c) {
-        for (int k = 0; k < MAX_SIDE_DEPTH; ++k) {
-            if (pl->side[c][k]) cudaStreamDestroy(pl->side[c][k]);
-            if (pl->ev_join[c][k]) cudaEventDestroy(pl->ev_join[c][k]);
-        }
-        if (pl->ev_fork[c]) cudaEventDestroy(pl->ev_fork[c]);
+    for (int k = 0; k < MAX_SIDE_DEPTH; ++k) {
+        if (pl->side[k]) cudaStreamDestroy(pl->side[k]);
+        if (pl->ev_join[k]) cudaEventDestroy(pl->ev_join[k]);
     }
-    if (pl->chain_stream) cudaStreamDestroy(pl->chain_stream);
-    if (pl->ev_chain_fork) cudaEventDestroy(pl->ev_chain_fork);
-    if (pl->ev_chain_shift) cudaEventDestroy(pl->ev_chain_shift);
-    if (pl->ev_chain_join) cudaEventDestroy(pl->ev_chain_join);
+    if (pl->ev_fork) cudaEventDestroy(pl->ev_fork);
     delete pl;
 }
 
@@ -2290,69 +2273,24 @@ int helm_solve_batch_device(helm_plan *pl, int32_t B, const double *d_scale, con
     memset(&local, 0, sizeof(local));
     local.kernel_launches = 1;
 
-    if (!pl->side[0][0]) {
+    if (!pl->side[0]) {
         // The side branch has few, long-running CTAs: with the higher priority they take a free slot
         // before the next CTA of the (much larger) main-branch grids does.  HELM_B200_SIDE_PRIO=0: A/B.
         int lo = 0, hi = 0;
         CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         const char *sp = getenv("HELM_B200_SIDE_PRIO");
-        for (int c = 0; c < 2; ++c) {
-            for (int k = 0; k < MAX_SIDE_DEPTH; ++k) {
-                CUDA_TRY(cudaStreamCreateWithPriority(&pl->side[c][k], cudaStreamNonBlocking, (sp && atoi(sp) == 0) ? lo : hi));
-                CUDA_TRY(cudaEventCreateWithFlags(&pl->ev_join[c][k], cudaEventDisableTiming));
-            }
-            CUDA_TRY(cudaEventCreateWithFlags(&pl->ev_fork[c], cudaEventDisableTiming));
+        for (int k = 0; k < MAX_SIDE_DEPTH; ++k) {
+            CUDA_TRY(cudaStreamCreateWithPriority(&pl->side[k], cudaStreamNonBlocking, (sp && atoi(sp) == 0) ? lo : hi));
+            CUDA_TRY(cudaEventCreateWithFlags(&pl->ev_join[k], cudaEventDisableTiming));
         }
-        CUDA_TRY(cudaStreamCreateWithFlags(&pl->chain_stream, cudaStreamNonBlocking));
-        CUDA_TRY(cudaEventCreateWithFlags(&pl->ev_chain_fork, cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&pl->ev_chain_shift, cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&pl->ev_chain_join, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming));
     }
-    // Two chains.  The solve is bound by dependent-instruction latency and leaves the memory system
-    // idle, k_eps / k_rhs_conv are bound by HBM and leave the issue slots idle.  With many resident
-    // scenarios the slot groups are split into two halves that run the same step machine on two
-    // streams, the second half a solve behind the first, so that one half's solve overlaps the
-    // other half's convolutions.  Each chain has its own factorization lists and side streams; the
-    // scenario queue and the active counter are shared (atomics).
-    const bool variants = prm->dsb_method || prm->pv_bus_model == 1;
-    // Measured (profiles/README.md): no gain on B200 — the block scheduler does not co-schedule the
-    // two halves the way the model assumes (15.1 k cases/s with one chain, 14.8 k with two) — so one
-    // chain is the default and HELM_B200_CHAINS=2 switches the second one on for experiments.
-    int nch = (L.G == 1 && !variants && !profile && L.ngroups >= 2048 && getenv("HELM_B200_CHAINS") &&
-               atoi(getenv("HELM_B200_CHAINS")) == 2) ? 2 : 1;
-#ifdef HELM_TIMELINE
-    nch = 1;
-#endif
-    WorkDev wc[2] = {w, w};
-    StepCtx ctx[2] = {StepCtx{st, pl->side[0], pl->ev_fork[0], pl->ev_join[0], depth},
-                      StepCtx{pl->chain_stream, pl->side[1], pl->ev_fork[1], pl->ev_join[1], depth}};
-    if (nch == 2) {
-        const int nA = L.ngroups / 2;
-        wc[0].ngroups = nA;
-        wc[1].grp_base = nA; wc[1].ngroups = L.ngroups - nA;
-        wc[1].fact_count = w.fact_count + (MAX_SIDE_DEPTH + 1);
-        wc[1].fact_list = w.fact_list + (size_t)(MAX_SIDE_DEPTH + 1) * nA;
-        wc[1].solve_count = w.solve_count + (MAX_SIDE_DEPTH + 1);
-        wc[1].solve_list = w.solve_list + (size_t)(MAX_SIDE_DEPTH + 1) * nA;
-    }
+    const StepCtx ctx{st, pl->side, pl->ev_fork, pl->ev_join, depth};
     const StepSeq seq = make_seq(w, L.G == 1 && p.use_coop_factor);
     const int STEP_LEN = 1 + seq.main_len + seq.side_len;
-    // `count` steps of every chain, starting at step index `first`; everything is joined back into st
+    // `count` steps starting at step index `first`; every side branch is joined back into st
     auto launch_batch = [&](long first, int count) {
-        if (nch == 2) {
-            cudaEventRecord(pl->ev_chain_fork, st);
-            cudaStreamWaitEvent(pl->chain_stream, pl->ev_chain_fork, 0);
-        }
-        for (int rep = 0; rep < count; ++rep)
-            launch_step(L.G, p, wc[0], ctx[0], seq, first + rep, rep == count - 1,
-                        (nch == 2 && rep == 0) ? pl->ev_chain_shift : nullptr);
-        if (nch == 2) {
-            cudaStreamWaitEvent(pl->chain_stream, pl->ev_chain_shift, 0);    // one solve behind chain 0
-            for (int rep = 0; rep < count; ++rep)
-                launch_step(L.G, p, wc[1], ctx[1], seq, first + rep, rep == count - 1);
-            cudaEventRecord(pl->ev_chain_join, pl->chain_stream);
-            cudaStreamWaitEvent(st, pl->ev_chain_join, 0);
-        }
+        for (int rep = 0; rep < count; ++rep) launch_step(L.G, p, w, ctx, seq, first + rep, rep == count - 1);
     };
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t gexec = nullptr;
@@ -2379,7 +2317,7 @@ int helm_solve_batch_device(helm_plan *pl, int32_t B, const double *d_scale, con
         } else {
             launch_batch(steps, poll_every);
         }
-        local.kernel_launches += (int64_t)poll_every * STEP_LEN * nch;
+        local.kernel_launches += (int64_t)poll_every * STEP_LEN;
         steps += poll_every;
         CUDA_TRY(cudaMemcpyAsync(pl->h_pinned, w.active_groups, sizeof(int), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
