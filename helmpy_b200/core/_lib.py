@@ -62,7 +62,7 @@ KERNEL_NAMES = ("assemble", "factor", "solve", "rhs_conv", "advance", "qlimit", 
 EXPORTED_SYMBOLS = (
     "helm_last_error", "helm_plan_create", "helm_plan_destroy", "helm_plan_get_info",
     "helm_plan_get_perm", "helm_plan_set_outages", "helm_workspace_bytes", "helm_solve_batch_device",
-    "helm_solve_batch_host", "helm_nr_batch_host", "helm_last_state_host", "helm_last_ploss_host", "helm_debug_factor_solve", "helm_debug_timeline", "helm_measure_peaks",
+    "helm_solve_batch_host", "helm_nr_batch_host", "helm_last_state_host", "helm_last_ploss_host", "helm_debug_factor_solve", "helm_debug_timeline", "helm_measure_peaks", "helm_measure_latencies",
     "helm_symbolic_create", "helm_symbolic_destroy", "helm_symbolic_array",
 )
 
@@ -107,6 +107,7 @@ def load():
                                             C.c_void_p, C.c_void_p]
     lib.helm_debug_timeline.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
     lib.helm_measure_peaks.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.helm_measure_latencies.argtypes = [C.c_void_p]
     lib.helm_symbolic_create.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.POINTER(C.c_void_p)]
     lib.helm_symbolic_destroy.argtypes = [C.c_void_p]
@@ -333,3 +334,10 @@ def measure_peaks():
     a, b = C.c_double(), C.c_double()
     check(load().helm_measure_peaks(C.byref(a), C.byref(b)), "helm_measure_peaks")
     return {"dfma_tflops": a.value, "copy_gbs": b.value}
+
+
+def measure_latencies():
+    """Dependent-operation latencies (cycles): DADD, DFMA, fp64 shuffle + add, LDS, L2-hit load."""
+    out = np.zeros(5)
+    check(load().helm_measure_latencies(_ptr(out)), "helm_measure_latencies")
+    return dict(zip(("dadd", "dfma", "shfl_dadd", "lds", "l2_load"), out.tolist()))

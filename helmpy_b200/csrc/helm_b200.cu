@@ -1660,6 +1660,39 @@ __global__ void k_dfma_peak(double *out, int iters) {
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
+// dependent-latency probe (one warp): cycles per dependent DADD, DFMA, fp64 shuffle+add round,
+// shared-memory load, and L2-hit global load — the building blocks of one level of a triangular solve
+__global__ void k_latency_probe(double *out, const int *chase, int n_chase) {
+    __shared__ int sm_chase[1024];
+    const int lane = threadIdx.x;
+    for (int i = lane; i < 1024; i += 32) sm_chase[i] = (i + 33) & 1023;
+    __syncwarp();
+    const int R = 256;
+    double a = 1.0 + lane * 1e-9, b = 1.0000001;
+    long long t0 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < R; ++i) a = a + b;
+    long long t1 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < R; ++i) a = fma(a, b, b);
+    long long t2 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < R; ++i) a += __shfl_down_sync(0xFFFFFFFFu, a, 1);
+    long long t3 = clock64();
+    int idx = lane;
+#pragma unroll 16
+    for (int i = 0; i < R; ++i) idx = sm_chase[idx];
+    long long t4 = clock64();
+    int g = lane;
+    for (int i = 0; i < R; ++i) g = __ldcg(chase + g);          // L2 (chase array is small and was just written)
+    long long t5 = clock64();
+    if (lane == 0) {
+        out[0] = double(t1 - t0) / R; out[1] = double(t2 - t1) / R; out[2] = double(t3 - t2) / R;
+        out[3] = double(t4 - t3) / R; out[4] = double(t5 - t4) / R;
+        out[5] = a + idx + g;                                   // keep the chains alive
+    }
+    (void)n_chase;
+}
 __global__ void k_copy(const double2 *__restrict__ a, double2 *__restrict__ b, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -2570,6 +2603,25 @@ int helm_debug_timeline(helm_plan *pl, uint64_t *out, int32_t max_steps) {
     g_err = "library built without -DHELM_TIMELINE";
     return HELM_E_ARG;
 #endif
+}
+
+int helm_measure_latencies(double *out5) {
+    if (!out5) { g_err = "null argument"; return HELM_E_ARG; }
+    double *d_out = nullptr;
+    int *d_chase = nullptr;
+    const int n = 1 << 14;
+    std::vector<int> h(n);
+    for (int i = 0; i < n; ++i) h[i] = (i + 4099) % n;        // stride of ~16 KB: different lines, L2-resident
+    CUDA_TRY(cudaMalloc((void **)&d_out, 8 * sizeof(double)));
+    CUDA_TRY(cudaMalloc((void **)&d_chase, n * sizeof(int)));
+    CUDA_TRY(cudaMemcpy(d_chase, h.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+    for (int rep = 0; rep < 2; ++rep) k_latency_probe<<<1, 32>>>(d_out, d_chase, n);
+    CUDA_TRY(cudaDeviceSynchronize());
+    double r[6];
+    CUDA_TRY(cudaMemcpy(r, d_out, sizeof(r), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 5; ++i) out5[i] = r[i];
+    cudaFree(d_out); cudaFree(d_chase);
+    return HELM_OK;
 }
 
 int helm_measure_peaks(double *dfma_tflops, double *copy_gbs) {

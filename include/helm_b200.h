@@ -207,6 +207,9 @@ int helm_symbolic_array(const helm_symbolic *sym, const char *name, const int32_
 
 /* measured fp64 FMA throughput microbenchmark (TFLOP/s) and copy bandwidth (GB/s) */
 int helm_measure_peaks(double *dfma_tflops, double *copy_gbs);
+/* Dependent-operation latencies in cycles, one warp alone: out5 = {DADD, DFMA, fp64 shuffle + add,
+ * shared-memory load, L2-hit global load} — what one level of a triangular solve is made of. */
+int helm_measure_latencies(double *out5);
 
 #ifdef __cplusplus
 }
