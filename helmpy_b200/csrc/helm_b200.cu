@@ -947,6 +947,38 @@ __device__ __forceinline__ void cta_thin_run(const int2 *swave, const double2 *s
         const CtaOps o = nx;
         if (k + 1 < e) cta_load_ops(nx, swave, slu, stab, slot0, tab0, k + 1, lane);
         if (k > a) __syncwarp();                             // x of the previous level is in shared memory
+        if (o.info & Sy::WAVE_ONEROW) {
+            // the whole wave is one row piece (the dense chain near the root): plain butterfly, no
+            // segment logic; lane 0 is the head (and holds the pivot block in the backward solve).
+            // A row longer than a wave hands its partial sum (and pivot) on through carry_s, like the
+            // general path, so the two paths can follow each other on the pieces of one row.
+            const int hmeta = __shfl_sync(0xFFFFFFFFu, o.meta, 0);
+            const int row = hmeta >> 9;
+            const bool rs = (hmeta & Sy::META_ROWSTART) != 0, re = (hmeta & Sy::META_ROWEND) != 0;
+            const bool isu = (o.info & Sy::WAVE_ISU) != 0;
+            double2 xg = zero;
+            if (!(o.meta & Sy::META_DIAG)) xg = xs[o.col];
+            const double2 b = rs ? xs[row] : carry_s[0];     // broadcast loads
+            double2 v = make_double2(o.m0.x * xg.x + o.m0.y * xg.y, o.m1.x * xg.x + o.m1.y * xg.y);
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) {
+                v.x += __shfl_xor_sync(0xFFFFFFFFu, v.x, s);
+                v.y += __shfl_xor_sync(0xFFFFFFFFu, v.y, s);
+            }
+            const double2 acc = make_double2(b.x - v.x, b.y - v.y);
+            if (re) {
+                double2 out = acc;
+                if (isu) {
+                    const double2 d0 = rs ? o.m0 : carry_s[1], d1 = rs ? o.m1 : carry_s[2];   // lane 0: the row's inverted pivot
+                    out = make_double2(d0.x * acc.x + d0.y * acc.y, d1.x * acc.x + d1.y * acc.y);
+                }
+                if (lane == 0) xs[row] = out;
+            } else if (lane == 0) {
+                carry_s[0] = acc;
+                if (isu && rs) { carry_s[1] = o.m0; carry_s[2] = o.m1; }
+            }
+            continue;
+        }
         const int meta = o.meta, info = o.info;
         double2 xg = zero, b = zero;
         if (!(meta & Sy::META_DIAG)) xg = xs[o.col];

@@ -405,6 +405,10 @@ bool build_symbolic(int N, const int32_t *adj_ptr, const int32_t *adj_idx, const
                 bool sync_k = (S.wave_tab[2 * k + 1] & Symbolic::WAVE_SYNC) != 0;
                 bool sync_next = (k + 1 >= nwv) || (S.wave_tab[2 * (k + 1) + 1] & Symbolic::WAVE_SYNC) != 0;
                 if (sync_k && sync_next) S.wave_tab[2 * k + 1] |= Symbolic::WAVE_THIN;
+                // one row piece: the first lane is its head and spans the whole wave
+                const int e0 = S.wave_tab[2 * k], n = S.wave_tab[2 * k + 1] & 63;
+                if ((S.smeta[e0] & Symbolic::META_HEAD) && (S.smeta[e0] & 31) == n - 1)
+                    S.wave_tab[2 * k + 1] |= Symbolic::WAVE_ONEROW;
             }
             int wv = 0;
             while (wv < nwv) {

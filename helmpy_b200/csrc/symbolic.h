@@ -50,6 +50,7 @@ struct Symbolic {
     int n_rows_nol = 0;                          // rows [0, n_rows_nol) have no L entries (forward level 0)
     static constexpr int WAVE_SYNC = 64, WAVE_CONT = 128, WAVE_ISU = 256;          // n in bits 0-5, maxspan in bits 9-13
     static constexpr int WAVE_THIN = 1 << 14;    // the wave is a whole level by itself (ordered before and after)
+    static constexpr int WAVE_ONEROW = 1 << 15;  // all blocks of the wave belong to one row (one piece of it)
     static constexpr int META_HEAD = 32, META_ROWSTART = 64, META_ROWEND = 128, META_DIAG = 256;  // span in bits 0-4
 
     inline int slotD(int q) const { return nL + uptr[q] + q; }
