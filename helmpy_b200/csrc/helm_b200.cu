@@ -104,6 +104,10 @@ struct WorkDev {
     // factorized, finished) do not occupy solve warps and more slots than solve warps can be resident
     int *solve_list;                  // [MAX_SIDE_DEPTH + 1][ngroups]
     int *solve_count;                 // [MAX_SIDE_DEPTH + 1]
+    // groups whose pass ended in this step (k_advance -> k_qlimit): list in the tail of solve_list's
+    // current index is not free, so it has its own array
+    int *pend_list;                   // [ngroups]
+    int *pend_count;                  // [1], reset by k_step_begin
     int parity;                       // list of the current step: step % (depth + 1) (host-set per launch)
     int depth;                        // steps a factorization may take (side-branch pipeline depth)
     int skip_asm;                     // k_factor_coop: the LU slots already hold the matrix (Newton-Raphson Jacobian)
@@ -1496,7 +1500,10 @@ __global__ void k_advance(WorkDev w) {
         w.s_fail[sg] = 0;
     }
     w.g_n[grp] = j;
-    if (nact == 0) gf |= GF_PASSEND;
+    if (nact == 0) {
+        gf |= GF_PASSEND;
+        w.pend_list[atomicAdd(w.pend_count, 1)] = grp;      // k_qlimit works on this list
+    }
     w.g_flags[grp] = gf;
 }
 
@@ -1504,20 +1511,21 @@ __global__ void k_advance(WorkDev w) {
 template <int G>
 __global__ void k_qlimit(PlanDev p, WorkDev w) {
     TL_SCOPE(w, 5);
-    int grp = blockIdx.y;
-    if (!(w.g_flags[grp] & GF_PASSEND)) return;
+    const int npend = *w.pend_count;
     int flat = blockIdx.x * blockDim.x + threadIdx.x;
     int i = flat / G, s = flat % G;
     if (i >= p.N) return;
+  for (int pi = blockIdx.y; pi < npend; pi += gridDim.y) {
+    const int grp = w.pend_list[pi];
     int sg = grp * G + s;
-    if (w.s_status[sg] != ST_FROZEN) return;
+    if (w.s_status[sg] != ST_FROZEN) continue;
     const int N = p.N;
     size_t bi = ix<G>(grp, N, i, s);
     double2 vi = w.Pcur[bi];
     const int scen = w.slot_scen[sg];
     if (scen >= 0) w.vout[(size_t)scen * N + p.perm[i]] = vi;
-    if (!w.enforce_q) return;
-    if (w.btype[bi] != HELM_BUS_PV) return;
+    if (!w.enforce_q) continue;
+    if (w.btype[bi] != HELM_BUS_PV) continue;
     const double2 *pc = w.Pcur + (size_t)grp * N * G;
     const OutageRef og = load_outage(p, w, sg);
     double q = 0.0;
@@ -1535,6 +1543,7 @@ __global__ void k_qlimit(PlanDev p, WorkDev w) {
         atomicAdd(&w.s_nswitch[sg], 1);
     }
     w.Qg[bi] = lim;
+  }
 }
 
 // ---- K_pend: pass bookkeeping (helm.py:936-955, 644-653) ----------------------------------
@@ -1621,6 +1630,7 @@ __global__ void k_step_begin(WorkDev w) {
     if (grp == 0) {
         w.fact_count[(w.parity + 1) % (w.depth + 1)] = 0;
         w.solve_count[(w.parity + 1) % (w.depth + 1)] = 0;
+        *w.pend_count = 0;
     }
     int gf = w.g_flags[grp];
     if (gf & GF_FACTORING) {
@@ -1804,7 +1814,7 @@ WsLayout layout(const helm_plan *pl, int B, const helm_params *prm) {
     auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes); return r; };
     L.off_scale = take(sizeof(double) * L.Bp);
     L.off_sint = take(sizeof(int) * L.Bp * (8 + HELM_MAX_PASSES));
-    L.off_gint = take(sizeof(int) * ((5 + 2 * MAX_SIDE_DEPTH) * L.ngroups + 32));
+    L.off_gint = take(sizeof(int) * ((6 + 2 * MAX_SIDE_DEPTH) * L.ngroups + 32));
     L.off_btype = take(per);
     L.off_Qg = take(per * sizeof(double));
     L.off_VVant = take(per * sizeof(double));
@@ -1847,7 +1857,8 @@ WorkDev bind(const helm_plan *pl, const WsLayout &L, int B, const helm_params *p
     w.g_n = gi; w.g_flags = gi + L.ngroups; w.active_groups = gi + 2 * L.ngroups; w.queue_next = gi + 2 * L.ngroups + 1;
     w.fact_count = gi + 2 * L.ngroups + 2; w.solve_count = gi + 2 * L.ngroups + 16;
     w.g_fage = gi + 2 * L.ngroups + 32; w.fact_list = gi + 3 * L.ngroups + 32;
-    w.solve_list = w.fact_list + (size_t)(MAX_SIDE_DEPTH + 1) * L.ngroups; w.parity = 0;
+    w.solve_list = w.fact_list + (size_t)(MAX_SIDE_DEPTH + 1) * L.ngroups;
+    w.pend_list = w.solve_list + (size_t)(MAX_SIDE_DEPTH + 1) * L.ngroups; w.pend_count = gi + 2 * L.ngroups + 24; w.parity = 0;
     w.depth = 1; w.skip_asm = 0;
     w.scale_in = nullptr; w.outage_in = nullptr; w.out_status = nullptr; w.out_ncoef = nullptr; w.out_nswitch = nullptr;
     w.btype = (unsigned char *)(b + L.off_btype);
@@ -1936,7 +1947,7 @@ void launch_kernel(int which, const PlanDev &p, const WorkDev &w, cudaStream_t s
             break;
         case KI_EPS: k_eps<G><<<dim3((p.N * G + 127) / 128, w.ngroups), 128, 0, st>>>(p, w); break;
         case KI_ADV: k_advance<<<gridGrp, 128, 0, st>>>(w); break;
-        case KI_QLIM: k_qlimit<G><<<gridBus, T_ELEM, 0, st>>>(p, w); break;
+        case KI_QLIM: k_qlimit<G><<<dim3(gridBus.x, std::min(w.ngroups, 512)), T_ELEM, 0, st>>>(p, w); break;
         case KI_PEND: k_pass_end<<<gridGrp, 128, 0, st>>>(w); break;
     }
 }
