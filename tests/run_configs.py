@@ -103,7 +103,7 @@ def batch_config(num, what, names, nscen, seed, lo, hi, maxc, ncheck, nr_check=0
     case = synth.tiled_case(names)
     scales = np.random.default_rng(seed).uniform(lo, hi, nscen)
     kw = dict(mismatch=1e-8, max_coefficients=maxc)
-    solve(case, scales[:min(nscen, 64 * WORLD)], **kw)            # warm-up: plan, workspace
+    solve(case, scales, **kw)                                     # warm-up: plan, workspace, page-locked result block
     V, st, nc, ns, dt = solve(case, scales, **kw)
     res = {'config': num, 'what': what, 'grid': 'synthetic: ' + '+'.join(names), 'n_bus': int(case.N), 'scenarios': nscen,
            'n_gpus': WORLD, 'converged': int((st == 2).sum()), 'wall_s': dt, 'cases_per_s': float((st == 2).sum() / dt),
@@ -158,7 +158,7 @@ def config5():
     outages = safe if not nmax else safe[:nmax]
     scales = np.ones(len(outages))
     kw = dict(mismatch=1e-8, max_coefficients=60)
-    solve(case, scales[:64 * WORLD], outages=outages[:64 * WORLD], **kw)
+    solve(case, scales, outages=outages, **kw)                    # warm-up
     V, st, nc, ns, dt = solve(case, scales, outages=outages, **kw)
     res = {'config': 5, 'what': 'case13659pegase-size N-1 branch-outage sweep (per-scenario numeric refactorization)',
            'grid': 'synthetic: ' + '+'.join(names), 'n_bus': int(case.N), 'branches': int(case.N_branches),
