@@ -314,3 +314,28 @@ def test_matpower_reader(name, tmp_path):
     matpower_to_xlsx(m, x)
     c3 = create_case_data_object_from_xlsx(x)
     assert np.array_equal(c3.Ytrans_val, ref.Ytrans_val) and np.array_equal(c3.Pd, ref.Pd)
+
+
+def test_bench_roofline_bytes_match_the_per_order_table():
+    """bench.roofline_model's closed forms equal a brute-force walk over every order of every pass with
+    the per-bus byte counts of DESIGN.md section 5."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('bench', os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    N, n_pv, nslots = 1000, 150, 6000
+    ncoef = np.array([[23, 25, 29, 0], [17, 0, 0, 0], [5, 7, 0, 0]], dtype=np.int32)
+    stats = {'ms_kernel': {'solve': 1.0, 'rhs_conv': 1.0, 'eps': 1.0, 'factor': 1.0}, 'steps': 10}
+    k = bench.roofline_model({'n_slots': nslots, 'n_pv': n_pv}, ncoef, stats, N)
+    solve = conv = eps = fac = 0.0
+    for m in ncoef[ncoef > 0]:
+        fac += (64 + 32) * nslots
+        for j in range(1, int(m)):
+            solve += 32 * nslots + 32 * N
+            i = j & 3
+            pq = (32 * j + (48 if j >= 4 else 0)) if (j < 4 or i == 0) else (16 + 16 * (4 * i - 4))
+            conv += (pq + 64) * (N - n_pv) + (32 * j + 64) * n_pv
+            if j % 2 == 0:
+                eps += (32 * j + 64) * N
+    assert k['solve']['bytes'] == solve and k['factor']['bytes'] == fac
+    assert abs(k['rhs_conv']['bytes'] - conv) < 1e-6 * conv and abs(k['eps']['bytes'] - eps) < 1e-6 * eps
