@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HELM_MAX_PASSES = 16
-ST_RUNNING, ST_CONVERGED, ST_DIVERGED, ST_SINGULAR = 0, 2, 3, 4
+ST_RUNNING, ST_CONVERGED, ST_DIVERGED, ST_SINGULAR, ST_PASS_LIMIT = 0, 2, 3, 4, 5
 
 _LIB_PATH = os.environ.get("HELM_B200_LIB") or os.path.join(
     os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "libhelm_b200.so")
@@ -41,6 +41,7 @@ class Params(C.Structure):
         ("enforce_q_limits", C.c_int32), ("group", C.c_int32),
         ("use_graph", C.c_int32), ("poll_every", C.c_int32), ("max_resident", C.c_int32),
         ("pv_bus_model", C.c_int32), ("dsb_method", C.c_int32), ("dsb_model", C.c_int32),
+        ("record_switches", C.c_int32),
     ]
 
 
@@ -62,7 +63,7 @@ KERNEL_NAMES = ("assemble", "factor", "solve", "rhs_conv", "advance", "qlimit", 
 EXPORTED_SYMBOLS = (
     "helm_last_error", "helm_plan_create", "helm_plan_destroy", "helm_plan_get_info",
     "helm_plan_get_perm", "helm_plan_set_outages", "helm_workspace_bytes", "helm_solve_batch_device",
-    "helm_solve_batch_host", "helm_nr_batch_host", "helm_last_state_host", "helm_last_ploss_host", "helm_debug_factor_solve", "helm_debug_timeline", "helm_measure_peaks", "helm_measure_latencies",
+    "helm_solve_batch_host", "helm_nr_batch_host", "helm_last_state_host", "helm_last_switches_host", "helm_last_ploss_host", "helm_debug_factor_solve", "helm_debug_timeline", "helm_measure_peaks", "helm_measure_latencies",
     "helm_symbolic_create", "helm_symbolic_destroy", "helm_symbolic_array",
 )
 
@@ -102,6 +103,7 @@ def load():
     lib.helm_nr_batch_host.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_double, C.c_int32, C.c_int32,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.helm_last_state_host.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.helm_last_switches_host.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.helm_last_ploss_host.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     lib.helm_debug_factor_solve.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                             C.c_void_p, C.c_void_p]
@@ -234,7 +236,8 @@ class Plan:
 
     @staticmethod
     def make_params(mismatch, max_coefficients, enforce_q_limits, group=0, use_graph=True,
-                    poll_every=0, max_resident=0, pv_bus_model=2, dsb_method=0, dsb_model=False):
+                    poll_every=0, max_resident=0, pv_bus_model=2, dsb_method=0, dsb_model=False,
+                    record_switches=False):
         p = Params()
         p.mismatch = float(mismatch)
         p.max_coefficients = int(max_coefficients)
@@ -246,6 +249,7 @@ class Plan:
         p.pv_bus_model = int(pv_bus_model)
         p.dsb_method = int(dsb_method or 0)
         p.dsb_model = int(bool(dsb_model))
+        p.record_switches = int(bool(record_switches))
         return p
 
     def workspace_bytes(self, n_scen, params):
@@ -304,6 +308,19 @@ class Plan:
         bt = np.zeros((n_scen, self.N), dtype=np.uint8)
         check(load().helm_last_state_host(self.handle, n_scen, _ptr(qg), _ptr(bt)), "helm_last_state_host")
         return qg, bt
+
+    def last_switches(self, n_scen, nswitch):
+        """PV->PQ switches of the last ``solve_host`` made with record_switches: per scenario a list
+        of (pass, bus, violating Qg) sorted by pass and bus (the order the reference visits them,
+        helm.py:479)."""
+        cap = max(1, int(np.max(nswitch)))
+        bus = np.zeros((n_scen, cap), dtype=np.int32)
+        pas = np.zeros((n_scen, cap), dtype=np.int32)
+        q = np.zeros((n_scen, cap), dtype=np.float64)
+        check(load().helm_last_switches_host(self.handle, n_scen, cap, _ptr(bus), _ptr(pas), _ptr(q)),
+              "helm_last_switches_host")
+        return [sorted((int(pas[b, k]), int(bus[b, k]), float(q[b, k])) for k in range(cap) if bus[b, k] >= 0)
+                for b in range(n_scen)]
 
     def last_ploss(self, n_scen, max_coefficients, dsb_method, pv_bus_model):
         """Ploss series [B, max_coefficients+1] of the last distributed-slack ``solve_host``."""

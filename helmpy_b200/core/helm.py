@@ -52,18 +52,31 @@ def validate_arguments(case, detailed_run_print, mismatch, scale, max_coefficien
     return True
 
 
+def _case_fingerprint(case):
+    """Cheap digest of everything of ``case`` the plan uploads (tens of KB)."""
+    import hashlib
+    h = hashlib.blake2b(digest_size=16)
+    for name in ("Pd", "Qd", "Pg", "Qgmax", "Qgmin", "V", "Yshunt", "Ytrans_val", "Y_val", "phase_val",
+                 "adj_ptr", "adj_idx", "phase_ptr", "phase_idx"):
+        h.update(np.ascontiguousarray(getattr(case, name)).tobytes())
+    h.update(np.ascontiguousarray(case.bus_types_code()).tobytes())
+    return h.digest()
+
+
 def get_plan(case):
     """Symbolic analysis + device-resident grid for ``case``; cached on the object.
 
-    The plan depends on topology, admittances, generator data and the unscaled
-    loads, so it is rebuilt if the case's scale is not 1 when first used.
+    The reference rebuilds its run state from ``case`` on every call (helm.py:934), so
+    whatever the caller did to the case in between (``set_scale``, edited loads or
+    limits) is what it solves.  The cached plan is therefore keyed on a digest of the
+    arrays it uploaded and rebuilt when they changed.
     """
+    fp = _case_fingerprint(case)
     plan = getattr(case, "_b200_plan", None)
-    if plan is None:
-        if case.scale != 1:
-            raise _lib.HelmB200Error("build the plan on an unscaled case (call reset_scale())")
+    if plan is None or getattr(case, "_b200_plan_fp", None) != fp:
         plan = _lib.Plan(case)
         case._b200_plan = plan
+        case._b200_plan_fp = fp
     return plan
 
 
@@ -90,7 +103,8 @@ class BatchResult:
 
 def helm_batch(case, scales, mismatch=1e-4, max_coefficients=100, enforce_Q_limits=True,
                group=0, use_graph=True, poll_every=0, max_resident=0,
-               pv_bus_model=2, DSB_model=False, DSB_model_method=None, outages=None):
+               pv_bus_model=2, DSB_model=False, DSB_model_method=None, outages=None,
+               record_switches=False):
     """Solve ``len(scales)`` load-scaling scenarios of ``case`` on the current GPU.
 
     Scenario b equals ``helm(case, scale=scales[b], mismatch=..., ...)``
@@ -109,7 +123,7 @@ def helm_batch(case, scales, mismatch=1e-4, max_coefficients=100, enforce_Q_limi
         DSB_model_method = 2                                   # helm.py:913-914
     prm = _lib.Plan.make_params(mismatch, max_coefficients, enforce_Q_limits, group, use_graph,
                                 poll_every, max_resident, pv_bus_model, DSB_model_method or 0,
-                                DSB_model)
+                                DSB_model, record_switches)
     if scales is None:
         scales = np.ones(len(outages))
     V, status, ncoef, nswitch, stats = plan.solve_host(np.asarray(scales, dtype=np.float64), prm, outages)
@@ -137,12 +151,28 @@ def helm(case, detailed_run_print=False, mismatch=1e-4, scale=1, max_coefficient
         algorithm = 'HELM ' + pv_str
     res = helm_batch(case, [float(scale)], mismatch=mismatch, max_coefficients=max_coefficients,
                      enforce_Q_limits=enforce_Q_limits, group=1, pv_bus_model=pv_bus_model,
-                     DSB_model=DSB_model, DSB_model_method=DSB_model_method)
+                     DSB_model=DSB_model, DSB_model_method=DSB_model_method,
+                     record_switches=detailed_run_print)
     coefs = res.list_coef(0)
+    converged = res.status[0] == ST_CONVERGED
     if detailed_run_print:
-        for p, m in enumerate(coefs[:-1]):
-            print("At coefficient %d the system is to be resolved due to PVLIM to PQ switches\n" % m)
-    if res.status[0] != ST_CONVERGED:
+        # the run's progress lines, replayed in the reference's order (helm.py:573, 489, 647)
+        switches = get_plan(case).last_switches(1, res.nswitch)[0]
+        npass = len(coefs)
+        for p, m in enumerate(coefs):
+            for n in range(1, m):
+                print("Computing coefficient: %d" % n)
+            for (sp, bus, q) in switches:
+                if sp == p:
+                    lim = case.Qgmax[bus] if q > case.Qgmax[bus] else case.Qgmin[bus]
+                    print('Bus %d exceeded its Qgen limit with %f. The exceeded limit %f will be assigned to the bus'
+                          % (bus + 1, q, lim))
+            if p < npass - 1 or not converged:
+                print("At coefficient %d the system is to be resolved due to PVLIM to PQ switches\n" % m)
+        if res.status[0] == _lib.ST_DIVERGED:
+            for n in range(1, max_coefficients):
+                print("Computing coefficient: %d" % n)
+    if not converged:
         print('\nMaximum number of coefficients has been reached. The problem has no physical solution')
         return None
     print('\nConvergence has been reached. %d coefficients were calculated' % coefs[-1])

@@ -43,7 +43,8 @@ thread_local std::string g_err;
     } while (0)
 
 // internal per-scenario status (superset of the public codes)
-enum : int { ST_ACTIVE = 0, ST_FROZEN = 1, ST_CONVERGED = 2, ST_DIVERGED = 3, ST_SINGULAR = 4, ST_PAD = 5 };
+enum : int { ST_ACTIVE = 0, ST_FROZEN = 1, ST_CONVERGED = 2, ST_DIVERGED = 3, ST_SINGULAR = 4, ST_PAD = 5, ST_PASSCAP = 6 };
+constexpr int PASS_CAP = 4 * HELM_MAX_PASSES;    // Q-limit passes after which a scenario is given up (HELM_ST_PASS_LIMIT)
 // group flags
 // PENDING: the group needs a (re)factorization; FACTORING: it is being factorized in the
 // side branch of the current step and sits this order out (see the step graph below).
@@ -83,6 +84,7 @@ struct PlanDev {
 
 struct WorkDev {
     int B, G, ngroups, K;  // B = scenarios in the queue; K = history planes = max_coef + 1
+    int nbus;
     double mismatch;
     int max_coef, enforce_q;
     double *scale;                    // [Bp]
@@ -123,6 +125,11 @@ struct WorkDev {
     double2 *Vh, *Hh, *Eh;            // [group][tile][K][HT][G]
     double2 *Pb;                      // [group][tile][3][HT][G] partial sums of the blocked W recurrence
     double2 *vout;                    // [B][N] original order
+    // optional log of the PV->PQ switches (helm(detailed_run_print=True) prints them, helm.py:489):
+    // entry k of a slot = {original bus, pass, Q that violated the limit}; k = order of the atomicAdd
+    int2 *sw_ent;                     // [Bp][sw_cap] or null
+    double *sw_q;                     // [Bp][sw_cap]
+    int sw_cap;
     unsigned long long *tl;           // timeline buffer (HELM_TIMELINE builds only), else null
     // variants (helm_variants.cuh): PV bus model 1 and the distributed slack
     int pv_model, dsb_method, dsb_model;
@@ -341,6 +348,14 @@ __global__ void __launch_bounds__(256) k_assemble(PlanDev p, WorkDev w) {
 }
 
 struct Blk { double a, b, c, d; };  // [[a b][c d]]
+__device__ __forceinline__ double bnorm2(const Blk &m) { return m.a * m.a + m.b * m.b + m.c * m.c + m.d * m.d; }
+// Static pivoting has no row exchanges to fall back on, so a pivot block is declared singular when
+// its smallest singular value (|det| / ||D||) has dropped to 1e-11 of the norm of the block the
+// matrix started with (n0 = ||D0||_F^2): islanded buses after an outage leave Schur complements of
+// ~1e-13 relative size, well-posed grids stay above ~1e-6.  NaN counts as singular.
+__device__ __forceinline__ bool pivot_singular(const Blk &d, double det, double n0) {
+    return !(det * det > 1e-22 * bnorm2(d) * n0);
+}
 __device__ __forceinline__ Blk ldblk(const double2 *lu, size_t e) {
     double2 r0 = lu[e * 2], r1 = lu[e * 2 + 1];
     return Blk{r0.x, r0.y, r1.x, r1.y};
@@ -376,6 +391,7 @@ __global__ void __launch_bounds__(WPB * 32) k_factor(PlanDev p, WorkDev w) {
         if (active) {
             for (int r = p.llev_ptr[l] + slot; r < r1; r += R) {
                 int e0 = p.lptr[r], e1 = p.lptr[r + 1];
+                const double n0 = bnorm2(ldblk(lu, (size_t)p.dslot[r] * G + s));
                 for (int e = e0; e < e1; ++e) {
                     int k = p.lcol[e];
                     int u0 = p.fptr[e], u1 = p.fptr[e + 1];
@@ -407,7 +423,7 @@ __global__ void __launch_bounds__(WPB * 32) k_factor(PlanDev p, WorkDev w) {
                 size_t dd = (size_t)p.dslot[r] * G + s;
                 Blk d = ldblk(lu, dd);
                 double det = d.a * d.d - d.b * d.c;
-                if (det == 0.0 || !(det == det)) { singular = true; det = 1.0; }
+                if (pivot_singular(d, det, n0)) { singular = true; det = 1.0; }
                 double inv = 1.0 / det;
                 stblk(lu, dd, Blk{d.d * inv, -d.b * inv, -d.c * inv, d.a * inv});
             }
@@ -499,7 +515,7 @@ __global__ void __launch_bounds__(WPB * 32) k_factor_coop(PlanDev p, WorkDev w) 
                 size_t dd = (size_t)__ldg(p.dslot + r);
                 Blk d = ldblk(lu, dd);
                 double det = d.a * d.d - d.b * d.c;
-                if (det == 0.0 || !(det == det)) { singular = true; det = 1.0; }
+                if (pivot_singular(d, det, bnorm2(d))) { singular = true; det = 1.0; }
                 double inv = 1.0 / det;
                 stblk(lu, dd, Blk{d.d * inv, -d.b * inv, -d.c * inv, d.a * inv});
             }
@@ -557,6 +573,7 @@ __global__ void __launch_bounds__(WPB * 32) k_factor_coop(PlanDev p, WorkDev w) 
         // ---- phase 2: eliminate from shared memory
         if (have) {
             const unsigned mask = (lpr >= 32) ? 0xFFFFFFFFu : (((1u << lpr) - 1u) << (rs * lpr));
+            const double n0 = bnorm2(ldsm(buf, nl));         // the pivot block as assembled
             for (int e = 0; e < nl; ++e) {
                 Blk m = bmul(ldsm(buf, e), ldsm(sDk, e0 + e - e_base));
                 int u0 = sUp[e0 + e - e_base], u1 = sUp[e0 + e + 1 - e_base];
@@ -574,7 +591,7 @@ __global__ void __launch_bounds__(WPB * 32) k_factor_coop(PlanDev p, WorkDev w) 
             if (sl == 0) {
                 Blk d = ldsm(buf, nl);
                 double det = d.a * d.d - d.b * d.c;
-                if (det == 0.0 || !(det == det)) { singular = true; det = 1.0; }
+                if (pivot_singular(d, det, n0)) { singular = true; det = 1.0; }
                 double inv = 1.0 / det;
                 stsm(buf, nl, Blk{d.d * inv, -d.b * inv, -d.c * inv, d.a * inv});
             }
@@ -1540,7 +1557,11 @@ __global__ void k_qlimit(PlanDev p, WorkDev w) {
         lim = (qg > p.qmax[i]) ? p.qmax[i] : p.qmin[i];
         w.btype[bi] = HELM_BUS_PQ;
         w.s_viol[sg] = 1;
-        atomicAdd(&w.s_nswitch[sg], 1);
+        const int k = atomicAdd(&w.s_nswitch[sg], 1);
+        if (w.sw_ent && k < w.sw_cap) {
+            w.sw_ent[(size_t)sg * w.sw_cap + k] = make_int2(p.perm[i], w.s_npass[sg]);
+            w.sw_q[(size_t)sg * w.sw_cap + k] = qg;
+        }
     }
     w.Qg[bi] = lim;
   }
@@ -1558,14 +1579,16 @@ __global__ void k_pass_end(WorkDev w) {
         int sg = grp * w.G + s;
         if (w.s_status[sg] == ST_FROZEN) {
             int np = w.s_npass[sg];
-            if (np < HELM_MAX_PASSES) w.s_ncoef[sg * HELM_MAX_PASSES + np] = w.s_mconv[sg];
+            // beyond HELM_MAX_PASSES recorded passes the last entry always holds the latest pass
+            w.s_ncoef[sg * HELM_MAX_PASSES + (np < HELM_MAX_PASSES ? np : HELM_MAX_PASSES - 1)] = w.s_mconv[sg];
             w.s_npass[sg] = np + 1;
-            if (w.s_viol[sg] && np + 1 < 4 * HELM_MAX_PASSES) {
+            if (w.s_viol[sg] && np + 1 < PASS_CAP) {
                 w.s_status[sg] = ST_ACTIVE;
                 w.s_viol[sg] = 0;
                 any = 1;
             } else {
-                w.s_status[sg] = ST_CONVERGED;
+                // violations still pending at the pass cap: not a solution of the reference's loop
+                w.s_status[sg] = w.s_viol[sg] ? ST_PASSCAP : ST_CONVERGED;
             }
         }
     }
@@ -1584,7 +1607,12 @@ __global__ void k_pass_end(WorkDev w) {
                 int st = w.s_status[sg];
                 w.out_status[scen] = (st == ST_CONVERGED) ? HELM_ST_CONVERGED
                                    : (st == ST_DIVERGED)  ? HELM_ST_DIVERGED
-                                   : (st == ST_SINGULAR)  ? HELM_ST_SINGULAR : HELM_ST_RUNNING;
+                                   : (st == ST_SINGULAR)  ? HELM_ST_SINGULAR
+                                   : (st == ST_PASSCAP)   ? HELM_ST_PASS_LIMIT : HELM_ST_RUNNING;
+                // k_qlimit wrote the voltages of every converged pass; a scenario that ends without a
+                // solution after an earlier converged pass gets its row zeroed again (rare)
+                if (st != ST_CONVERGED && w.s_npass[sg] > 0 && w.vout)
+                    for (int i = 0; i < w.nbus; ++i) w.vout[(size_t)scen * w.nbus + i] = make_double2(0.0, 0.0);
                 if (w.out_nswitch) w.out_nswitch[scen] = w.s_nswitch[sg];
                 if (w.out_ncoef)
                     for (int k = 0; k < HELM_MAX_PASSES; ++k)
@@ -1767,10 +1795,22 @@ struct helm_plan {
     unsigned long long *tl = nullptr;
     int *d_outage = nullptr;      // pending N-1 list for the next solve (helm_plan_set_outages)
     int outage_n = 0;
-    int last_B = 0, last_G = 0, last_maxcoef = 0, last_resident = 0, last_dsb = 0, last_pv = 0;   // layout of the last host-buffer solve
+    int last_B = 0, last_G = 0, last_maxcoef = 0, last_resident = 0, last_dsb = 0, last_pv = 0, last_rec = 0;   // layout of the last host-buffer solve
 };
 
 namespace {
+
+// The N-1 list set by helm_plan_set_outages belongs to exactly one solve call: whatever way that
+// call ends (argument error, CUDA error, success), the list is gone afterwards, so that a later call
+// without outages can never silently solve N-1 networks.
+struct OutageGuard {
+    helm_plan *pl;
+    explicit OutageGuard(helm_plan *p) : pl(p) {}
+    ~OutageGuard() {
+        if (pl && pl->d_outage) { cudaFree(pl->d_outage); pl->d_outage = nullptr; }
+        if (pl) pl->outage_n = 0;
+    }
+};
 
 template <typename T>
 int upload(helm_plan *pl, const std::vector<T> &v, const T **out) {
@@ -1796,6 +1836,8 @@ struct WsLayout {
     size_t total = 0;
     size_t off_scale, off_sint, off_gint, off_btype, off_Qg, off_VVant, off_Pcur, off_rhs, off_xb, off_lu, off_Vh, off_Hh, off_Eh;
     size_t off_var_s, off_ploss, off_zb, off_Qh, off_vre, off_qcur, off_lu_shared, off_shprep, off_Pb;
+    size_t off_sw_ent, off_sw_q;
+    int sw_cap;
     int G, ngroups, Bp, K;
 };
 
@@ -1840,6 +1882,13 @@ WsLayout layout(const helm_plan *pl, int B, const helm_params *prm) {
         L.off_vre = take(per * sizeof(double));
         L.off_qcur = take(per * sizeof(double));
     }
+    L.off_sw_ent = L.off_sw_q = 0;
+    L.sw_cap = 0;
+    if (prm->record_switches) {
+        L.sw_cap = std::max(1, pl->n_pv);                    // a bus switches at most once
+        L.off_sw_ent = take(sizeof(int2) * (size_t)L.Bp * L.sw_cap);
+        L.off_sw_q = take(sizeof(double) * (size_t)L.Bp * L.sw_cap);
+    }
     L.total = o;
     return L;
 }
@@ -1847,7 +1896,7 @@ WsLayout layout(const helm_plan *pl, int B, const helm_params *prm) {
 WorkDev bind(const helm_plan *pl, const WsLayout &L, int B, const helm_params *prm, void *ws, double *vout) {
     WorkDev w;
     char *b = (char *)ws;
-    w.B = B; w.G = L.G; w.ngroups = L.ngroups; w.K = L.K;
+    w.B = B; w.G = L.G; w.ngroups = L.ngroups; w.K = L.K; w.nbus = pl->S.N;
     w.mismatch = prm->mismatch; w.max_coef = prm->max_coefficients; w.enforce_q = prm->enforce_q_limits;
     w.scale = (double *)(b + L.off_scale);
     int *si = (int *)(b + L.off_sint);
@@ -1875,6 +1924,11 @@ WorkDev bind(const helm_plan *pl, const WsLayout &L, int B, const helm_params *p
     w.Pb = (double2 *)(b + L.off_Pb);
     w.vout = (double2 *)vout;
     w.tl = pl->tl;
+    w.sw_ent = nullptr; w.sw_q = nullptr; w.sw_cap = L.sw_cap;
+    if (L.sw_cap) {
+        w.sw_ent = (int2 *)(b + L.off_sw_ent);
+        w.sw_q = (double *)(b + L.off_sw_q);
+    }
     w.pv_model = prm->pv_bus_model == 1 ? 1 : 2;
     w.dsb_method = prm->dsb_method;
     w.dsb_model = prm->dsb_model;
@@ -2277,14 +2331,17 @@ static int check_params(const helm_params *prm) {
 int helm_solve_batch_device(helm_plan *pl, int32_t B, const double *d_scale, const helm_params *prm,
                             void *d_ws, size_t ws_bytes, double *d_vout, int32_t *d_status,
                             int32_t *d_ncoef, int32_t *d_nswitch, void *stream_, helm_stats *stats) {
-    if (!pl || !d_scale || !d_ws || !d_vout || !d_status || B <= 0) { g_err = "null/invalid argument"; return HELM_E_ARG; }
+    if (!pl) { g_err = "null plan"; return HELM_E_ARG; }
+    OutageGuard outage_guard(pl);                            // the pending N-1 list ends with this call
+    if (!d_scale || !d_ws || !d_vout || !d_status || B <= 0) { g_err = "null/invalid argument"; return HELM_E_ARG; }
     int rc = check_params(prm);
     if (rc) return rc;
     WsLayout L = layout(pl, B, prm);
     if (ws_bytes < L.total) { g_err = "workspace too small"; return HELM_E_NOMEM; }
     cudaStream_t st = (cudaStream_t)stream_;
     WorkDev w = bind(pl, L, B, prm, d_ws, d_vout);
-    if (pl->d_outage && pl->outage_n == B) {
+    if (pl->d_outage) {
+        if (pl->outage_n != B) { g_err = "the outage list was set for a different number of scenarios"; return HELM_E_ARG; }
         if (prm->dsb_method || prm->pv_bus_model == 1) { g_err = "outage scenarios need pv_bus_model 2 and the classic slack"; return HELM_E_ARG; }
         w.outage_in = pl->d_outage;
     }
@@ -2322,6 +2379,7 @@ int helm_solve_batch_device(helm_plan *pl, int32_t B, const double *d_scale, con
     CUDA_TRY(cudaEventCreate(&ev1));
     CUDA_TRY(cudaEventRecord(ev0, st));
     CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int) * B, st));           // HELM_ST_RUNNING until a scenario ends
+    CUDA_TRY(cudaMemsetAsync(d_vout, 0, sizeof(double) * 2 * (size_t)pl->S.N * B, st));   // rows of scenarios without a solution stay zero
     if (d_ncoef) CUDA_TRY(cudaMemsetAsync(d_ncoef, 0, sizeof(int) * B * HELM_MAX_PASSES, st));
     if (d_nswitch) CUDA_TRY(cudaMemsetAsync(d_nswitch, 0, sizeof(int) * B, st));
     launch_setup(L.G, p, w, d_scale, st);
@@ -2410,7 +2468,6 @@ int helm_solve_batch_device(helm_plan *pl, int32_t B, const double *d_scale, con
     for (auto &e : pev) cudaEventDestroy(e);
     if (gexec) cudaGraphExecDestroy(gexec);
     if (graph) cudaGraphDestroy(graph);
-    if (pl->d_outage) { cudaFree(pl->d_outage); pl->d_outage = nullptr; pl->outage_n = 0; }   // consumed
     CUDA_TRY(cudaGetLastError());
     if (stats) *stats = local;
     return HELM_OK;
@@ -2419,7 +2476,9 @@ int helm_solve_batch_device(helm_plan *pl, int32_t B, const double *d_scale, con
 int helm_solve_batch_host(helm_plan *pl, int32_t B, const double *h_scale, const helm_params *prm,
                           double *h_vout, int32_t *h_status, int32_t *h_ncoef, int32_t *h_nswitch,
                           helm_stats *stats) {
-    if (!pl || !h_scale || !h_vout || !h_status || B <= 0) { g_err = "null/invalid argument"; return HELM_E_ARG; }
+    if (!pl) { g_err = "null plan"; return HELM_E_ARG; }
+    OutageGuard outage_guard(pl);
+    if (!h_scale || !h_vout || !h_status || B <= 0) { g_err = "null/invalid argument"; return HELM_E_ARG; }
     int rc = check_params(prm);
     if (rc) return rc;
     helm_params prm_local = *prm;
@@ -2456,11 +2515,10 @@ int helm_solve_batch_host(helm_plan *pl, int32_t B, const double *h_scale, const
     }
     cudaStream_t st = pl->stream;
     CUDA_TRY(cudaMemcpyAsync(pl->d_scale, h_scale, sizeof(double) * B, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemsetAsync(pl->d_vout, 0, sizeof(double) * 2 * N * B, st));
     rc = helm_solve_batch_device(pl, B, pl->d_scale, prm, pl->ws, pl->ws_bytes, pl->d_vout, pl->d_status,
                                  pl->d_ncoef, pl->d_nswitch, st, stats);
     if (rc) return rc;
-    pl->last_B = B; pl->last_G = L.G; pl->last_maxcoef = prm->max_coefficients; pl->last_resident = prm->max_resident; pl->last_dsb = prm->dsb_method; pl->last_pv = prm->pv_bus_model;
+    pl->last_B = B; pl->last_G = L.G; pl->last_maxcoef = prm->max_coefficients; pl->last_resident = prm->max_resident; pl->last_dsb = prm->dsb_method; pl->last_pv = prm->pv_bus_model; pl->last_rec = prm->record_switches;
     CUDA_TRY(cudaMemcpyAsync(h_vout, pl->d_vout, sizeof(double) * 2 * N * B, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(h_status, pl->d_status, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
     if (h_ncoef) CUDA_TRY(cudaMemcpyAsync(h_ncoef, pl->d_ncoef, sizeof(int) * B * HELM_MAX_PASSES, cudaMemcpyDeviceToHost, st));
@@ -2472,7 +2530,9 @@ int helm_solve_batch_host(helm_plan *pl, int32_t B, const double *h_scale, const
 int helm_nr_batch_host(helm_plan *pl, int32_t B, const double *h_scale, double mismatch, int32_t max_iterations,
                        int32_t enforce_q_limits, double *h_vout, int32_t *h_status, int32_t *h_iters,
                        int32_t *h_nswitch) {
-    if (!pl || !h_scale || !h_vout || !h_status || B <= 0) { g_err = "null/invalid argument"; return HELM_E_ARG; }
+    if (!pl) { g_err = "null plan"; return HELM_E_ARG; }
+    OutageGuard outage_guard(pl);                            // NR has no outage scenarios: a pending list is dropped
+    if (!h_scale || !h_vout || !h_status || B <= 0) { g_err = "null/invalid argument"; return HELM_E_ARG; }
     if (!(mismatch > 0) || max_iterations < 1) { g_err = "mismatch must be positive and max_iterations >= 1"; return HELM_E_ARG; }
     if (!pl->d.use_coop_factor) { g_err = "grid too large for the staged factorization used by the GPU Newton-Raphson"; return HELM_E_STRUCT; }
     const PlanDev &p = pl->d;
@@ -2544,6 +2604,7 @@ int helm_last_state_host(helm_plan *pl, int32_t B, double *h_qg, uint8_t *h_bus_
     helm_params prm;
     memset(&prm, 0, sizeof(prm));
     prm.mismatch = 1.0; prm.max_coefficients = pl->last_maxcoef; prm.group = pl->last_G; prm.max_resident = pl->last_resident; prm.dsb_method = pl->last_dsb; prm.pv_bus_model = pl->last_pv;
+    prm.record_switches = pl->last_rec;
     WsLayout L = layout(pl, B, &prm);
     if (L.Bp < B) { g_err = "per-bus state is only kept when every scenario has its own slot (n_scen <= max_resident)"; return HELM_E_ARG; }
     const size_t N = pl->S.N, per = (size_t)L.Bp * N;
@@ -2563,12 +2624,40 @@ int helm_last_state_host(helm_plan *pl, int32_t B, double *h_qg, uint8_t *h_bus_
     return HELM_OK;
 }
 
+int helm_last_switches_host(helm_plan *pl, int32_t B, int32_t cap, int32_t *h_bus, int32_t *h_pass, double *h_q) {
+    if (!pl || !h_bus || !h_pass || !h_q || B <= 0 || cap <= 0 || B != pl->last_B || !pl->ws || !pl->last_rec) {
+        g_err = "no matching host solve with record_switches to read from";
+        return HELM_E_ARG;
+    }
+    helm_params prm;
+    memset(&prm, 0, sizeof(prm));
+    prm.mismatch = 1.0; prm.max_coefficients = pl->last_maxcoef; prm.group = pl->last_G; prm.max_resident = pl->last_resident;
+    prm.dsb_method = pl->last_dsb; prm.pv_bus_model = pl->last_pv; prm.record_switches = 1;
+    WsLayout L = layout(pl, B, &prm);
+    if (L.Bp < B) { g_err = "per-scenario state is only kept when every scenario has its own slot"; return HELM_E_ARG; }
+    std::vector<int2> ent((size_t)L.Bp * L.sw_cap);
+    std::vector<double> q((size_t)L.Bp * L.sw_cap);
+    std::vector<int> nsw(L.Bp);
+    CUDA_TRY(cudaMemcpy(ent.data(), (char *)pl->ws + L.off_sw_ent, ent.size() * sizeof(int2), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(q.data(), (char *)pl->ws + L.off_sw_q, q.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(nsw.data(), (char *)pl->ws + L.off_sint + sizeof(int) * 5 * (size_t)L.Bp, sizeof(int) * L.Bp, cudaMemcpyDeviceToHost));
+    for (int b = 0; b < B; ++b)
+        for (int k = 0; k < cap; ++k) {
+            const bool have = k < nsw[b] && k < L.sw_cap;
+            const size_t src = (size_t)b * L.sw_cap + k, dst = (size_t)b * cap + k;
+            h_bus[dst] = have ? ent[src].x : -1;
+            h_pass[dst] = have ? ent[src].y : -1;
+            h_q[dst] = have ? q[src] : 0.0;
+        }
+    return HELM_OK;
+}
+
 int helm_last_ploss_host(helm_plan *pl, int32_t B, int32_t dsb_method, int32_t pv_bus_model, double *h_ploss) {
     if (!pl || !h_ploss || B <= 0 || B != pl->last_B || !pl->ws || !dsb_method) { g_err = "no matching distributed-slack host solve"; return HELM_E_ARG; }
     helm_params prm;
     memset(&prm, 0, sizeof(prm));
     prm.mismatch = 1.0; prm.max_coefficients = pl->last_maxcoef; prm.group = 1; prm.max_resident = pl->last_resident;
-    prm.dsb_method = dsb_method; prm.pv_bus_model = pv_bus_model;
+    prm.dsb_method = dsb_method; prm.pv_bus_model = pv_bus_model; prm.record_switches = pl->last_rec;
     WsLayout L = layout(pl, B, &prm);
     if (L.Bp < B) { g_err = "per-scenario state is only kept when every scenario has its own slot"; return HELM_E_ARG; }
     CUDA_TRY(cudaMemcpy(h_ploss, (char *)pl->ws + L.off_ploss, sizeof(double) * (size_t)B * L.K, cudaMemcpyDeviceToHost));

@@ -39,9 +39,11 @@ extern "C" {
 #define HELM_ST_RUNNING 0
 #define HELM_ST_CONVERGED 2   /* helm() would return the voltage vector        */
 #define HELM_ST_DIVERGED 3    /* helm() would return None (helm.py:654-657)    */
-#define HELM_ST_SINGULAR 4    /* zero 2x2 pivot in the numeric factorization   */
+#define HELM_ST_SINGULAR 4    /* (numerically) singular 2x2 pivot in the numeric factorization */
+#define HELM_ST_PASS_LIMIT 5  /* Q-limit violations still pending after 4*HELM_MAX_PASSES passes */
 
-#define HELM_MAX_PASSES 16    /* Q-limit passes recorded in ncoef[]            */
+#define HELM_MAX_PASSES 16    /* Q-limit passes recorded in ncoef[]; with more passes the last
+                                 entry holds the most recent pass                 */
 
 /* bus type codes (reference strings 'PQ', 'PV'/'PVLIM', 'Slack') */
 #define HELM_BUS_PQ 0
@@ -95,6 +97,8 @@ typedef struct helm_params {
     int32_t pv_bus_model;       /* helm(pv_bus_model=): 1 or 2; 0 = 2 (the reference default)   */
     int32_t dsb_method;         /* helm(DSB_model_method=): 0 = classic slack, 1 or 2            */
     int32_t dsb_model;          /* helm(DSB_model=): participation factors (needs dsb_method)    */
+    int32_t record_switches;    /* keep a log of the PV->PQ switches (bus, pass, violating Q) for
+                                   helm_last_switches_host: helm(detailed_run_print=True), helm.py:489 */
 } helm_params;
 
 typedef struct helm_plan_info {
@@ -146,7 +150,8 @@ size_t helm_workspace_bytes(const helm_plan *plan, int32_t n_scen, const helm_pa
  * device; work is enqueued on `stream` (a cudaStream_t) and the call returns
  * after the last poll, with results complete on the stream.
  *   d_scale    [n_scen] double
- *   d_vout     [n_scen * n_bus] complex, scenario-major, original bus order
+ *   d_vout     [n_scen * n_bus] complex, scenario-major, original bus order; zeroed by the call,
+ *              rows of scenarios that end without a solution stay zero
  *   d_status   [n_scen] int32 HELM_ST_*
  *   d_ncoef    [n_scen * HELM_MAX_PASSES] int32: coefficients per pass (run.list_coef), 0-padded
  *   d_nswitch  [n_scen] int32: PV->PQ switches
@@ -178,6 +183,14 @@ int helm_nr_batch_host(helm_plan *plan, int32_t n_scen, const double *h_scale, d
  * helm.py:670-759).  h_qg [n_scen*n_bus] p.u., h_bus_type [n_scen*n_bus] HELM_BUS_*;
  * original bus order; either pointer may be NULL. */
 int helm_last_state_host(helm_plan *plan, int32_t n_scen, double *h_qg, uint8_t *h_bus_type);
+
+/* PV->PQ switches of the last helm_solve_batch_host call made with params.record_switches
+ * (reference check_PVLIM_violation, helm.py:468-490, whose detailed print is helm.py:489): for
+ * scenario b, entries k < min(nswitch[b], cap): h_bus[b*cap+k] = original bus index, h_pass = Q-limit
+ * pass (0-based) in which it switched, h_q = the reactive generation that violated the limit (p.u.);
+ * unused entries are -1 / -1 / 0.  Entries of one pass are in no particular order. */
+int helm_last_switches_host(helm_plan *plan, int32_t n_scen, int32_t cap, int32_t *h_bus,
+                            int32_t *h_pass, double *h_q);
 
 /* Ploss series of the last distributed-slack helm_solve_batch_host call (reference
  * run.coefficients[2N][:], used by the report, helm.py:963-965): h_ploss [n_scen*(max_coefficients+1)]. */

@@ -58,8 +58,17 @@ def load_reference():
         return pd.DataFrame(cols)
 
     pd.read_excel = read_excel
+    # the repository ships a `helmpy` package of its own (the drop-in name, bound to the CUDA
+    # build): make sure the name resolves to the REFERENCE here, whatever was imported before
+    for name in [m for m in sys.modules if m == "helmpy" or m.startswith("helmpy.")]:
+        del sys.modules[name]
     sys.path.insert(0, REFERENCE_ROOT)
-    import helmpy  # noqa: the reference package
+    try:
+        import helmpy  # noqa: the reference package
+    finally:
+        sys.path.remove(REFERENCE_ROOT)
+    if getattr(helmpy, "IMPLEMENTATION", None) == "helmpy_b200":
+        raise RuntimeError("imported the drop-in shim instead of the reference")
     _ref = helmpy
     return _ref
 

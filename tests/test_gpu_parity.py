@@ -211,8 +211,9 @@ def test_detailed_print_matches_reference_stdout(hb, name, scale, capsys):
     hb.helm(case, detailed_run_print=True, mismatch=1e-8, scale=scale, max_coefficients=40)
     out = capsys.readouterr().out
     ref = open(os.path.join(GOLDEN, 'ref_stdout_%s_%s.txt' % (name, scale))).read()
-    ours = out[out.index('\tVoltage profile:'):]
-    theirs = ref[ref.index('\tVoltage profile:'):]
+    # the whole stdout: progress lines (helm.py:573), Q-limit switches (489), restart notices (647),
+    # the convergence line (651) and the report
+    ours, theirs = out, ref
     strip = lambda t: [' '.join(l.split()) for l in t.strip().splitlines()]
     lo, lt = strip(ours), strip(theirs)
     assert len(lo) == len(lt)
@@ -337,8 +338,7 @@ def test_distributed_slack_report_matches_reference_stdout(hb, name, variant, ca
             pv_bus_model=pv, DSB_model=dsb, DSB_model_method=method)
     out = capsys.readouterr().out
     ref = open(os.path.join(GOLDEN, 'ref_stdout_%s_ds_%d_%d_%d.txt' % (name, pv, int(dsb), method))).read()
-    ours = out[out.index('\tVoltage profile:'):]
-    theirs = ref[ref.index('\tVoltage profile:'):]
+    ours, theirs = out, ref
     strip = lambda t: [' '.join(l.split()) for l in t.strip().splitlines()]
     lo, lt = strip(ours), strip(theirs)
     assert len(lo) == len(lt)
@@ -463,3 +463,69 @@ def test_large_batch_kernels_agree_with_small_batch(hb, kw):
     assert big.converged.all()
     assert np.array_equal(big.status[:40], small.status) and np.array_equal(big.ncoef[:40], small.ncoef)
     assert np.max(np.abs(big.V[:40] - small.V)) < 1e-10
+
+
+def test_failed_outage_call_does_not_leak_into_the_next_solve(hb):
+    """A call that sets an N-1 list and then fails must not leave the list behind: the next call
+    without outages solves the base network (round-1 advisor finding)."""
+    from helmpy_b200.core import _lib
+    case = load_case('case118')
+    safe = hb.non_islanding_branches(case)
+    scales = np.array([1.0, 0.95, 1.02])
+    outages = np.asarray(safe[:3], dtype=np.int32)
+    with pytest.raises(_lib.HelmB200Error):
+        hb.helm_batch(case, scales, mismatch=1e-8, max_coefficients=40, outages=outages, pv_bus_model=1)
+    after = hb.helm_batch(case, scales, mismatch=1e-8, max_coefficients=40)
+    for b, s in enumerate(scales):
+        Vo, info = ho.helm_oracle(case, mismatch=1e-8, scale=s, max_coefficients=40)
+        assert after.list_coef(b) == info['list_coef']
+        dmag, dang = polar_err(after.V[b], Vo)
+        assert dmag <= TOL_MAG and dang <= TOL_ANG
+    # a list of the wrong length is an error, not silently ignored
+    plan = hb.core.helm.get_plan(case) if False else None
+    from helmpy_b200.core.helm import get_plan
+    plan = get_plan(case)
+    import ctypes as C
+    lib = _lib.load()
+    o4 = np.asarray(safe[:4], dtype=np.int32)
+    _lib.check(lib.helm_plan_set_outages(plan.handle, 4, o4.ctypes.data_as(C.c_void_p)), 'set_outages')
+    with pytest.raises(_lib.HelmB200Error):
+        plan.solve_host(scales, _lib.Plan.make_params(1e-8, 40, True))
+    again = hb.helm_batch(case, scales, mismatch=1e-8, max_coefficients=40)
+    assert np.array_equal(again.V, after.V)
+
+
+def test_islanding_outage_is_reported_singular(hb):
+    """Removing a bridge islands part of the grid: the matrix is singular.  Static pivoting must say
+    so (status 4, zero row) instead of returning voltages from a 1e-13 pivot."""
+    case = load_case('case118')
+    safe = set(int(b) for b in hb.non_islanding_branches(case))
+    bridges = [b for b in range(case.N_branches) if b not in safe]
+    assert bridges
+    outages = np.array(bridges[:4] + [-1], dtype=np.int32)
+    res = hb.helm_batch(case, np.ones(len(outages)), mismatch=1e-8, max_coefficients=40, outages=outages)
+    assert res.converged[-1]
+    for k in range(len(outages) - 1):
+        assert res.status[k] in (3, 4), (k, outages[k], res.status[k])
+        assert np.all(res.V[k] == 0)
+
+
+def test_plan_follows_mutations_of_the_case(hb, capsys):
+    """The reference rebuilds its run state from the case on every call (helm.py:934): a case scaled
+    in place with set_scale, or with edited limits, is solved as it stands."""
+    from common import load_tables
+    from helmpy_b200.core.classes import create_case_data_object_from_arrays
+    case = create_case_data_object_from_arrays(*load_tables('case118'), 'case118')
+    V1 = hb.helm(case, mismatch=1e-8, max_coefficients=40)
+    case.set_scale(1.05)
+    V2 = hb.helm(case, mismatch=1e-8, max_coefficients=40)
+    case.reset_scale()
+    V3 = hb.helm(case, mismatch=1e-8, scale=1.05, max_coefficients=40)
+    assert np.max(np.abs(V2 - V3)) < 1e-12 and np.max(np.abs(V1 - V2)) > 1e-4
+    case.Qgmax[:] = 99.0
+    case.Qgmin[:] = -99.0
+    V4 = hb.helm(case, mismatch=1e-8, max_coefficients=40)
+    Vo, info = ho.helm_oracle(case, mismatch=1e-8, scale=1, max_coefficients=40)
+    assert len(info['switched']) == 0
+    dmag, dang = polar_err(V4, Vo)
+    assert dmag <= TOL_MAG and dang <= TOL_ANG
