@@ -63,7 +63,7 @@ KERNEL_NAMES = ("assemble", "factor", "solve", "rhs_conv", "advance", "qlimit", 
 EXPORTED_SYMBOLS = (
     "helm_last_error", "helm_plan_create", "helm_plan_destroy", "helm_plan_get_info",
     "helm_plan_get_perm", "helm_plan_set_outages", "helm_workspace_bytes", "helm_solve_batch_device",
-    "helm_solve_batch_host", "helm_nr_batch_host", "helm_last_state_host", "helm_last_switches_host", "helm_last_ploss_host", "helm_debug_factor_solve", "helm_debug_timeline", "helm_measure_peaks", "helm_measure_latencies",
+    "helm_solve_batch_host", "helm_nr_batch_host", "helm_last_state_host", "helm_last_switches_host", "helm_last_series_host", "helm_last_ploss_host", "helm_debug_factor_solve", "helm_debug_timeline", "helm_measure_peaks", "helm_measure_latencies",
     "helm_symbolic_create", "helm_symbolic_destroy", "helm_symbolic_array",
 )
 
@@ -104,6 +104,7 @@ def load():
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.helm_last_state_host.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     lib.helm_last_switches_host.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.helm_last_series_host.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     lib.helm_last_ploss_host.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     lib.helm_debug_factor_solve.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                             C.c_void_p, C.c_void_p]
@@ -308,6 +309,15 @@ class Plan:
         bt = np.zeros((n_scen, self.N), dtype=np.uint8)
         check(load().helm_last_state_host(self.handle, n_scen, _ptr(qg), _ptr(bt)), "helm_last_state_host")
         return qg, bt
+
+    def last_series(self, n_scen, scen, n_terms):
+        """(V [n_terms, N], H [n_terms, N]) series of the last pass of scenario ``scen`` after a
+        ``solve_host`` of n_scen resident scenarios: H = W on PQ buses, barras_CC on PV buses."""
+        V = np.zeros((n_terms, self.N), dtype=np.complex128)
+        H = np.zeros((n_terms, self.N), dtype=np.complex128)
+        check(load().helm_last_series_host(self.handle, n_scen, scen, n_terms, _ptr(V), _ptr(H)),
+              "helm_last_series_host")
+        return V, H
 
     def last_switches(self, n_scen, nswitch):
         """PV->PQ switches of the last ``solve_host`` made with record_switches: per scenario a list

@@ -2624,6 +2624,37 @@ int helm_last_state_host(helm_plan *pl, int32_t B, double *h_qg, uint8_t *h_bus_
     return HELM_OK;
 }
 
+int helm_last_series_host(helm_plan *pl, int32_t B, int32_t scen, int32_t n_terms, double *h_V, double *h_H) {
+    if (!pl || B <= 0 || B != pl->last_B || !pl->ws || scen < 0 || scen >= B || n_terms <= 0 || (!h_V && !h_H)) {
+        g_err = "no matching host solve to read the series from";
+        return HELM_E_ARG;
+    }
+    if (pl->last_G != 1) { g_err = "series read-back needs group = 1"; return HELM_E_ARG; }
+    helm_params prm;
+    memset(&prm, 0, sizeof(prm));
+    prm.mismatch = 1.0; prm.max_coefficients = pl->last_maxcoef; prm.group = 1; prm.max_resident = pl->last_resident;
+    prm.dsb_method = pl->last_dsb; prm.pv_bus_model = pl->last_pv; prm.record_switches = pl->last_rec;
+    WsLayout L = layout(pl, B, &prm);
+    if (L.Bp < B) { g_err = "per-scenario state is only kept when every scenario has its own slot"; return HELM_E_ARG; }
+    if (n_terms > L.K) { g_err = "n_terms exceeds max_coefficients + 1"; return HELM_E_ARG; }
+    const size_t N = pl->S.N, ntile = (N + HT - 1) / HT, per = ntile * L.K * HT;
+    std::vector<double2> buf(per);
+    for (int which = 0; which < 2; ++which) {
+        double *dst = which ? h_H : h_V;
+        if (!dst) continue;
+        const size_t off = which ? L.off_Hh : L.off_Vh;
+        CUDA_TRY(cudaMemcpy(buf.data(), (char *)pl->ws + off + (size_t)scen * per * sizeof(double2), per * sizeof(double2), cudaMemcpyDeviceToHost));
+        for (int k = 0; k < n_terms; ++k)
+            for (size_t r = 0; r < N; ++r) {
+                const double2 v = buf[((r / HT) * L.K + k) * HT + (r % HT)];
+                const size_t o = (size_t)k * N + pl->S.perm[r];
+                dst[2 * o] = v.x;
+                dst[2 * o + 1] = v.y;
+            }
+    }
+    return HELM_OK;
+}
+
 int helm_last_switches_host(helm_plan *pl, int32_t B, int32_t cap, int32_t *h_bus, int32_t *h_pass, double *h_q) {
     if (!pl || !h_bus || !h_pass || !h_q || B <= 0 || cap <= 0 || B != pl->last_B || !pl->ws || !pl->last_rec) {
         g_err = "no matching host solve with record_switches to read from";

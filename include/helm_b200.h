@@ -184,6 +184,14 @@ int helm_nr_batch_host(helm_plan *plan, int32_t n_scen, const double *h_scale, d
  * original bus order; either pointer may be NULL. */
 int helm_last_state_host(helm_plan *plan, int32_t n_scen, double *h_qg, uint8_t *h_bus_type);
 
+/* Series coefficients of the LAST pass of scenario `scen` of the last helm_solve_batch_host call
+ * (group 1, every scenario resident): h_V[k*n_bus + i] = V_i[k] (reference run.V_complex[i][k],
+ * classes.py:262), h_H[k*n_bus + i] = W_i[k] for buses that ended as PQ (run.W, classes.py:263) and
+ * barras_CC_i[k] for buses that ended as PV (helm.py:310-313), k < n_terms <= max_coefficients + 1;
+ * complex, original bus order; either pointer may be NULL.  Per-order parity tests. */
+int helm_last_series_host(helm_plan *plan, int32_t n_scen, int32_t scen, int32_t n_terms,
+                          double *h_V, double *h_H);
+
 /* PV->PQ switches of the last helm_solve_batch_host call made with params.record_switches
  * (reference check_PVLIM_violation, helm.py:468-490, whose detailed print is helm.py:489): for
  * scenario b, entries k < min(nswitch[b], cap): h_bus[b*cap+k] = original bus index, h_pass = Q-limit

@@ -167,6 +167,22 @@ def config5():
     if RANK == 0:
         idx = np.random.default_rng(7).choice(len(outages), size=2, replace=False)
         res['oracle'] = check_vs_oracle(case, V, st, scales, idx, 60, outages=outages, tables=tables)
+        # the outages that did NOT converge: does the reference algorithm (oracle) agree that there is
+        # no solution within max_coefficients, or is the GPU path wrong there?
+        from helmpy_b200.core.classes import create_case_data_object_from_arrays
+        bad = np.nonzero(st != 2)[0]
+        verdicts = []
+        for b in bad[:int(os.environ.get('HELM_N1_ORACLE_MAX', '24'))]:
+            c2 = create_case_data_object_from_arrays(*tables, 'n1', skip_branch=int(outages[b]))
+            try:
+                Vo, info = ho.helm_oracle(c2, mismatch=1e-8, scale=1.0, max_coefficients=60)
+                verdict = 'converged' if Vo is not None else 'diverged'
+            except Exception as e:                                # SuperLU: exactly singular matrix
+                verdict = 'error:' + type(e).__name__
+            verdicts.append({'scenario': int(b), 'branch': int(outages[b]), 'gpu_status': int(st[b]), 'oracle': verdict})
+        res['non_converged'] = {'count': int(len(bad)), 'checked': len(verdicts), 'verdicts': verdicts,
+                                'oracle_also_without_solution': int(sum(v['oracle'] != 'converged' for v in verdicts))}
+        res['non_converged']['same_verdict'] = all(v['oracle'] != 'converged' for v in verdicts)
     return res
 
 

@@ -529,3 +529,80 @@ def test_plan_follows_mutations_of_the_case(hb, capsys):
     assert len(info['switched']) == 0
     dmag, dang = polar_err(V4, Vo)
     assert dmag <= TOL_MAG and dang <= TOL_ANG
+
+
+@pytest.mark.parametrize('name', ['case9', 'case118'])
+def test_per_order_coefficients_match_reference(hb, name):
+    """Intermediate parity: the series coefficients V_i[n] and W_i[n] of every order of
+    the last pass against run.V_complex / run.W recorded from the unmodified reference
+    (oracle/gen_golden.py -> tests/golden/ref_<case>.npz), not only the final voltages."""
+    from helmpy_b200.core.helm import get_plan
+    case = load_case(name)
+    runs, z = ref_outputs(name)
+    ref = z['last_pass_coefficients']                 # run.coefficients[:, :m]: rows 2i / 2i+1 = Re / Im V_i
+    refW = z['last_pass_W']
+    m = ref.shape[1]
+    res = hb.helm_batch(case, [1.0], mismatch=1e-8, max_coefficients=40)
+    assert res.list_coef(0)[-1] == m
+    plan = get_plan(case)
+    V, H = plan.last_series(1, 0, m)
+    _, bt = plan.last_state(1)
+    Vref = (ref[0:2 * case.N:2] + 1j * ref[1:2 * case.N:2]).T          # [m, N]
+    scale = np.maximum(1.0, np.max(np.abs(Vref), axis=1, keepdims=True))
+    assert np.max(np.abs(V - Vref) / scale) < 1e-10
+    pq = bt[0] == 0
+    assert pq.sum() > 0
+    Wref = refW.T[:, pq]
+    wscale = np.maximum(1.0, np.max(np.abs(Wref), axis=1, keepdims=True))
+    assert np.max(np.abs(H[:, pq] - Wref) / wscale) < 1e-9
+
+
+@pytest.mark.parametrize('name,scale', [('case118', 1.05), ('case1354pegase', 0.97)])
+def test_per_order_coefficients_match_oracle(hb, name, scale):
+    """The same per-order check against the oracle at a scale with Q-limit passes."""
+    from helmpy_b200.core.helm import get_plan
+    case = load_case(name)
+    Vo, info = ho.helm_oracle(case, mismatch=1e-8, scale=scale, max_coefficients=40, record=True)
+    last = info['passes'][-1]
+    m = last['m']
+    res = hb.helm_batch(case, [scale], mismatch=1e-8, max_coefficients=40)
+    assert res.list_coef(0) == info['list_coef']
+    plan = get_plan(case)
+    V, H = plan.last_series(1, 0, m)
+    _, bt = plan.last_state(1)
+    Vref = last['V'].T
+    scl = np.maximum(1.0, np.max(np.abs(Vref), axis=1, keepdims=True))
+    assert np.max(np.abs(V - Vref) / scl) < 1e-10
+    pq = bt[0] == 0
+    Wref = last['W'].T[:, pq]
+    wscl = np.maximum(1.0, np.max(np.abs(Wref), axis=1, keepdims=True))
+    assert np.max(np.abs(H[:, pq] - Wref) / wscl) < 1e-9
+
+
+def test_benchmark_path_matches_oracle(hb):
+    """The path bench.py times — case2869pegase, more scenarios than slots (continuous batching with
+    slot refill), > 888 resident so the warp-per-scenario wave solve (k_solve_flat) runs, shared
+    first-pass factors, two-step factorization pipeline — against the oracle on sampled scenarios:
+    status, coefficients per pass, switch count, |dV| and d(angle) <= 1e-8 (reference helm.py:896-985)."""
+    case = load_case('case2869pegase')
+    B, resident = 2304, 1024
+    scales = np.random.default_rng(11).uniform(0.80, 1.05, B)
+    res = hb.helm_batch(case, scales, mismatch=1e-8, max_coefficients=40, max_resident=resident)
+    assert res.converged.all()
+    # samples: scenarios of the first wave of slots, refilled slots, and the tail of the queue
+    idx = np.unique(np.concatenate([np.arange(0, 4), np.arange(resident - 2, resident + 4),
+                                    np.random.default_rng(1).choice(B, 8, replace=False), [B - 1]]))
+    assert len(idx) >= 16
+    worst = (0.0, 0.0)
+    for b in idx:
+        Vo, info = ho.helm_oracle(case, mismatch=1e-8, scale=float(scales[b]), max_coefficients=40)
+        assert Vo is not None
+        assert res.list_coef(b) == info['list_coef'], (b, res.list_coef(b), info['list_coef'])
+        assert res.nswitch[b] == len(info['switched'])
+        dmag, dang = polar_err(res.V[b], Vo)
+        worst = (max(worst[0], dmag), max(worst[1], dang))
+    assert worst[0] <= TOL_MAG and worst[1] <= TOL_ANG, worst
+    # the same scenarios solved alone (CTA solve, private factors, one-step pipeline) agree to rounding
+    small = hb.helm_batch(case, scales[idx], mismatch=1e-8, max_coefficients=40)
+    assert np.array_equal(small.ncoef, res.ncoef[idx])
+    assert np.max(np.abs(small.V - res.V[idx])) < 1e-10
