@@ -2,7 +2,8 @@
 """Benchmark of the HELM + Pade hot path (contract: see the task prompt / DESIGN.md §7).
 
     python bench.py --gpus N --steps K --warmup W            # this build (CUDA)
-    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU arm
+    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU arm: the unmodified reference
+    python bench.py --strong --gpus N                        # BASELINE config 3: 4096 scenarios over N GPUs
 
 A *step* is one pass of the hot path over one batch of synthetic input: B
 load-scaling scenarios of case2869pegase per GPU (scales ~ U[0.80, 1.05],
@@ -14,6 +15,15 @@ C-ABI call (`helm_batch`): scales host->device and voltages device->host inside
 the timed region.  4096 scenarios are resident at a time (7 MB each, 28 GB:
 far beyond the 126 MB L2, so every step streams from HBM); the rest of the batch
 queues on the device and takes over slots as scenarios finish.
+
+Parity gate: scenarios of the last timed step are re-solved with the oracle
+(oracle/helm_oracle.py, the checker) and compared — status, coefficients per pass,
+|dV| and d(angle) <= 1e-8; the line carries `parity` and the run fails if it is not met.
+
+CPU arm: the unmodified reference from oracle/_ref (oracle/build_ref.sh copies it there from
+/root/reference; git-ignored, travels to the box), one independent helm() call per host core
+and step, through oracle/ref_shim.py.  Without oracle/_ref the oracle port is timed instead
+(`cpu_baseline.kind` says which).
 """
 import argparse
 import json
@@ -36,6 +46,7 @@ SCALE_LO, SCALE_HI = 0.80, 1.05
 RESIDENT = [4096]
 METRIC = 'converged_power_flow_cases_per_sec'
 UNIT = 'cases/s'
+REF_DIR = os.path.join(REPO, 'oracle', '_ref')
 
 
 def scenario_scales(n, seed):
@@ -43,35 +54,74 @@ def scenario_scales(n, seed):
 
 
 # ------------------------------------------------------------------------------------------
-# CPU arm: the oracle port (the reference is pure Python and cannot travel to the GPU box;
-# oracle/helm_oracle.py restates its algorithm and is pinned to it, see tests/test_oracle.py)
+# CPU side.  Two implementations, both only ever timed or used as the checker:
+#   'reference'  the unmodified HELMpy package in oracle/_ref, through oracle/ref_shim.py
+#   'port'       oracle/helm_oracle.py, the numpy/scipy restatement pinned to it (tests/test_oracle.py)
 # ------------------------------------------------------------------------------------------
-def _cpu_worker(args):
+_worker_state = {}
+
+
+def _worker_init():
     os.environ['OPENBLAS_NUM_THREADS'] = '1'
     os.environ['OMP_NUM_THREADS'] = '1'
-    from common import load_case
-    from oracle import helm_oracle as ho
-    scales = args
-    case = load_case(CASE)
+    os.environ['MKL_NUM_THREADS'] = '1'
+
+
+def _port_worker(scales):
+    """Oracle port on a list of scales -> list of (V or None, list_coef)."""
+    if 'port_case' not in _worker_state:
+        from common import load_case
+        from oracle import helm_oracle as ho
+        _worker_state['port_case'] = load_case(CASE)
+        _worker_state['ho'] = ho
+    ho, case = _worker_state['ho'], _worker_state['port_case']
+    out = []
+    for s in scales:
+        V, info = ho.helm_oracle(case, mismatch=MISMATCH, scale=float(s), max_coefficients=MAX_COEF)
+        out.append((V, info['list_coef']))
+    return out
+
+
+def _ref_worker(scales):
+    """The unmodified reference's helm() on a list of scales -> number converged."""
+    if 'ref_case' not in _worker_state:
+        os.environ['HELMPY_REFERENCE_ROOT'] = REF_DIR
+        from oracle import ref_shim
+        _worker_state['ref_shim'] = ref_shim
+        _worker_state['ref_case'] = ref_shim.ref_case(os.path.join(REF_DIR, 'data', 'cases', CASE + '.xlsx'))
+    rs, case = _worker_state['ref_shim'], _worker_state['ref_case']
     nconv = 0
     for s in scales:
-        V, _ = ho.helm_oracle(case, mismatch=MISMATCH, scale=float(s), max_coefficients=MAX_COEF)
+        V, _ = rs.ref_helm(case, mismatch=MISMATCH, scale=float(s), max_coefficients=MAX_COEF)
         nconv += V is not None
     return nconv
 
 
-def cpu_cases_per_sec(n_scen, cores, seed=0):
-    """Solve n_scen scenarios with the oracle on `cores` processes; return (cases/s, elapsed)."""
-    import multiprocessing as mp
-    scales = scenario_scales(n_scen, seed)
-    chunks = [c for c in np.array_split(scales, cores) if len(c)]
-    ctx = mp.get_context('spawn')
-    with ctx.Pool(len(chunks)) as pool:
-        pool.map(_cpu_worker, [c[:1] for c in chunks])          # warm-up: imports, case load
+def reference_available():
+    return os.path.isdir(os.path.join(REF_DIR, 'helmpy', 'core')) and \
+        os.path.exists(os.path.join(REF_DIR, 'data', 'cases', CASE + '.xlsx'))
+
+
+class CpuPool:
+    """Persistent process pool: one worker per host core, imports and case loading paid once."""
+
+    def __init__(self, cores):
+        import multiprocessing as mp
+        self.cores = cores
+        self.pool = mp.get_context('spawn').Pool(cores, initializer=_worker_init)
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+    def run(self, fn, scales):
+        chunks = [c for c in np.array_split(np.asarray(scales, dtype=np.float64), self.cores) if len(c)]
         t0 = time.perf_counter()
-        nconv = sum(pool.map(_cpu_worker, chunks))
-        dt = time.perf_counter() - t0
-    return nconv / dt, dt, nconv
+        parts = self.pool.map(fn, chunks)
+        return parts, time.perf_counter() - t0
+
+    def warm(self, fn):
+        self.pool.map(fn, [np.array([1.0])[:0]] * self.cores)     # imports + case load, no solve
 
 
 def run_reference(args):
@@ -79,23 +129,38 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    per_step = 4 * cores          # ~3-4 s of the oracle port per step on every core
+    pool = CpuPool(cores)
+    use_ref = reference_available()
+    fn = _ref_worker if use_ref else _port_worker
+    per_step = cores if use_ref else 4 * cores      # reference: one helm() call per core and step (~6-10 s)
+    pool.warm(fn)
     vals = []
     for it in range(args.warmup + args.steps):
-        v, dt, nconv = cpu_cases_per_sec(per_step, cores, seed=it)
+        parts, dt = pool.run(fn, scenario_scales(per_step, it))
+        nconv = sum(parts) if use_ref else sum(v is not None for p in parts for v, _ in p)
         if it >= args.warmup:
-            vals.append((v, dt))
+            vals.append((nconv / dt, dt))
+    # the other implementation on one bounded sample, for the record
+    other = None
+    if use_ref:
+        pool.warm(_port_worker)
+        parts, dt = pool.run(_port_worker, scenario_scales(4 * cores, 0))
+        other = {'kind': 'port', 'value': sum(v is not None for p in parts for v, _ in p) / dt, 'unit': UNIT,
+                 'sample': '%d scenarios, %d processes, %.1f s' % (4 * cores, cores, dt)}
+    pool.close()
     value = float(np.mean([v for v, _ in vals]))
     ms = float(np.mean([dt for _, dt in vals])) * 1e3
+    kind = 'reference' if use_ref else 'port'
+    what = ('unmodified HELMpy helm() from oracle/_ref (pure Python + SuperLU + LAPACK), one call per process'
+            if use_ref else 'numpy/scipy oracle port of the reference algorithm (oracle/_ref not built)')
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': workload_config(args.batch, args.gpus),      # the CUDA arm's workload; each step times a bounded sample of it
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                         'sample': '%d scenarios per step over %d processes (numpy/scipy oracle port of '
-                                   'the reference algorithm; the reference itself is pure Python and is '
-                                   '~12x slower per case, DESIGN.md §7)' % (per_step, cores)},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': kind,
+                         'sample': '%d scenarios per step over %d processes; %s' % (per_step, cores, what),
+                         'other_implementation': other},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line), flush=True)
@@ -177,6 +242,29 @@ def load_peaks():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
+def parity_check(scales, V, status, ncoef, oracle_results):
+    """GPU results of some scenarios against the oracle's (V or None, list_coef) for the same scales."""
+    max_dmag = max_dang = 0.0
+    bad = []
+    for b, (Vo, lc) in enumerate(oracle_results):
+        conv = int(status[b]) == 2
+        if conv != (Vo is not None):
+            bad.append({'scenario': b, 'scale': float(scales[b]), 'why': 'status %d vs oracle %s' % (status[b], 'converged' if Vo is not None else 'none')})
+            continue
+        if Vo is None:
+            continue
+        mine = [int(x) for x in ncoef[b][ncoef[b] > 0]]
+        if mine != [int(x) for x in lc]:
+            bad.append({'scenario': b, 'scale': float(scales[b]), 'why': 'list_coef %s vs %s' % (mine, lc)})
+        dmag = float(np.max(np.abs(np.abs(V[b]) - np.abs(Vo))))
+        dang = float(np.max(np.abs(np.angle(V[b]) - np.angle(Vo))))
+        max_dmag, max_dang = max(max_dmag, dmag), max(max_dang, dang)
+    ok = not bad and max_dmag <= 1e-8 and max_dang <= 1e-8
+    return {'checked': len(oracle_results), 'max_dmag': max_dmag, 'max_dang': max_dang, 'tolerance': 1e-8,
+            'status_and_list_coef_equal': not bad, 'mismatches': bad[:4], 'ok': ok,
+            'against': 'oracle/helm_oracle.py (pinned to the reference, tests/test_oracle.py) on scenarios of the last timed step'}
+
+
 def run_cuda(args):
     import torch
     import torch.distributed as dist
@@ -202,17 +290,24 @@ def run_cuda(args):
     plan = get_plan(case)
     prm = _lib.Plan.make_params(MISMATCH, MAX_COEF, True, args.group, True, 0, args.resident)
     ws = torch.empty(plan.workspace_bytes(B, prm), dtype=torch.uint8, device=dev)
-    d_vout = torch.zeros(B, N, dtype=torch.complex128, device=dev)
+    # results are double-buffered: while step k+1 solves into one buffer, the gather of step k (the
+    # path's only exchange, NCCL over NVLink) runs from the other on its own stream
+    nbuf = 2 if world > 1 else 1
+    d_vout = [torch.zeros(B, N, dtype=torch.complex128, device=dev) for _ in range(nbuf)]
     d_status = torch.zeros(B, dtype=torch.int32, device=dev)
     d_ncoef = torch.zeros(B, _lib.HELM_MAX_PASSES, dtype=torch.int32, device=dev)
     d_nsw = torch.zeros(B, dtype=torch.int32, device=dev)
     gathered = None
     if world > 1:
-        gathered = torch.empty(world, B, N, 2, dtype=torch.float64, device=dev)
+        gathered = [torch.empty(world * B, N, 2, dtype=torch.float64, device=dev) for _ in range(nbuf)]
     stream = torch.cuda.Stream(device=dev)
+    comm = torch.cuda.Stream(device=dev)
+    ev_solved = [torch.cuda.Event() for _ in range(nbuf)]
+    ev_gathered = [torch.cuda.Event() for _ in range(nbuf)]
     total_steps = args.warmup + args.steps
     # every step gets fresh scenarios (rank- and step-dependent seed), resident in HBM beforehand
-    d_scales = [torch.from_numpy(scenario_scales(B, 1000 * rank + it)).to(dev) for it in range(total_steps)]
+    seeds = [1000 * rank + it for it in range(total_steps)]
+    d_scales = [torch.from_numpy(scenario_scales(B, sd)).to(dev) for sd in seeds]
     torch.cuda.synchronize()
 
     launches = 0
@@ -221,15 +316,22 @@ def run_cuda(args):
     kernel_ms = 0.0
 
     def one_step(it):
-        nonlocal launches, solves, conv_total, kernel_ms
+        k = it % nbuf
         with torch.cuda.stream(stream):
-            st = plan.solve_device(d_scales[it], prm, ws, d_vout, d_status, d_ncoef, d_nsw, stream.cuda_stream)
-            if world > 1:   # the path's only exchange: final gather of the voltages (NCCL over NVLink)
-                dist.all_gather_into_tensor(gathered.view(world * B, N, 2), torch.view_as_real(d_vout))
+            if world > 1:
+                stream.wait_event(ev_gathered[k])       # the gather that last read this buffer is done
+            st = plan.solve_device(d_scales[it], prm, ws, d_vout[k], d_status, d_ncoef, d_nsw, stream.cuda_stream)
+            ev_solved[k].record(stream)
+        if world > 1:
+            with torch.cuda.stream(comm):
+                comm.wait_event(ev_solved[k])
+                dist.all_gather_into_tensor(gathered[k], torch.view_as_real(d_vout[k]))
+                ev_gathered[k].record(comm)
         return st
 
     def barrier():
         stream.synchronize()
+        comm.synchronize()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -249,7 +351,9 @@ def run_cuda(args):
         kernel_ms += st['ms_total']
         conv_total += int((d_status == _lib.ST_CONVERGED).sum().item())
         solves += int(torch.clamp(d_ncoef - 1, min=0).sum().item())
-    ev1.record(stream)
+    with torch.cuda.stream(stream):
+        stream.wait_stream(comm)                        # the last gather is part of the timed region
+        ev1.record(stream)
     barrier()
     elapsed_ms = ev0.elapsed_time(ev1)
     if rank == 0:
@@ -266,6 +370,18 @@ def run_cuda(args):
         conv_all, launches_all, solves_all = float(conv_total), float(launches), float(solves)
     value = conv_all / (elapsed_ms * 1e-3)
 
+    # results of the last timed step on rank 0, kept for the parity gate
+    last = (total_steps - 1) % nbuf
+    n_par = min(B, args.parity if args.parity > 0 else (12 * (os.cpu_count() or 1) if world == 1 else 8))
+    par_scales = scenario_scales(B, seeds[-1])[:n_par]
+    par_V = d_vout[last][:n_par].cpu().numpy()
+    par_status = d_status[:n_par].cpu().numpy()
+    par_ncoef = d_ncoef[:n_par].cpu().numpy()
+    if world > 1 and rank == 0:
+        # the gathered copy of this rank's block must be the block itself
+        own = torch.view_as_complex(gathered[last][rank * B: rank * B + n_par])
+        assert torch.equal(own, d_vout[last][:n_par]), 'gathered voltages differ from the solved ones'
+
     # ---- e2e: host buffers through the public API, H2D + D2H inside the timed region -------
     host_scales = [scenario_scales(B, 5000 + 1000 * rank + it) for it in range(2)]
     res = None
@@ -276,7 +392,7 @@ def run_cuda(args):
         dist.barrier()
     t0 = time.perf_counter()
     e2e_conv = 0
-    e2e_steps = max(1, min(args.steps, 2))
+    e2e_steps = max(1, args.steps)
     for it in range(e2e_steps):
         res = helmpy_b200.helm_batch(case, host_scales[it % 2], mismatch=MISMATCH, max_coefficients=MAX_COEF,
                                      group=args.group, max_resident=args.resident)
@@ -300,15 +416,17 @@ def run_cuda(args):
     if rank == 0:
         os.environ['HELM_B200_PROFILE'] = '1'
         with torch.cuda.stream(stream):
-            stp = plan.solve_device(d_scales[-1], prm, ws, d_vout, d_status, d_ncoef, d_nsw, stream.cuda_stream)
+            stp = plan.solve_device(d_scales[-1], prm, ws, d_vout[last], d_status, d_ncoef, d_nsw, stream.cuda_stream)
         stream.synchronize()
         os.environ.pop('HELM_B200_PROFILE', None)
         nc = d_ncoef.cpu().numpy()
         info = plan.info
-        kernels = roofline_model(info, nc, stp, N)
+        kernels = roofline_model(info, nc, stp, N, shared_first_pass=(min(B, args.resident) >= 64))
         peak, how = load_peaks()
         for k in kernels.values():
             k['frac_of_hbm_peak'] = k['gbs'] / peak
+            if 'gbs_8d' in k:
+                k['frac_8d'] = k['gbs_8d'] / peak
         # dominant kernel = the largest of the main branch (solve -> eps -> rhs_conv is the critical
         # path of a step; the factorization runs beside it in the side branch, two steps deep)
         dom = max((kernels[k] for k in ('solve', 'rhs_conv', 'eps')), key=lambda k: k['ms'])
@@ -316,6 +434,7 @@ def run_cuda(args):
         roof = {'bound': 'hbm', 'kernel': dom['name'], 'achieved': dom['gbs'], 'peak': peak, 'unit': 'GB/s',
                 'frac': dom['gbs'] / peak, 'traffic': tr['dram_bytes'] if tr else None,
                 'traffic_source': tr, 'peak_source': how,
+                'bytes_model': dom['model'],
                 'share_of_step': dom['ms'] / max(1e-9, sum(kernels[k]['ms'] for k in ('solve', 'rhs_conv', 'eps'))),
                 'share_of_step_note': 'share of the main-branch kernel time (solve + eps + rhs_conv); factorization overlaps in the side branch',
                 'launches': dom['launches'], 'avg_launch_ms': dom['ms'] / max(1, dom['launches']),
@@ -331,15 +450,34 @@ def run_cuda(args):
             r1 = helmpy_b200.helm_batch(case, [1.0], mismatch=MISMATCH, max_coefficients=MAX_COEF)
             ts.append(r1.stats['ms_total'])
         single_ms = float(np.median(ts))
+    rc = 0
     if rank == 0:
+        # ---- CPU leg: parity gate (oracle port as the checker) and the CPU baseline -------------
+        cores = os.cpu_count() or 1
+        pool = CpuPool(min(cores, max(1, n_par)))
+        pool.warm(_port_worker)
+        parts, dt_port = pool.run(_port_worker, par_scales)
+        oracle_results = [r for p in parts for r in p]
+        parity = parity_check(par_scales, par_V, par_status, par_ncoef, oracle_results)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            n = 12 * cores                # bounded sample: ~10 s of wall time on all host cores
-            v, dt, nconv = cpu_cases_per_sec(n, cores, seed=0)
-            cpu = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                   'sample': '%d scenarios of the same workload (seed 0), %d processes, %.1f s; numpy/scipy '
-                             'oracle port (oracle/helm_oracle.py)' % (n, cores, dt)}
+            port_v = sum(v is not None for v, _ in oracle_results) / dt_port
+            port = {'kind': 'port', 'value': port_v, 'unit': UNIT, 'cores': pool.cores,
+                    'sample': '%d scenarios of the last timed step, %d processes, %.1f s; numpy/scipy oracle '
+                              'port (oracle/helm_oracle.py) — the same runs are the parity check' % (n_par, pool.cores, dt_port)}
+            if reference_available():
+                pool.close()
+                pool = CpuPool(cores)
+                pool.warm(_ref_worker)
+                n_ref = 2 * cores             # two unmodified-reference helm() calls per core: ~15-25 s
+                parts, dt_ref = pool.run(_ref_worker, par_scales[:n_ref] if n_par >= n_ref else scenario_scales(n_ref, seeds[-1]))
+                cpu = {'value': sum(parts) / dt_ref, 'unit': UNIT, 'cores': cores, 'kind': 'reference',
+                       'sample': '%d scenarios of the last timed step, %d processes, %.1f s; unmodified HELMpy helm() '
+                                 'from oracle/_ref (pure Python + SuperLU + LAPACK)' % (n_ref, cores, dt_ref),
+                       'other_implementation': port}
+            else:
+                cpu = port
+        pool.close()
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True,
@@ -349,24 +487,44 @@ def run_cuda(args):
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'steps': e2e_steps},
             'gpu_launches': int(launches_all),
+            'parity': parity,
             'roofline': roof, 'roofline_kernels': kernels, 'cpu_baseline': cpu,
             'single_case_ms': single_ms, 'scenario_orders': int(solves_all), 'converged': int(conv_all),
             'group': prm.group, 'device_ms_sum_rank0': kernel_ms,
+            'gather': ('all_gather_into_tensor of the voltages on a second stream, double-buffered: the gather of '
+                       'step k overlaps the solve of step k+1; the last one is inside the timed region') if world > 1 else None,
         }
         print(json.dumps(line), flush=True)
+        if not parity['ok']:
+            print('PARITY GATE FAILED: %s' % json.dumps(parity), file=sys.stderr, flush=True)
+            rc = 1
     if world > 1:
         dist.destroy_process_group()
+    if rc:
+        sys.exit(rc)
 
 
-def roofline_model(info, ncoef, stats, N):
-    """Algorithmic HBM bytes per kernel / measured kernel time.
+def roofline_model(info, ncoef, stats, N, shared_first_pass=True):
+    """Algorithmic HBM bytes per kernel / measured kernel time, two byte models each.
 
-    ncoef[b, p] = coefficients of scenario b in pass p.  A pass with m coefficients
-    runs orders j = 1..m-1.
+    ncoef[b, p] = coefficients of scenario b in pass p.  A pass with m coefficients runs orders
+    j = 1..m-1.  `bytes` / `gbs` follow SURVEY §8(d) for the solve (factor bytes divided by the number
+    of scenarios sharing a factorization: first-pass solves read ONE shared, L2-resident copy, so only
+    the orders of passes >= 2 are charged factor bytes; first-pass factorizations do not run) and the
+    kernel's own algorithm for K1 / K3 (their O(j) history walks are HBM traffic of the algorithm as
+    built: the history does not fit shared memory at 5.8 MB per scenario x 4096 resident).
+    `bytes_8d` / `gbs_8d` are SURVEY §8(d)'s figures, which assume an SMEM-resident history:
+    K1 64 B per bus-order, K3 16 (m + 1) B per bus and check with m = j + 1 terms.
     """
-    m = ncoef[ncoef > 0].astype(np.float64)
+    nz = ncoef > 0
+    m = ncoef[nz].astype(np.float64)
+    first = np.zeros_like(ncoef, dtype=bool)
+    first[:, 0] = True
+    m_first = ncoef[nz & first].astype(np.float64)
+    m_later = ncoef[nz & ~first].astype(np.float64)
     orders = float(np.sum(m - 1))                       # scenario-orders = triangular solves
-    passes = float(len(m))
+    orders_private = float(np.sum(m_later - 1)) if shared_first_pass else orders
+    passes_factored = float(len(m_later)) if shared_first_pass else float(len(m))
     sum_j = float(np.sum((m - 1) * m / 2))              # sum over orders of j
     half = np.floor((m - 1) / 2)
     sum_j_even = float(np.sum(half * (half + 1)))       # sum over the even orders of j
@@ -374,8 +532,9 @@ def roofline_model(info, ncoef, stats, N):
     out = {}
     ms = stats['ms_kernel']
     steps = max(1, stats['steps'])
-    # K2 solve: LU blocks (32 B each) once + rhs read + x write (16 B each per bus)
-    b_solve = orders * (32.0 * nslots + 32.0 * N)
+    # K2 solve: rhs read + x write (16 B each per bus) at every order; LU blocks (32 B each) only
+    # when the scenario reads private factors (passes >= 2 with the shared first-pass factors)
+    b_solve = orders_private * 32.0 * nslots + orders * 32.0 * N
     # K1 k_rhs_conv at order j, per bus (x read, V[j], H[j], rhs written: 64 B at every order):
     #   PV bus: histories V and CC, read j each (32 j).  PQ bus, blocked W recurrence (block 4):
     #   j < 4 or j % 4 == 0: histories V and W read j each (32 j), at a block start also three
@@ -394,14 +553,78 @@ def roofline_model(info, ncoef, stats, N):
     b_pq = float(sum(c * conv_bytes_pq(v) for v, c in zip(um, cnt)))
     b_rhs = b_pq * (N - n_pv) + (32.0 * sum_j + 64.0 * orders) * n_pv
     b_eps = (32.0 * sum_j_even + 64.0 * orders_even) * N
-    # K2f factor: read A blocks + write LU blocks (32 B per slot each way), per pass
-    b_fac = passes * (64.0 + 32.0) * nslots       # assembly (write) + factorization (read, write)
+    b_rhs_8d = 64.0 * N * orders
+    b_eps_8d = (16.0 * sum_j_even + 32.0 * orders_even) * N    # sum over the even orders of 16 (m + 1), m = j + 1 terms
+    # K2f factor: assembly (write) + factorization (read, write), 32 B per slot each, per factorized pass
+    b_fac = passes_factored * (64.0 + 32.0) * nslots
     knames = {'solve': 'k_solve_flat', 'rhs_conv': 'k_rhs_conv', 'eps': 'k_eps', 'factor': 'k_factor_coop'}
+    models = {
+        'solve': 'SURVEY 8(d): 32 B per LU block / R + 32 B per bus, R = scenarios sharing the factors '
+                 '(first-pass orders read one shared copy: charged no factor bytes)',
+        'rhs_conv': 'own algorithm: history walks of the blocked W recurrence and the PV convolutions + 64 B per bus-order',
+        'eps': 'own algorithm: epsilon anti-diagonal read and written at even orders + 64 B per bus',
+        'factor': '96 B per LU block per factorized pass (first passes share one factorization)',
+    }
     for name, b in (('solve', b_solve), ('rhs_conv', b_rhs), ('eps', b_eps), ('factor', b_fac)):
         t = ms.get(name, 0.0)
         out[name] = {'name': knames[name], 'ms': t, 'bytes': b, 'gbs': (b / (t * 1e-3) / 1e9) if t > 0 else 0.0,
-                     'launches': steps}
+                     'launches': steps, 'model': models[name]}
+    for name, b in (('rhs_conv', b_rhs_8d), ('eps', b_eps_8d)):
+        t = out[name]['ms']
+        out[name]['bytes_8d'] = b
+        out[name]['gbs_8d'] = (b / (t * 1e-3) / 1e9) if t > 0 else 0.0
+    out['solve']['orders'] = orders
+    out['solve']['orders_on_shared_first_pass_factors'] = orders - orders_private
     return out
+
+
+# ------------------------------------------------------------------------------------------
+# Strong scaling of BASELINE config 3: 4096 load-scaling scenarios of a case2383wp-size grid
+# (synthetic stand-in, tests/synth.py) over N GPUs through the public sharded call.
+# ------------------------------------------------------------------------------------------
+def run_strong(args):
+    import torch
+    import torch.distributed as dist
+    import synth
+    from helmpy_b200.core.parallel import helm_batch_sharded
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+    os.environ.setdefault('MASTER_PORT', '29533')
+    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+    dist.init_process_group('nccl', device_id=dev, rank=rank, world_size=world)
+    names = ['case1354pegase'] + ['case118'] * 8 + ['case9'] * 9
+    case = synth.tiled_case(names)
+    nscen = args.strong_scenarios
+    kw = dict(mismatch=MISMATCH, max_coefficients=60)
+    ts = []
+    for it in range(args.warmup + args.steps):
+        scales = np.random.default_rng(it).uniform(SCALE_LO, SCALE_HI, nscen)
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        V, st, nc, ns = helm_batch_sharded(case, scales, device=dev, **kw)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        if it >= args.warmup:
+            ts.append((float(dt.item()), int((st == 2).sum())))
+    if rank == 0:
+        dt = float(np.mean([t for t, _ in ts]))
+        conv = float(np.mean([c for _, c in ts]))
+        print(json.dumps({
+            'metric': METRIC, 'value': conv / dt, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic',
+            'config': {'workload': 'BASELINE config 3: %d load-scaling scenarios of a case2383wp-size grid (synthetic: %s, %d buses), '
+                                   'sharded over %d GPUs through helm_batch_sharded (host scales in, host results out on every rank)'
+                                   % (nscen, '+'.join(sorted(set(names))), case.N, world),
+                       'scenarios_total': nscen, 'n_bus': int(case.N)},
+            'converged': conv}), flush=True)
+    dist.destroy_process_group()
 
 
 def main():
@@ -415,11 +638,16 @@ def main():
     ap.add_argument('--group', type=int, default=int(os.environ.get('HELM_BENCH_GROUP', '1')))
     ap.add_argument('--resident', type=int, default=int(os.environ.get('HELM_BENCH_RESIDENT', '4096')),
                     help='scenarios resident on the GPU at once; the rest of the batch queues (continuous batching)')
+    ap.add_argument('--parity', type=int, default=0, help='scenarios of the last timed step checked against the oracle (0: auto)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--strong', action='store_true', help='strong scaling of BASELINE config 3 instead of the headline workload')
+    ap.add_argument('--strong-scenarios', type=int, default=4096)
     args = ap.parse_args()
     RESIDENT[0] = args.resident
     if args.impl == 'reference':
         run_reference(args)
+    elif args.strong:
+        run_strong(args)
     else:
         run_cuda(args)
 

@@ -19,10 +19,24 @@ import sys
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("HELMPY_REFERENCE_ROOT", "/root/reference")
 _REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if _REPO not in sys.path:
     sys.path.insert(0, _REPO)
+# oracle/_ref: the unmodified reference package + grids as copied by oracle/build_ref.sh (git-ignored;
+# it is what travels to the GPU box, where /root/reference does not exist)
+LOCAL_COPY = os.path.join(_REPO, "oracle", "_ref")
+
+
+def _default_root():
+    env = os.environ.get("HELMPY_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/helmpy/core"):
+        return "/root/reference"
+    return LOCAL_COPY
+
+
+REFERENCE_ROOT = _default_root()
 
 
 def available():

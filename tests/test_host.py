@@ -326,16 +326,23 @@ def test_bench_roofline_bytes_match_the_per_order_table():
     N, n_pv, nslots = 1000, 150, 6000
     ncoef = np.array([[23, 25, 29, 0], [17, 0, 0, 0], [5, 7, 0, 0]], dtype=np.int32)
     stats = {'ms_kernel': {'solve': 1.0, 'rhs_conv': 1.0, 'eps': 1.0, 'factor': 1.0}, 'steps': 10}
-    k = bench.roofline_model({'n_slots': nslots, 'n_pv': n_pv}, ncoef, stats, N)
-    solve = conv = eps = fac = 0.0
-    for m in ncoef[ncoef > 0]:
-        fac += (64 + 32) * nslots
-        for j in range(1, int(m)):
-            solve += 32 * nslots + 32 * N
-            i = j & 3
-            pq = (32 * j + (48 if j >= 4 else 0)) if (j < 4 or i == 0) else (16 + 16 * (4 * i - 4))
-            conv += (pq + 64) * (N - n_pv) + (32 * j + 64) * n_pv
-            if j % 2 == 0:
-                eps += (32 * j + 64) * N
-    assert k['solve']['bytes'] == solve and k['factor']['bytes'] == fac
-    assert abs(k['rhs_conv']['bytes'] - conv) < 1e-6 * conv and abs(k['eps']['bytes'] - eps) < 1e-6 * eps
+    for shared in (True, False):
+        k = bench.roofline_model({'n_slots': nslots, 'n_pv': n_pv}, ncoef, stats, N, shared_first_pass=shared)
+        solve = conv = eps = fac = conv8 = eps8 = 0.0
+        for row in ncoef:
+            for pidx, m in enumerate(row[row > 0]):
+                private = not (shared and pidx == 0)        # first passes run on ONE shared factorization (12 nnz / R)
+                if private:
+                    fac += (64 + 32) * nslots
+                for j in range(1, int(m)):
+                    solve += (32 * nslots if private else 0) + 32 * N
+                    i = j & 3
+                    pq = (32 * j + (48 if j >= 4 else 0)) if (j < 4 or i == 0) else (16 + 16 * (4 * i - 4))
+                    conv += (pq + 64) * (N - n_pv) + (32 * j + 64) * n_pv
+                    conv8 += 64 * N                          # x in, rhs out, V and W columns written once
+                    if j % 2 == 0:
+                        eps += (32 * j + 64) * N
+                        eps8 += (16 * (j + 1) + 16) * N      # 16 m N read + 16 N write, m = j + 1 terms
+        assert k['solve']['bytes'] == solve and k['factor']['bytes'] == fac
+        assert k['rhs_conv']['bytes_8d'] == conv8 and k['eps']['bytes_8d'] == eps8
+        assert abs(k['rhs_conv']['bytes'] - conv) < 1e-6 * conv and abs(k['eps']['bytes'] - eps) < 1e-6 * eps

@@ -37,6 +37,18 @@ def _stub_solver(case, scales, outages=None, **kw):
     return r
 
 
+def _stub_device_solver(d_scale, d_V, d_status, d_ncoef, d_nswitch, outages):
+    """Same results as _stub_solver, written into the caller's (CPU) torch buffers the way
+    helm_solve_batch_device writes device memory."""
+    import torch
+    sc = d_scale.numpy().copy()
+    r = _stub_solver(None, sc, outages=outages)
+    d_V.copy_(torch.from_numpy(r.V))
+    d_status.copy_(torch.from_numpy(r.status))
+    d_ncoef.copy_(torch.from_numpy(r.ncoef))
+    d_nswitch.copy_(torch.from_numpy(r.nswitch))
+
+
 def _worker(rank, world, port, n, q):
     import torch.distributed as dist
     os.environ['MASTER_ADDR'] = '127.0.0.1'
@@ -57,6 +69,18 @@ def _worker(rank, world, port, n, q):
     outages = np.arange(n, dtype=np.int32)[::-1].copy()
     V2, st2, _, _ = parallel.helm_batch_sharded(None, None, solve_fn=_stub_solver, outages=outages)
     ok = ok and np.array_equal(V2, _stub_solver(None, np.ones(n), outages=outages).V)
+    # the device-resident path (one all_gather_into_tensor of padded blocks) with CPU tensors
+    import torch
+    for root in (None, 0):
+        out = parallel.helm_batch_sharded(None, scales, device=torch.device('cpu'), device_solver=_stub_device_solver,
+                                          root=root, n_bus=5, outages=outages)
+        if root is not None and rank != root:
+            ok = ok and all(o is None for o in out)
+            continue
+        V3, st3, nc3, ns3 = out
+        ref3 = _stub_solver(None, scales, outages=outages)
+        ok = ok and np.array_equal(V3, ref3.V) and np.array_equal(st3, ref3.status) and np.array_equal(ns3, ref3.nswitch)
+        ok = ok and np.array_equal(nc3, np.concatenate(exp)) and V3.shape == (n, 5) and nc3.shape == (n, 16)
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 
