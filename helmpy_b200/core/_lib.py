@@ -63,7 +63,7 @@ KERNEL_NAMES = ("assemble", "factor", "solve", "rhs_conv", "advance", "qlimit", 
 EXPORTED_SYMBOLS = (
     "helm_last_error", "helm_plan_create", "helm_plan_destroy", "helm_plan_get_info",
     "helm_plan_get_perm", "helm_plan_set_outages", "helm_workspace_bytes", "helm_solve_batch_device",
-    "helm_solve_batch_host", "helm_nr_batch_host", "helm_last_state_host", "helm_last_switches_host", "helm_last_series_host", "helm_last_ploss_host", "helm_debug_factor_solve", "helm_debug_timeline", "helm_measure_peaks", "helm_measure_latencies",
+    "helm_solve_batch_host", "helm_nr_batch_host", "helm_last_state_host", "helm_last_switches_host", "helm_last_series_host", "helm_last_ploss_host", "helm_debug_factor_solve", "helm_debug_solve_time", "helm_debug_timeline", "helm_measure_peaks", "helm_measure_latencies",
     "helm_symbolic_create", "helm_symbolic_destroy", "helm_symbolic_array",
 )
 
@@ -108,6 +108,7 @@ def load():
     lib.helm_last_ploss_host.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     lib.helm_debug_factor_solve.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                             C.c_void_p, C.c_void_p]
+    lib.helm_debug_solve_time.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double)]
     lib.helm_debug_timeline.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
     lib.helm_measure_peaks.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.helm_measure_latencies.argtypes = [C.c_void_p]
@@ -147,7 +148,7 @@ def symbolic_arrays(adj_ptr, adj_idx, bus_type=None):
         for name in ("perm", "iperm", "adj_ptr", "adj_idx", "adj_src", "adj_slot", "lptr", "lcol",
                      "llev_ptr", "urow", "qof", "ulev_ptr", "uptr", "ucol", "dslot", "fptr",
                      "fsrc", "fdst", "fdst_local", "fchunk_row", "fchunk_lpr", "frow_off",
-                     "slot_src", "slot_row", "slot_col", "wave_tab", "smeta", "scm", "solve_chunks"):
+                     "slot_src", "slot_row", "slot_col", "wave_tab", "smeta", "scm", "solve_chunks", "solve_segs", "one_lists"):
             data = C.c_void_p()
             n = C.c_int32()
             rc = lib.helm_symbolic_array(h, name.encode(), C.byref(data), C.byref(n))
@@ -338,6 +339,12 @@ class Plan:
         check(load().helm_last_ploss_host(self.handle, n_scen, int(dsb_method), int(pv_bus_model), _ptr(out)),
               "helm_last_ploss_host")
         return out
+
+    def debug_solve_time(self, kernel=0, ablation=0, reps=50):
+        """Device time (ms) of one triangular solve of one scenario, one kernel alone on the GPU."""
+        ms = C.c_double()
+        check(load().helm_debug_solve_time(self.handle, kernel, ablation, reps, C.byref(ms)), "helm_debug_solve_time")
+        return ms.value
 
     def debug_factor_solve(self, bus_types, rhs, group=1):
         bus_types = np.ascontiguousarray(bus_types, dtype=np.uint8)

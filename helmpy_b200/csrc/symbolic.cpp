@@ -422,6 +422,40 @@ bool build_symbolic(int N, const int32_t *adj_ptr, const int32_t *adj_idx, const
                 S.solve_chunks.push_back(s0);
                 S.solve_chunks.push_back(ns);
             }
+            // segments of the one-CTA solve (k_solve_one): the waves between two ordering points are
+            // independent of each other and are dealt to the warps of the CTA (WIDE segment, a block
+            // barrier after it); a run of consecutive one-wave levels is one THIN segment that a single
+            // warp walks through with warp barriers only.  2 ints per segment: {first wave, waves | thin << 30}.
+            S.solve_segs.clear();
+            {
+                int k = 0;
+                while (k < nwv) {
+                    const bool thin = (S.wave_tab[2 * k + 1] & Symbolic::WAVE_THIN) != 0;
+                    int e = k + 1;
+                    if (thin) {
+                        while (e < nwv && (S.wave_tab[2 * e + 1] & Symbolic::WAVE_THIN)) ++e;
+                    } else {
+                        while (e < nwv && !(S.wave_tab[2 * e + 1] & Symbolic::WAVE_SYNC)) ++e;
+                    }
+                    S.solve_segs.push_back(k);
+                    S.solve_segs.push_back((e - k) | (thin ? (1 << 30) : 0));
+                    k = e;
+                }
+            }
+            // per-warp wave lists of k_solve_one (ONE_WARPS warps): the waves of a WIDE segment are dealt
+            // round-robin, THIN segments go to warp 0.  Layout: [ONE_WARPS + 1 offsets][waves in order].
+            {
+                const int W = Symbolic::ONE_WARPS;
+                std::vector<std::vector<int>> lists(W);
+                for (size_t sgi = 0; sgi + 1 < S.solve_segs.size(); sgi += 2) {
+                    const int first = S.solve_segs[sgi], n = S.solve_segs[sgi + 1] & 0x3FFFFFFF;
+                    const bool thin = (S.solve_segs[sgi + 1] >> 30) != 0;
+                    for (int j = 0; j < n; ++j) lists[thin ? 0 : (j % W)].push_back(first + j);
+                }
+                S.one_lists.assign(W + 1, 0);
+                for (int wq = 0; wq < W; ++wq) S.one_lists[wq + 1] = S.one_lists[wq] + (int)lists[wq].size();
+                for (int wq = 0; wq < W; ++wq) S.one_lists.insert(S.one_lists.end(), lists[wq].begin(), lists[wq].end());
+            }
             if (nwv & 1) { S.wave_tab.push_back(0); S.wave_tab.push_back(0); }   // 16-byte multiple
         }
         // rows without L entries get x = rhs directly: they are the rows of forward level 0 and

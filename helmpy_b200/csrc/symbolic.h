@@ -44,6 +44,10 @@ struct Symbolic {
     std::vector<int> wave_tab, smeta;
     // k_solve_cta: scm = {column, meta} per slot; solve_chunks = 4 ints per chunk {first wave, waves, first slot, slots}
     std::vector<int> scm, solve_chunks;
+    // k_solve_one: 2 ints per segment {first wave, waves | thin << 30} (see symbolic.cpp)
+    std::vector<int> solve_segs;
+    static constexpr int ONE_WARPS = 8;
+    std::vector<int> one_lists;                  // per-warp wave lists of k_solve_one (see symbolic.cpp)
     int n_waves = 0;                             // waves (wave_tab may carry one padding entry)
     static constexpr int SOLVE_CHUNK_SLOTS = 128;
     int n_waves_l = 0;                           // waves of the forward solve (the rest is backward)

@@ -1,0 +1,6 @@
+#!/bin/bash
+python tools/single_case.py
+HELM_B200_LIB=$PWD/helmpy_b200/libhelm_b200_tl.so python tools/step_times.py case2869pegase 1 2>&1 | head -5
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q 2>&1 | tail -3
+python tools/sweep.py case2869pegase 512 1 2>&1 | grep '"case"'
+HELM_B200_ONE_SOLVE=2 python tools/sweep.py case2869pegase 16384 1 profile 2>&1 | grep '"case"' | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms'], d['ms_kernel']['solve'], d['conv'])"
