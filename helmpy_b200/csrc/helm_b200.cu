@@ -2315,6 +2315,11 @@ struct helm_plan {
     cudaStream_t side[MAX_SIDE_DEPTH] = {};          // side branches of consecutive steps (factorization pipeline)
     cudaEvent_t ev_fork = nullptr, ev_join[MAX_SIDE_DEPTH] = {};
     unsigned long long *tl = nullptr;
+    // the instantiated CUDA graph of `poll_every` steps is kept between calls: it is valid as long as every
+    // kernel argument (buffers, sizes, parameters, stream) is the same, which `graph_key` records
+    cudaGraphExec_t gexec = nullptr;
+    cudaGraph_t graph = nullptr;
+    std::vector<unsigned long long> graph_key;
     int *d_outage = nullptr;      // pending N-1 list for the next solve (helm_plan_set_outages)
     int outage_n = 0;
     int last_B = 0, last_G = 0, last_maxcoef = 0, last_resident = 0, last_dsb = 0, last_pv = 0, last_rec = 0;   // layout of the last host-buffer solve
@@ -2845,6 +2850,8 @@ void helm_plan_destroy(helm_plan *pl) {
     if (pl->h_pinned) cudaFreeHost(pl->h_pinned);
     if (pl->h_vout_pinned) cudaFreeHost(pl->h_vout_pinned);
     if (pl->d_outage) cudaFree(pl->d_outage);
+    if (pl->gexec) cudaGraphExecDestroy(pl->gexec);
+    if (pl->graph) cudaGraphDestroy(pl->graph);
     if (pl->stream) cudaStreamDestroy(pl->stream);
     for (int k = 0; k < MAX_SIDE_DEPTH; ++k) {
         if (pl->side[k]) cudaStreamDestroy(pl->side[k]);
@@ -2928,7 +2935,9 @@ int helm_solve_batch_device(helm_plan *pl, int32_t B, const double *d_scale, con
     // steps per graph launch / per poll: a multiple of depth * (depth + 1) so that list and stream
     // indices repeat from one graph launch to the next
     const int cyc = depth * (depth + 1);
-    int poll_every = prm->poll_every > 0 ? prm->poll_every : (L.Bp < 256 ? 4 : 12);
+    // steps per graph launch and host poll: steps after the last scenario has ended only launch kernels
+    // that return at once (~10 us per step), a poll costs a stream synchronisation
+    int poll_every = prm->poll_every > 0 ? prm->poll_every : 12;
     poll_every = (poll_every + cyc - 1) / cyc * cyc;
     if (!pl->h_pinned) CUDA_TRY(cudaMallocHost((void **)&pl->h_pinned, 64));
 
@@ -2995,13 +3004,28 @@ int helm_solve_batch_device(helm_plan *pl, int32_t B, const double *d_scale, con
     auto launch_batch = [&](long first, int count) {
         for (int rep = 0; rep < count; ++rep) launch_step(L.G, p, w, ctx, seq, first + rep, rep == count - 1);
     };
-    cudaGraph_t graph = nullptr;
     cudaGraphExec_t gexec = nullptr;
     if (use_graph) {
-        CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        launch_batch(0, poll_every);
-        CUDA_TRY(cudaStreamEndCapture(st, &graph));
-        CUDA_TRY(cudaGraphInstantiate(&gexec, graph, 0));
+        auto u = [](const void *ptr) { return (unsigned long long)(uintptr_t)ptr; };
+        unsigned long long mm;
+        memcpy(&mm, &prm->mismatch, sizeof(mm));
+        const std::vector<unsigned long long> key = {
+            u(d_ws), (unsigned long long)ws_bytes, (unsigned long long)B, u(d_scale), u(d_vout), u(d_status), u(d_ncoef), u(d_nswitch),
+            u(st), u(w.outage_in), u(w.lu_shared), u(w.lu_il), u(w.tl), mm, (unsigned long long)prm->max_coefficients,
+            (unsigned long long)prm->enforce_q_limits, (unsigned long long)L.G, (unsigned long long)L.ngroups,
+            (unsigned long long)prm->pv_bus_model, (unsigned long long)prm->dsb_method, (unsigned long long)prm->dsb_model,
+            (unsigned long long)prm->record_switches, (unsigned long long)depth, (unsigned long long)poll_every,
+            (unsigned long long)L.total, (unsigned long long)p.use_one_solve, (unsigned long long)p.cta_solve_max_groups};
+        if (!pl->gexec || pl->graph_key != key) {
+            if (pl->gexec) { cudaGraphExecDestroy(pl->gexec); pl->gexec = nullptr; }
+            if (pl->graph) { cudaGraphDestroy(pl->graph); pl->graph = nullptr; }
+            CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            launch_batch(0, poll_every);
+            CUDA_TRY(cudaStreamEndCapture(st, &pl->graph));
+            CUDA_TRY(cudaGraphInstantiate(&pl->gexec, pl->graph, 0));
+            pl->graph_key = key;
+        }
+        gexec = pl->gexec;
     }
     std::vector<cudaEvent_t> pev;
     if (profile) {
@@ -3035,8 +3059,6 @@ int helm_solve_batch_device(helm_plan *pl, int32_t B, const double *d_scale, con
     cudaEventDestroy(ev0);
     cudaEventDestroy(ev1);
     for (auto &e : pev) cudaEventDestroy(e);
-    if (gexec) cudaGraphExecDestroy(gexec);
-    if (graph) cudaGraphDestroy(graph);
     CUDA_TRY(cudaGetLastError());
     if (stats) *stats = local;
     return HELM_OK;
