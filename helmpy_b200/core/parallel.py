@@ -111,7 +111,10 @@ def _sharded_device(case, scales, outages, device, root, kw, device_solver=None,
                 'ncoef': torch.zeros(nmax, MAXP, dtype=torch.int32, device=device),
                 'gV': torch.empty(world * nmax, N, 2, dtype=torch.float64, device=device),
                 'gI': torch.empty(world * (2 + MAXP), nmax, dtype=torch.int32, device=device),
-                'ws': None}
+                'ws': None,
+                # the solve replays a captured CUDA graph: it needs a stream of its own (capture is not
+                # allowed on the legacy default stream)
+                'stream': torch.cuda.Stream(device) if is_cuda else None}
         holder._shard_bufs = bufs
     ints = bufs['ints']
     if nloc:
@@ -128,8 +131,12 @@ def _sharded_device(case, scales, outages, device, root, kw, device_solver=None,
             if ob is not None:
                 _lib.check(_lib.load().helm_plan_set_outages(plan.handle, nloc, ob.ctypes.data_as(C.c_void_p)),
                            "helm_plan_set_outages")
-            plan.solve_device(bufs['scale'][:nloc], prm, bufs['ws'], bufs['V'][:nloc], ints[0, :nloc],
-                              bufs['ncoef'][:nloc], ints[1, :nloc], torch.cuda.current_stream(device).cuda_stream)
+            st = bufs['stream']
+            st.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(st):
+                plan.solve_device(bufs['scale'][:nloc], prm, bufs['ws'], bufs['V'][:nloc], ints[0, :nloc],
+                                  bufs['ncoef'][:nloc], ints[1, :nloc], st.cuda_stream)
+            torch.cuda.current_stream(device).wait_stream(st)
         ints[2:, :nloc].copy_(bufs['ncoef'][:nloc].t())
     dist.all_gather_into_tensor(bufs['gV'], torch.view_as_real(bufs['V']))
     dist.all_gather_into_tensor(bufs['gI'], ints)

@@ -71,7 +71,7 @@ struct PlanDev {
     const int *br_f, *br_t, *br_a, *br_p;   // br_a[4b..]: adjacency entries (f,t),(t,f),(f,f),(t,t); br_p[2b..]: phase entries
     const double *br_val;                   // [10b..]: y, sh_f, sh_t, ph_ft, ph_tf (complex)
     const int *fptr, *fsrc, *fdst, *fdstl, *qof;
-    const int *fchunk_row, *fchunk_lpr, *frow_off;
+    const int *fchunk_row, *fchunk_lpr, *frow_off, *flev_chunk;
     int use_coop_factor;
     int max_row_blocks, nfchunks, cap_upd, cap_ent, cap_rowblk;
     const int2 *wave_tab;
@@ -117,6 +117,7 @@ struct WorkDev {
     int parity;                       // list of the current step: step % (depth + 1) (host-set per launch)
     int depth;                        // steps a factorization may take (side-branch pipeline depth)
     int skip_asm;                     // k_factor_coop: the LU slots already hold the matrix (Newton-Raphson Jacobian)
+    int factor_cta;                   // k_factor_coop: the warps of a CTA share one scenario (few scenarios: latency path)
     int *out_status, *out_ncoef, *out_nswitch;   // per-scenario outputs, written when a scenario ends
     unsigned char *btype;             // [group][N][G]
     double *Qg, *VVant;               // [group][N][G]
@@ -495,36 +496,9 @@ __host__ __device__ inline size_t factor_smem_per_warp(int cap_upd, int cap_ent,
 // memory-level parallelism.  Phase 2: each row is eliminated by a sub-warp of `lpr` lanes from
 // shared memory only; the updates of one L entry have distinct destinations and are spread over
 // the lanes, only the multiplier chain is serial.  Phase 3: rows are written back.
-template <int WPB>
-__global__ void __launch_bounds__(WPB * 32) k_factor_coop(PlanDev p, WorkDev w) {
-    TL_SCOPE(w, 1);
-    extern __shared__ double2 smem_f[];
-    const int wib = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const int nfact = w.fact_count[w.parity];
-  for (int fi = blockIdx.x * WPB + wib; fi < nfact; fi += gridDim.x * WPB) {
-    const int grp = w.fact_list[(size_t)w.parity * w.ngroups + fi];
-    if (w.s_status[grp] != ST_ACTIVE) continue;             // G = 1: warp-uniform
-    // assembly of A by the same warp (no separate kernel in front: the factorization starts at the
-    // beginning of the step, while the main branch's solve is being dispatched)
-    if (!w.skip_asm) {
-        if (w.g_flags[grp] & GF_NEWSCEN) {
-            asm_reset<1>(p, w, grp, lane, 32);
-            __syncwarp();
-        }
-        if (uses_shared_lu(w, grp)) continue;               // first pass: the shared factors are used
-        for (int slot = lane; slot < p.nslots; slot += 32) asm_slot<1>(p, w, grp, slot, 0);
-        __syncwarp();
-    }
-    double2 *lu = w.lu + (size_t)grp * p.nslots * 2;
-    char *base = (char *)smem_f + (size_t)wib * factor_smem_per_warp(p.cap_upd, p.cap_ent, p.cap_rowblk);
-    double2 *sSrc = (double2 *)base;
-    double2 *sDk = sSrc + (size_t)p.cap_upd * 2;
-    double2 *sRow = sDk + (size_t)p.cap_ent * 2;
-    int *sDl = (int *)(sRow + (size_t)p.cap_rowblk * 2);
-    int *sUp = sDl + (p.cap_upd + 3) / 4 * 4;
-    bool singular = false;
-    for (int c = 0; c < p.nfchunks; ++c) {
+// one chunk of the factorization of scenario slot `grp` by one warp (see k_factor_coop)
+__device__ __forceinline__ void factor_chunk(const PlanDev &p, const WorkDev &w, double2 *lu, int grp, int c, int lane,
+                                             double2 *sSrc, double2 *sDk, double2 *sRow, int *sDl, int *sUp, bool &singular) {
         const int r0 = __ldg(p.fchunk_row + c), r1 = __ldg(p.fchunk_row + c + 1);
         const int lpr = __ldg(p.fchunk_lpr + c);
         if (lpr == 0) {                                     // rows without L entries: invert the pivot
@@ -538,7 +512,7 @@ __global__ void __launch_bounds__(WPB * 32) k_factor_coop(PlanDev p, WorkDev w) 
                 st_il(p, w, grp, (int)dd, make_double2(d.d * inv, -d.b * inv), make_double2(-d.c * inv, d.a * inv));
             }
             __syncwarp();
-            continue;
+            return;
         }
         const int e_base = __ldg(p.lptr + r0), e_end = __ldg(p.lptr + r1);
         const int u_base = __ldg(p.fptr + e_base), u_end = __ldg(p.fptr + e_end);
@@ -623,7 +597,79 @@ __global__ void __launch_bounds__(WPB * 32) k_factor_coop(PlanDev p, WorkDev w) 
             }
         }
         __syncwarp();
+}
+
+template <int WPB>
+__global__ void __launch_bounds__(WPB * 32) k_factor_coop(PlanDev p, WorkDev w) {
+    TL_SCOPE(w, 1);
+    extern __shared__ double2 smem_f[];
+    const int wib = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int nfact = w.fact_count[w.parity];
+    char *base = (char *)smem_f + (size_t)wib * factor_smem_per_warp(p.cap_upd, p.cap_ent, p.cap_rowblk);
+    double2 *sSrc = (double2 *)base;
+    double2 *sDk = sSrc + (size_t)p.cap_upd * 2;
+    double2 *sRow = sDk + (size_t)p.cap_ent * 2;
+    int *sDl = (int *)(sRow + (size_t)p.cap_rowblk * 2);
+    int *sUp = sDl + (p.cap_upd + 3) / 4 * 4;
+  if (w.factor_cta) {
+    // Few scenarios (the single-case path): the WPB warps of a CTA share ONE scenario.  The chunks of a
+    // level are independent of each other and are dealt to the warps; a block barrier per level.
+    for (int fi = blockIdx.x; fi < nfact; fi += gridDim.x) {
+        const int grp = w.fact_list[(size_t)w.parity * w.ngroups + fi];
+        if (w.s_status[grp] != ST_ACTIVE) continue;         // CTA-uniform
+        if (!w.skip_asm) {
+            if (w.g_flags[grp] & GF_NEWSCEN) {
+                asm_reset<1>(p, w, grp, threadIdx.x, WPB * 32);
+                __syncthreads();
+            }
+            if (uses_shared_lu(w, grp)) continue;
+            for (int slot = threadIdx.x; slot < p.nslots; slot += WPB * 32) asm_slot<1>(p, w, grp, slot, 0);
+        }
+        __syncthreads();
+        double2 *lu = w.lu + (size_t)grp * p.nslots * 2;
+        bool singular = false;
+        for (int l = 0; l < p.nLlev; ++l) {
+            const int c0 = __ldg(p.flev_chunk + l), c1 = __ldg(p.flev_chunk + l + 1);
+            if (c1 - c0 == 1 && __ldg(p.fchunk_lpr + c0) == 0) {
+                // rows without L entries (level 0, half of the grid): pivots inverted by the whole CTA
+                const int r0 = __ldg(p.fchunk_row + c0), r1 = __ldg(p.fchunk_row + c0 + 1);
+                for (int r = r0 + (int)threadIdx.x; r < r1; r += WPB * 32) {
+                    const size_t dd = (size_t)__ldg(p.dslot + r);
+                    const Blk d = ldblk(lu, dd);
+                    double det = d.a * d.d - d.b * d.c;
+                    if (pivot_singular(d, det, bnorm2(d))) { singular = true; det = 1.0; }
+                    const double inv = 1.0 / det;
+                    stblk(lu, dd, Blk{d.d * inv, -d.b * inv, -d.c * inv, d.a * inv});
+                    st_il(p, w, grp, (int)dd, make_double2(d.d * inv, -d.b * inv), make_double2(-d.c * inv, d.a * inv));
+                }
+            } else {
+                for (int c = c0 + wib; c < c1; c += WPB) factor_chunk(p, w, lu, grp, c, lane, sSrc, sDk, sRow, sDl, sUp, singular);
+            }
+            __syncthreads();
+        }
+        if (__syncthreads_or(singular) && threadIdx.x == 0) w.s_status[grp] = ST_SINGULAR;
+        __syncthreads();
     }
+    return;
+  }
+  for (int fi = blockIdx.x * WPB + wib; fi < nfact; fi += gridDim.x * WPB) {
+    const int grp = w.fact_list[(size_t)w.parity * w.ngroups + fi];
+    if (w.s_status[grp] != ST_ACTIVE) continue;             // G = 1: warp-uniform
+    // assembly of A by the same warp (no separate kernel in front: the factorization starts at the
+    // beginning of the step, while the main branch's solve is being dispatched)
+    if (!w.skip_asm) {
+        if (w.g_flags[grp] & GF_NEWSCEN) {
+            asm_reset<1>(p, w, grp, lane, 32);
+            __syncwarp();
+        }
+        if (uses_shared_lu(w, grp)) continue;               // first pass: the shared factors are used
+        for (int slot = lane; slot < p.nslots; slot += 32) asm_slot<1>(p, w, grp, slot, 0);
+        __syncwarp();
+    }
+    double2 *lu = w.lu + (size_t)grp * p.nslots * 2;
+    bool singular = false;
+    for (int c = 0; c < p.nfchunks; ++c) factor_chunk(p, w, lu, grp, c, lane, sSrc, sDk, sRow, sDl, sUp, singular);
     if (__any_sync(0xFFFFFFFFu, singular) && lane == 0) w.s_status[grp] = ST_SINGULAR;
     __syncwarp();
   }
@@ -2444,6 +2490,7 @@ WorkDev bind(const helm_plan *pl, const WsLayout &L, int B, const helm_params *p
     w.solve_list = w.fact_list + (size_t)(MAX_SIDE_DEPTH + 1) * L.ngroups;
     w.pend_list = w.solve_list + (size_t)(MAX_SIDE_DEPTH + 1) * L.ngroups; w.pend_count = gi + 2 * L.ngroups + 24; w.parity = 0;
     w.depth = 1; w.skip_asm = 0;
+    w.factor_cta = (L.Bp * WPB_FACTOR <= 296 * 2 && !getenv("HELM_B200_NO_FACTOR_CTA")) ? 1 : 0;   // at most ~one CTA per SM
     w.scale_in = nullptr; w.outage_in = nullptr; w.out_status = nullptr; w.out_ncoef = nullptr; w.out_nswitch = nullptr;
     w.btype = (unsigned char *)(b + L.off_btype);
     w.Qg = (double *)(b + L.off_Qg);
@@ -2502,7 +2549,8 @@ void launch_kernel(int which, const PlanDev &p, const WorkDev &w, cudaStream_t s
         case KI_FACTOR:
             if (G == 1 && p.use_coop_factor) {
                 size_t smem = WPB_FACTOR * factor_smem_per_warp(p.cap_upd, p.cap_ent, p.cap_rowblk);
-                k_factor_coop<WPB_FACTOR><<<std::min((w.ngroups + WPB_FACTOR - 1) / WPB_FACTOR, 296), WPB_FACTOR * 32, smem, st>>>(p, w);
+                const int nctas = w.factor_cta ? w.ngroups : (w.ngroups + WPB_FACTOR - 1) / WPB_FACTOR;
+                k_factor_coop<WPB_FACTOR><<<std::min(nctas, 296), WPB_FACTOR * 32, smem, st>>>(p, w);
             } else {
                 k_factor<G, WPB_SOLVE><<<(w.ngroups + WPB_SOLVE - 1) / WPB_SOLVE, WPB_SOLVE * 32, 0, st>>>(p, w);
             }
@@ -2762,7 +2810,7 @@ int helm_plan_create(const helm_grid_host *g, helm_plan **out) {
     UP(S.slot_src, slot_src) UP(S.slot_row, slot_row) UP(S.slot_col, slot_col)
     UP(br_f, br_f) UP(br_t, br_t) UP(br_a, br_a) UP(br_p, br_p) UP(br_val, br_val)
     UP(S.fptr, fptr) UP(S.fsrc, fsrc) UP(S.fdst, fdst) UP(S.fdst_local, fdstl) UP(S.qof, qof)
-    UP(S.fchunk_row, fchunk_row) UP(S.fchunk_lpr, fchunk_lpr) UP(S.frow_off, frow_off)
+    UP(S.fchunk_row, fchunk_row) UP(S.fchunk_lpr, fchunk_lpr) UP(S.frow_off, frow_off) UP(S.flev_chunk, flev_chunk)
     UP(S.smeta, smeta)
     {
         const int *wt = nullptr;
@@ -2891,6 +2939,22 @@ int helm_plan_set_outages(helm_plan *pl, int32_t n, const int32_t *h_outage) {
 size_t helm_workspace_bytes(const helm_plan *pl, int32_t n_scen, const helm_params *prm) {
     if (!pl || !prm || n_scen <= 0) return 0;
     return layout(pl, n_scen, prm).total;
+}
+
+// per-scenario input / output device buffers of the host-buffer entry points, kept in the plan
+static int ensure_io_buffers(helm_plan *pl, int B) {
+    if (pl->cached_B >= B) return HELM_OK;
+    if (pl->d_scale) { cudaFree(pl->d_scale); cudaFree(pl->d_vout); cudaFree(pl->d_status); cudaFree(pl->d_ncoef); cudaFree(pl->d_nswitch); }
+    pl->d_scale = nullptr; pl->d_vout = nullptr; pl->d_status = nullptr; pl->d_ncoef = nullptr; pl->d_nswitch = nullptr;
+    pl->cached_B = 0;
+    const size_t N = pl->S.N;
+    CUDA_TRY(cudaMalloc((void **)&pl->d_scale, sizeof(double) * B));
+    CUDA_TRY(cudaMalloc((void **)&pl->d_vout, sizeof(double) * 2 * N * B));
+    CUDA_TRY(cudaMalloc((void **)&pl->d_status, sizeof(int) * B));
+    CUDA_TRY(cudaMalloc((void **)&pl->d_ncoef, sizeof(int) * B * HELM_MAX_PASSES));
+    CUDA_TRY(cudaMalloc((void **)&pl->d_nswitch, sizeof(int) * B));
+    pl->cached_B = B;
+    return HELM_OK;
 }
 
 static int check_params(const helm_params *prm) {
@@ -3094,16 +3158,8 @@ int helm_solve_batch_host(helm_plan *pl, int32_t B, const double *h_scale, const
         pl->ws_bytes = L.total;
     }
     size_t N = pl->S.N;
-    if (pl->cached_B < B) {
-        if (pl->d_scale) { cudaFree(pl->d_scale); cudaFree(pl->d_vout); cudaFree(pl->d_status); cudaFree(pl->d_ncoef); cudaFree(pl->d_nswitch); }
-        pl->d_scale = nullptr; pl->cached_B = 0;
-        CUDA_TRY(cudaMalloc((void **)&pl->d_scale, sizeof(double) * B));
-        CUDA_TRY(cudaMalloc((void **)&pl->d_vout, sizeof(double) * 2 * N * B));
-        CUDA_TRY(cudaMalloc((void **)&pl->d_status, sizeof(int) * B));
-        CUDA_TRY(cudaMalloc((void **)&pl->d_ncoef, sizeof(int) * B * HELM_MAX_PASSES));
-        CUDA_TRY(cudaMalloc((void **)&pl->d_nswitch, sizeof(int) * B));
-        pl->cached_B = B;
-    }
+    rc = ensure_io_buffers(pl, B);
+    if (rc) return rc;
     cudaStream_t st = pl->stream;
     CUDA_TRY(cudaMemcpyAsync(pl->d_scale, h_scale, sizeof(double) * B, cudaMemcpyHostToDevice, st));
     rc = helm_solve_batch_device(pl, B, pl->d_scale, prm, pl->ws, pl->ws_bytes, pl->d_vout, pl->d_status,
@@ -3144,19 +3200,16 @@ int helm_nr_batch_host(helm_plan *pl, int32_t B, const double *h_scale, double m
         pl->ws_bytes = L.total;
     }
     pl->last_B = 0;                                         // the HELM state of the workspace is gone
-    double *d_scale = nullptr, *d_vout = nullptr;
-    int *d_int = nullptr;
-    CUDA_TRY(cudaMalloc((void **)&d_scale, sizeof(double) * nmax));
-    CUDA_TRY(cudaMalloc((void **)&d_vout, sizeof(double) * 2 * N * nmax));
-    CUDA_TRY(cudaMalloc((void **)&d_int, sizeof(int) * nmax * (2 + HELM_MAX_PASSES)));
-    int rc = HELM_OK;
+    int rc = ensure_io_buffers(pl, nmax);                   // the plan's cached per-scenario buffers
+    if (rc) return rc;
+    double *d_scale = pl->d_scale, *d_vout = pl->d_vout;
     for (int b0 = 0; b0 < B && rc == HELM_OK; b0 += CH) {
         const int nb = std::min(CH, B - b0);
         L = layout(pl, nb, &prm);
         WorkDev w = bind(pl, L, nb, &prm, pl->ws, d_vout);
         w.scale_in = d_scale;
         w.skip_asm = 1;
-        int *d_status = d_int, *d_nsw = d_int + nb, *d_iters = d_int + 2 * nb;
+        int *d_status = pl->d_status, *d_nsw = pl->d_nswitch, *d_iters = pl->d_ncoef;
         cudaMemcpyAsync(d_scale, h_scale + b0, sizeof(double) * nb, cudaMemcpyHostToDevice, st);
         dim3 gridBus((p.N + T_ELEM - 1) / T_ELEM, w.ngroups);
         const int gridGrp = (w.ngroups + 127) / 128;
@@ -3186,7 +3239,6 @@ int helm_nr_batch_host(helm_plan *pl, int32_t B, const double *h_scale, double m
         if (h_nswitch) cudaMemcpyAsync(h_nswitch + b0, d_nsw, sizeof(int) * nb, cudaMemcpyDeviceToHost, st);
         if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) { g_err = "CUDA failure in the Newton-Raphson batch"; rc = HELM_E_CUDA; }
     }
-    cudaFree(d_scale); cudaFree(d_vout); cudaFree(d_int);
     return rc;
 }
 

@@ -286,7 +286,9 @@ bool build_symbolic(int N, const int32_t *adj_ptr, const int32_t *adj_idx, const
         S.frow_off.assign(N, 0);
         S.fchunk_row.clear();
         S.fchunk_lpr.clear();
+        S.flev_chunk.clear();
         for (int l = 0; l < nLlev; ++l) {
+            S.flev_chunk.push_back((int)S.fchunk_lpr.size());     // first chunk of level l
             int r0 = S.llev_ptr[l], r1 = S.llev_ptr[l + 1];
             bool diag_only = true;
             for (int r = r0; r < r1; ++r) diag_only = diag_only && (S.lptr[r + 1] == S.lptr[r]);
@@ -318,6 +320,7 @@ bool build_symbolic(int N, const int32_t *adj_ptr, const int32_t *adj_idx, const
             }
         }
         S.fchunk_row.push_back(N);
+        S.flev_chunk.push_back((int)S.fchunk_lpr.size());
     }
 
     // ---- 4b-flat. flat solve schedule ---------------------------------------------------------

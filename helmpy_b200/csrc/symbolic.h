@@ -33,6 +33,7 @@ struct Symbolic {
     // with all their operands staged in shared memory.  Chunk c covers rows
     // [fchunk_row[c], fchunk_row[c+1]); fchunk_lpr[c] = lanes per row (0: diagonal-only rows).
     std::vector<int> fchunk_row, fchunk_lpr;
+    std::vector<int> flev_chunk;                 // chunks of L-level l: [flev_chunk[l], flev_chunk[l+1])
     std::vector<int> frow_off;                   // row -> block offset of its buffer inside its chunk
     int cap_upd = 0, cap_ent = 0, cap_rowblk = 0;  // staging capacities (max over chunks)
     // assembly map: slot -> adjacency entry (or -1 for fill), slot -> row
