@@ -1497,9 +1497,10 @@ __global__ void __launch_bounds__(CS_T) k_solve_cta(PlanDev p, WorkDev w, int si
 // and small batches):
 //   * the waves between two ordering points form a segment (host table, symbolic.cpp): the waves of
 //     a WIDE segment are dealt to the warps, one block barrier per segment; a run of one-wave levels
-//     (the chain near the root of the elimination tree) is one THIN segment that warp 0 walks alone
-//     with warp barriers — no scanning of the wave table, no per-chunk barriers; every warp has its
-//     list of waves from the host;
+//     (the chain near the root of the elimination tree) is one THIN segment that warps 0 and 1 walk
+//     alternately, handing over through a named barrier of the two warps, so that the x-independent
+//     part of a wave overlaps the dependent part of the wave before it — no scanning of the wave
+//     table, no per-chunk barriers; every warp has its list of waves from the host;
 //   * everything of a wave that does not depend on x — factor blocks, columns and row metadata, one
 //     contiguous KB + 256 B per wave — is copied ONE_D waves ahead from global memory / L2 into a
 //     per-warp shared-memory ring with cp.async (no register is tied to a load in flight), so the
@@ -1681,6 +1682,17 @@ __global__ void __launch_bounds__(ONE_T) k_solve_one(PlanDev p, WorkDev w, int s
         ++li; ++cons;
         return o;
     };
+    // `pre` = operands of the warp's next wave, fetched right after the previous one was processed: the
+    // x-independent part of a wave (ring wait, shared-memory loads, issue of the next copies) runs
+    // while the warp would otherwise wait at the barrier of the segment
+    OneOps pre;
+    if (l0 < l1) pre = take(slist[l0]);
+    auto run = [&]() {
+        OneOps o = pre;
+        if (abl & 1) o.info &= ~(31 << 9);
+        if (abl & 4) o.meta |= Sy::META_DIAG;
+        return o;
+    };
     for (int s = 0; s < nsegs; ++s) {
         const int2 sg = sseg[s];
         const int first = sg.x, n = sg.y & 0x3FFFFFFF;
@@ -1691,22 +1703,23 @@ __global__ void __launch_bounds__(ONE_T) k_solve_one(PlanDev p, WorkDev w, int s
         if ((abl & 16) && thin) continue;
         if ((abl & 32) && !thin) continue;
         if (thin) {
-            if (wp == 0) {
-                for (int k = first; k < first + n; ++k) {
-                    OneOps o = take(k);
-                    if (abl & 1) o.info &= ~(31 << 9);
-                    if (abl & 4) o.meta |= Sy::META_DIAG;
+            // warps 0 and 1 alternate; wave j waits for wave j - 1 on a named barrier of the two warps
+            // (id 1: an even wave is done, id 2: an odd wave is done)
+            if (wp < 2) {
+                for (int j = wp; j < n; j += 2) {
+                    const OneOps o = run();
+                    if (j > 0) asm volatile("bar.sync %0, 64;" ::"r"(wp ? 1 : 2) : "memory");
                     one_wave(o, xs, carry_s, lane);
-                    __syncwarp();
+                    if (j + 1 < n) asm volatile("bar.arrive %0, 64;" ::"r"(wp ? 2 : 1) : "memory");
+                    if (l0 + cons < l1) pre = take(slist[l0 + cons]);
                 }
             }
             TL_CLK_ADD(w, 3);
         } else {
             for (int k = first + wp; k < first + n; k += ONE_NW) {
-                OneOps o = take(k);
-                if (abl & 1) o.info &= ~(31 << 9);
-                if (abl & 4) o.meta |= Sy::META_DIAG;
+                const OneOps o = run();
                 one_wave(o, xs, carry_s, lane);
+                if (l0 + cons < l1) pre = take(slist[l0 + cons]);
             }
             TL_CLK_ADD(w, 4);
         }

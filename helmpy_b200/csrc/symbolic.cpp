@@ -446,14 +446,16 @@ bool build_symbolic(int N, const int32_t *adj_ptr, const int32_t *adj_idx, const
                 }
             }
             // per-warp wave lists of k_solve_one (ONE_WARPS warps): the waves of a WIDE segment are dealt
-            // round-robin, THIN segments go to warp 0.  Layout: [ONE_WARPS + 1 offsets][waves in order].
+            // round-robin, the waves of a THIN segment alternate between warps 0 and 1.  Layout: [ONE_WARPS + 1 offsets][waves in order].
             {
                 const int W = Symbolic::ONE_WARPS;
                 std::vector<std::vector<int>> lists(W);
                 for (size_t sgi = 0; sgi + 1 < S.solve_segs.size(); sgi += 2) {
                     const int first = S.solve_segs[sgi], n = S.solve_segs[sgi + 1] & 0x3FFFFFFF;
                     const bool thin = (S.solve_segs[sgi + 1] >> 30) != 0;
-                    for (int j = 0; j < n; ++j) lists[thin ? 0 : (j % W)].push_back(first + j);
+                    // THIN segments: warps 0 and 1 alternate, so that everything of a wave that does not
+                    // depend on x overlaps the dependent part of the wave before it
+                    for (int j = 0; j < n; ++j) lists[thin ? (j & 1) : (j % W)].push_back(first + j);
                 }
                 S.one_lists.assign(W + 1, 0);
                 for (int wq = 0; wq < W; ++wq) S.one_lists[wq + 1] = S.one_lists[wq] + (int)lists[wq].size();
