@@ -80,7 +80,6 @@ struct PlanDev {
     const int *scm;
     const int4 *solve_chunks;
     int nschunks, use_cta_solve, cta_solve_max_groups;
-    int use_lane_solve, lanes_idx_global;
     const int2 *solve_segs;
     const int *one_lists;
     int nsegs, use_one_solve, nonelist;
@@ -127,9 +126,6 @@ struct WorkDev {
     // factors of the first pass, shared by every scenario without an outage: the matrix of a pass depends
     // on the topology and the bus types only (helm.py:46-60), not on the load scale.  null: not used.
     const double2 *lu_shared;
-    // lane-per-scenario solve (k_solve_lanes): interleaved copy of the factors [group of 32 slots][LU slot][lane][2]
-    // and the interleaved scratch vector [group][row][lane]; null when that solve is not in use
-    double2 *lu_il, *xi;
     double2 *Vh, *Hh, *Eh;            // [group][tile][K][HT][G]
     double2 *Pb;                      // [group][tile][3][HT][G] partial sums of the blocked W recurrence
     double2 *vout;                    // [B][N] original order
@@ -308,15 +304,6 @@ __device__ __forceinline__ void asm_reset(const PlanDev &p, const WorkDev &w, in
         w.Pcur[bi] = make_double2(0.0, 0.0);
     }
 }
-// interleaved copy of LU block `slot` of scenario slot `grp` (G = 1; null pointer: not kept)
-__device__ __forceinline__ void st_il(const PlanDev &p, const WorkDev &w, int grp, int slot, double2 r0, double2 r1) {
-    if (w.lu_il) {
-        double2 *d = w.lu_il + (((size_t)(grp >> 5) * p.nslots + slot) * 32 + (grp & 31)) * 2;
-        d[0] = r0;
-        d[1] = r1;
-    }
-}
-
 template <int G>
 __device__ __forceinline__ void asm_slot(const PlanDev &p, const WorkDev &w, int grp, int slot, int s) {
     int r = p.slot_row[slot];
@@ -343,7 +330,6 @@ __device__ __forceinline__ void asm_slot(const PlanDev &p, const WorkDev &w, int
     double2 *dst = w.lu + ix<G>(grp, p.nslots, slot, s) * 2;
     dst[0] = r0;
     dst[1] = r1;
-    if (G == 1) st_il(p, w, grp, slot, r0, r1);
 }
 
 template <int G>
@@ -509,7 +495,6 @@ __device__ __forceinline__ void factor_chunk(const PlanDev &p, const WorkDev &w,
                 if (pivot_singular(d, det, bnorm2(d))) { singular = true; det = 1.0; }
                 double inv = 1.0 / det;
                 stblk(lu, dd, Blk{d.d * inv, -d.b * inv, -d.c * inv, d.a * inv});
-                st_il(p, w, grp, (int)dd, make_double2(d.d * inv, -d.b * inv), make_double2(-d.c * inv, d.a * inv));
             }
             __syncwarp();
             return;
@@ -593,7 +578,6 @@ __device__ __forceinline__ void factor_chunk(const PlanDev &p, const WorkDev &w,
                 size_t slot = (b < nl) ? (size_t)(e0 + b) : (size_t)(dbase + (b - nl));
                 lu[slot * 2] = buf[2 * b];
                 lu[slot * 2 + 1] = buf[2 * b + 1];
-                st_il(p, w, grp, (int)slot, buf[2 * b], buf[2 * b + 1]);
             }
         }
         __syncwarp();
@@ -641,7 +625,6 @@ __global__ void __launch_bounds__(WPB * 32) k_factor_coop(PlanDev p, WorkDev w) 
                     if (pivot_singular(d, det, bnorm2(d))) { singular = true; det = 1.0; }
                     const double inv = 1.0 / det;
                     stblk(lu, dd, Blk{d.d * inv, -d.b * inv, -d.c * inv, d.a * inv});
-                    st_il(p, w, grp, (int)dd, make_double2(d.d * inv, -d.b * inv), make_double2(-d.c * inv, d.a * inv));
                 }
             } else {
                 for (int c = c0 + wib; c < c1; c += WPB) factor_chunk(p, w, lu, grp, c, lane, sSrc, sDk, sRow, sDl, sUp, singular);
@@ -944,273 +927,6 @@ __global__ void __maxnreg__(64) k_solve_flat(PlanDev p, WorkDev w, int side) {
             }
         }
     }
-}
-
-// ---- K2 (G = 1), lane-per-scenario solve -----------------------------------------------------------
-// One CTA solves the 32 scenarios of slots 32c .. 32c+31 at once: LANE = SCENARIO.  Every scenario has
-// the same sparsity pattern, so the 32 lanes of a warp walk the same row of L or [D|U] in lock step
-// with warp-uniform indices — no row sums across lanes, no shuffles, no per-slot metadata: per 2x2
-// block a lane issues two 16 B factor loads, one 16 B gather of x and four DFMA (the wave solve spends
-// ~200 instructions per 26 blocks on the segmented reductions and their bookkeeping).
-//
-// Coalescing needs the 32 scenarios interleaved: the factors of a slot group are kept in a second,
-// interleaved copy lu_il[group][slot][lane][2x2 block] (written by the assembly / factorization next
-// to the scenario-major copy), so a warp's factor load is one contiguous KB; and the kernel works on
-// an interleaved scratch vector xi[row][lane], filled from the scenario-major rhs and emptied into the
-// scenario-major x by 32 x 32 tile transposes through shared memory.  Lanes whose scenario runs on
-// the shared first-pass factors point at that one copy instead (same address in every such lane).
-//
-// The rows of a level are dealt to the LN_WARPS warps of the CTA; a level ends with a block barrier
-// (xi lives in global memory / L2; the barrier makes the level's rows visible to the other warps).
-// The lone rows of the chain near the root of the elimination tree are split over all warps (partial
-// sums through shared memory).  The group's factor stream is contiguous in consumption order: one
-// thread prefetches it into L2 with bulk-prefetch instructions a fixed distance ahead of the level
-// being solved, so the dependent chain of levels does not wait for HBM.
-#ifndef LN_WARPS_N
-#define LN_WARPS_N 16
-#endif
-#ifndef LN_UNROLL
-#define LN_UNROLL 4
-#endif
-#ifndef LN_HINT
-#define LN_HINT 0
-#endif
-constexpr int LN_WARPS = LN_WARPS_N;
-constexpr int LN_TW = 4;         // warps that take part in the tile transposes (16 KB of shared memory each)
-constexpr int LN_LONG = 20;      // a lone row with more blocks than this is split over the warps
-constexpr int LN_PF = 192;       // prefetch distance of the factor stream, in slots (1 KB each per group)
-
-__device__ __forceinline__ void bulk_prefetch_l2(const void *gsrc, unsigned bytes) {
-#if LN_HINT
-    unsigned long long pol;
-    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(gsrc), "r"(bytes), "l"(pol) : "memory");
-#else
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
-#endif
-}
-
-// lane's factor block e: ptr[e * stride], ptr[e * stride + 1]; pol: L2 eviction policy of the lane's
-// factor loads (evict-first for the private stream, which is read once per solve and must not push the
-// interleaved x out of L2; normal for the shared first-pass factors, which every solve re-reads)
-struct LaneF { const double2 *ptr; int stride; unsigned long long pol; };
-
-__device__ __forceinline__ unsigned long long l2_policy(bool evict_first) {
-    unsigned long long a, b;
-    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(a));
-    asm("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(b));
-    return evict_first ? a : b;
-}
-__device__ __forceinline__ double2 ldf(const LaneF &f, size_t i) {
-#if LN_HINT
-    double2 v;
-    asm("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(f.ptr + i), "l"(f.pol));
-    return v;
-#else
-    return f.ptr[i];
-#endif
-}
-
-__device__ __forceinline__ void lanes_accumulate(const LaneF f, const double2 *xi, const int *cols, int slot0, int n,
-                                                 int lane, double2 &acc) {
-    int t = 0;
-    for (; t + LN_UNROLL <= n; t += LN_UNROLL) {       // LN_UNROLL entries in flight
-        int c[LN_UNROLL];
-        double2 a0[LN_UNROLL], a1[LN_UNROLL], x[LN_UNROLL];
-#pragma unroll
-        for (int u = 0; u < LN_UNROLL; ++u) c[u] = cols[t + u];
-#pragma unroll
-        for (int u = 0; u < LN_UNROLL; ++u) {
-            const size_t i = (size_t)(slot0 + t + u) * f.stride;
-            a0[u] = ldf(f, i);
-            a1[u] = ldf(f, i + 1);
-        }
-#pragma unroll
-        for (int u = 0; u < LN_UNROLL; ++u) x[u] = xi[c[u] * 32 + lane];
-#pragma unroll
-        for (int u = 0; u < LN_UNROLL; ++u) {
-            acc.x -= a0[u].x * x[u].x + a0[u].y * x[u].y;
-            acc.y -= a1[u].x * x[u].x + a1[u].y * x[u].y;
-        }
-    }
-    for (; t < n; ++t) {
-        const int c = cols[t];
-        const size_t i = (size_t)(slot0 + t) * f.stride;
-        const double2 a0 = ldf(f, i), a1 = ldf(f, i + 1);
-        const double2 x0 = xi[c * 32 + lane];
-        acc.x -= a0.x * x0.x + a0.y * x0.y; acc.y -= a1.x * x0.x + a1.y * x0.y;
-    }
-}
-
-// index tables of the solve, either staged in shared memory (generic pointers) or left in global memory
-struct LaneIdx { const int *lptr, *lcol, *uptr, *ucol, *urow, *llev, *ulev; };
-
-// one row (ISU: position q of the backward order) for the 32 scenarios of the warp
-template <bool ISU>
-__device__ __forceinline__ void lanes_row(const LaneIdx &ix_, int nL, const LaneF f, double2 *xi, int item, int lane) {
-    if (!ISU) {
-        const int e0 = ix_.lptr[item], n = ix_.lptr[item + 1] - e0;
-        double2 acc = xi[item * 32 + lane];
-        lanes_accumulate(f, xi, ix_.lcol + e0, e0, n, lane, acc);
-        xi[item * 32 + lane] = acc;
-    } else {
-        const int r = ix_.urow[item];
-        const int u0 = ix_.uptr[item], nu = ix_.uptr[item + 1] - u0;
-        const int base = nL + u0 + item;
-        const double2 d0 = ldf(f, (size_t)base * f.stride), d1 = ldf(f, (size_t)base * f.stride + 1);
-        double2 acc = xi[r * 32 + lane];
-        lanes_accumulate(f, xi, ix_.ucol + u0, base + 1, nu, lane, acc);
-        xi[r * 32 + lane] = make_double2(d0.x * acc.x + d0.y * acc.y, d1.x * acc.x + d1.y * acc.y);
-    }
-}
-
-// shared memory: [tiles LN_TW x 16 KB][partial sums LN_WARPS x 512 B][index tables, if they fit]
-__host__ __device__ inline size_t lanes_idx_ints(int N, int nL, int nU, int nLlev, int nUlev) {
-    return (size_t)(N + 1) * 2 + N + nL + nU + (nLlev + 1) + (nUlev + 1) + 8;
-}
-constexpr size_t LN_SMEM_BASE = (size_t)LN_TW * 32 * 32 * sizeof(double2) + (size_t)LN_WARPS * 32 * sizeof(double2);
-
-__global__ void __launch_bounds__(LN_WARPS * 32, 1) k_solve_lanes(PlanDev p, WorkDev w, int idx_in_smem) {
-    TL_SCOPE(w, 2);
-    extern __shared__ __align__(16) double2 smem_l[];
-    double2 (*tiles)[32][32] = (double2 (*)[32][32])smem_l;                        // [LN_TW][scenario][row ^ scenario]
-    double2 (*part)[32] = (double2 (*)[32])(smem_l + (size_t)LN_TW * 32 * 32);     // [LN_WARPS][lane]
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int g0 = blockIdx.x * 32;
-    const int grp = min(g0 + lane, w.ngroups - 1);
-    bool act = false;
-    if (g0 + lane < w.ngroups) act = !(w.g_flags[grp] & (GF_DONE | GF_FACTORING)) && w.s_status[grp] == ST_ACTIVE;
-    const unsigned actmask = __ballot_sync(0xFFFFFFFFu, act);                      // the same in every warp
-    if (actmask == 0) return;
-    const int N = p.N, nslots = p.nslots, nL = p.nL;
-    LaneIdx ix_{p.lptr, p.lcol, p.uptr, p.ucol, p.urow, p.llev_ptr, p.ulev_ptr};
-    if (idx_in_smem) {
-        int *si = (int *)((char *)smem_l + LN_SMEM_BASE);
-        int *s_lptr = si, *s_uptr = s_lptr + (N + 1), *s_urow = s_uptr + (N + 1), *s_lcol = s_urow + N;
-        int *s_ucol = s_lcol + p.nL, *s_llev = s_ucol + p.nU, *s_ulev = s_llev + (p.nLlev + 1);
-        for (int i = threadIdx.x; i <= N; i += LN_WARPS * 32) { s_lptr[i] = __ldg(p.lptr + i); s_uptr[i] = __ldg(p.uptr + i); }
-        for (int i = threadIdx.x; i < N; i += LN_WARPS * 32) s_urow[i] = __ldg(p.urow + i);
-        for (int i = threadIdx.x; i < p.nL; i += LN_WARPS * 32) s_lcol[i] = __ldg(p.lcol + i);
-        for (int i = threadIdx.x; i < p.nU; i += LN_WARPS * 32) s_ucol[i] = __ldg(p.ucol + i);
-        for (int i = threadIdx.x; i <= p.nLlev; i += LN_WARPS * 32) s_llev[i] = __ldg(p.llev_ptr + i);
-        for (int i = threadIdx.x; i <= p.nUlev; i += LN_WARPS * 32) s_ulev[i] = __ldg(p.ulev_ptr + i);
-        ix_ = LaneIdx{s_lptr, s_lcol, s_uptr, s_ucol, s_urow, s_llev, s_ulev};
-    }
-    const double2 *lug = w.lu_il + (size_t)blockIdx.x * nslots * 64;               // the group's interleaved factors
-    LaneF f;
-    const bool shared = act && uses_shared_lu(w, grp);
-    f.ptr = shared ? w.lu_shared : lug + lane * 2;
-    f.stride = shared ? 2 : 64;
-    f.pol = l2_policy(!shared);
-    const bool any_private = __ballot_sync(0xFFFFFFFFu, act && !shared) != 0;
-    double2 *xi = w.xi + (size_t)blockIdx.x * N * 32;
-    // prefetch frontier of the group's factor stream (slot index)
-    int pf = 0;
-    auto advance_prefetch = [&](int upto) {
-        upto = min(upto, nslots);
-        if (upto > pf) {
-            if (threadIdx.x == 0 && any_private) bulk_prefetch_l2(lug + (size_t)pf * 64, (unsigned)(upto - pf) * 1024u);
-            pf = upto;
-        }
-    };
-    advance_prefetch(LN_PF);
-    TL_CLK_DECL;
-    // ---- rhs (scenario-major) -> xi (interleaved), 32 x 32 tiles through shared memory
-    const int ntile = (N + 31) / 32;
-    if (wid < LN_TW) {
-        double2 (*tile)[32] = tiles[wid];
-        for (int t = wid; t < ntile; t += LN_TW) {
-            const int r = t * 32 + lane;
-#pragma unroll 16
-            for (int k = 0; k < 32; ++k) {
-                double2 v = make_double2(0.0, 0.0);
-                if (r < N && ((actmask >> k) & 1u)) v = w.rhs[(size_t)(g0 + k) * N + r];
-                tile[k][lane ^ k] = v;
-            }
-            __syncwarp();
-#pragma unroll 16
-            for (int j = 0; j < 32; ++j)
-                if (t * 32 + j < N) xi[(t * 32 + j) * 32 + lane] = tile[lane][j ^ lane];
-            __syncwarp();
-        }
-    }
-    __syncthreads();
-    TL_CLK_ADD(w, 1);
-    // ---- forward: rows without L entries are y = rhs already
-    for (int l = 1; l < p.nLlev; ++l) {
-        const int r0 = ix_.llev[l], r1 = ix_.llev[l + 1];
-        const int e0 = ix_.lptr[r0], e1 = ix_.lptr[r1];
-        advance_prefetch(e1 + LN_PF);
-        if (r1 - r0 == 1 && e1 - e0 > LN_LONG) {
-            // one long row: every warp sums a strided share of its blocks
-            double2 acc = make_double2(0.0, 0.0);
-            for (int t = e0 + wid; t < e1; t += LN_WARPS) {
-                const double2 a0 = ldf(f, (size_t)t * f.stride), a1 = ldf(f, (size_t)t * f.stride + 1);
-                const double2 x0 = xi[ix_.lcol[t] * 32 + lane];
-                acc.x -= a0.x * x0.x + a0.y * x0.y; acc.y -= a1.x * x0.x + a1.y * x0.y;
-            }
-            part[wid][lane] = acc;
-            __syncthreads();
-            if (wid == 0) {
-                double2 b = xi[r0 * 32 + lane];
-#pragma unroll
-                for (int k = 0; k < LN_WARPS; ++k) { b.x += part[k][lane].x; b.y += part[k][lane].y; }
-                xi[r0 * 32 + lane] = b;
-            }
-        } else {
-            for (int r = r0 + wid; r < r1; r += LN_WARPS) lanes_row<false>(ix_, nL, f, xi, r, lane);
-        }
-        __syncthreads();
-        TL_CLK_ADD(w, (r1 - r0 >= LN_WARPS) ? 2 : ((r1 - r0 == 1 && e1 - e0 > LN_LONG) ? 4 : 3));
-    }
-    // ---- backward
-    for (int l = 0; l < p.nUlev; ++l) {
-        const int q0 = ix_.ulev[l], q1 = ix_.ulev[l + 1];
-        const int u0 = ix_.uptr[q0], u1 = ix_.uptr[q1];
-        advance_prefetch(nL + u1 + q1 + LN_PF);
-        if (q1 - q0 == 1 && u1 - u0 > LN_LONG) {
-            const int base = nL + u0 + q0;
-            const int r = ix_.urow[q0];
-            double2 acc = make_double2(0.0, 0.0);
-            for (int t = wid; t < u1 - u0; t += LN_WARPS) {
-                const double2 a0 = ldf(f, (size_t)(base + 1 + t) * f.stride), a1 = ldf(f, (size_t)(base + 1 + t) * f.stride + 1);
-                const double2 x0 = xi[ix_.ucol[u0 + t] * 32 + lane];
-                acc.x -= a0.x * x0.x + a0.y * x0.y; acc.y -= a1.x * x0.x + a1.y * x0.y;
-            }
-            part[wid][lane] = acc;
-            __syncthreads();
-            if (wid == 0) {
-                const double2 d0 = ldf(f, (size_t)base * f.stride), d1 = ldf(f, (size_t)base * f.stride + 1);
-                double2 b = xi[r * 32 + lane];
-#pragma unroll
-                for (int k = 0; k < LN_WARPS; ++k) { b.x += part[k][lane].x; b.y += part[k][lane].y; }
-                xi[r * 32 + lane] = make_double2(d0.x * b.x + d0.y * b.y, d1.x * b.x + d1.y * b.y);
-            }
-        } else {
-            for (int q = q0 + wid; q < q1; q += LN_WARPS) lanes_row<true>(ix_, nL, f, xi, q, lane);
-        }
-        __syncthreads();
-        TL_CLK_ADD(w, (q1 - q0 >= LN_WARPS) ? 6 : 5);
-    }
-    // ---- xi -> x (scenario-major), active scenarios only
-    if (wid < LN_TW) {
-        double2 (*tile)[32] = tiles[wid];
-        for (int t = wid; t < ntile; t += LN_TW) {
-#pragma unroll 16
-            for (int j = 0; j < 32; ++j) {
-                double2 v = make_double2(0.0, 0.0);
-                if (t * 32 + j < N) v = xi[(t * 32 + j) * 32 + lane];
-                tile[lane][j ^ lane] = v;
-            }
-            __syncwarp();
-            const int r = t * 32 + lane;
-#pragma unroll 16
-            for (int k = 0; k < 32; ++k)
-                if (r < N && ((actmask >> k) & 1u)) w.xb[(size_t)(g0 + k) * N + r] = tile[k][lane ^ k];
-            __syncwarp();
-        }
-    }
-    TL_CLK_ADD(w, 7);
 }
 
 // ---- K2 (G = 1), shared-memory wave solve --------------------------------------------------------
@@ -2422,7 +2138,7 @@ struct WsLayout {
     size_t total = 0;
     size_t off_scale, off_sint, off_gint, off_btype, off_Qg, off_VVant, off_Pcur, off_rhs, off_xb, off_lu, off_Vh, off_Hh, off_Eh;
     size_t off_var_s, off_ploss, off_zb, off_Qh, off_vre, off_qcur, off_lu_shared, off_shprep, off_Pb;
-    size_t off_sw_ent, off_sw_q, off_lu_il, off_xi;
+    size_t off_sw_ent, off_sw_q;
     int sw_cap;
     int G, ngroups, Bp, K;
 };
@@ -2468,14 +2184,6 @@ WsLayout layout(const helm_plan *pl, int B, const helm_params *prm) {
         L.off_vre = take(per * sizeof(double));
         L.off_qcur = take(per * sizeof(double));
     }
-    // lane-per-scenario solve: interleaved factor copy + interleaved scratch vector, per group of 32 slots
-    L.off_lu_il = L.off_xi = 0;
-    if (pl->d.use_lane_solve && pl->d.use_coop_factor && L.G == 1 && !prm->dsb_method && prm->pv_bus_model != 1 &&
-        L.ngroups > pl->d.cta_solve_max_groups) {
-        const size_t ng32 = (size_t)(L.ngroups + 31) / 32;
-        L.off_lu_il = take(ng32 * pl->S.nslots * 32 * 2 * sizeof(double2));
-        L.off_xi = take(ng32 * N * 32 * sizeof(double2));
-    }
     L.off_sw_ent = L.off_sw_q = 0;
     L.sw_cap = 0;
     if (prm->record_switches) {
@@ -2513,8 +2221,6 @@ WorkDev bind(const helm_plan *pl, const WsLayout &L, int B, const helm_params *p
     w.xb = (double2 *)(b + L.off_xb);
     w.lu = (double2 *)(b + L.off_lu);
     w.lu_shared = nullptr;
-    w.lu_il = L.off_lu_il ? (double2 *)(b + L.off_lu_il) : nullptr;
-    w.xi = L.off_xi ? (double2 *)(b + L.off_xi) : nullptr;
     w.Vh = (double2 *)(b + L.off_Vh);
     w.Hh = (double2 *)(b + L.off_Hh);
     w.Eh = (double2 *)(b + L.off_Eh);
@@ -2591,12 +2297,6 @@ void launch_kernel(int which, const PlanDev &p, const WorkDev &w, cudaStream_t s
                 else k_solve_one<<<w.ngroups, ONE_T, one_layout(p.N, p.nwaves, p.nsegs, p.nonelist).total, st>>>(p, w, 2);
             } else if (G == 1 && p.use_cta_solve && w.ngroups <= p.cta_solve_max_groups) {
                 k_solve_cta<<<w.ngroups, CS_T, cta_solve_layout(p.N, p.nwaves, p.nschunks).total, st>>>(p, w, 0);
-            } else if (G == 1 && w.lu_il) {
-                {
-                    const size_t isz = lanes_idx_ints(p.N, p.nL, p.nU, p.nLlev, p.nUlev) * sizeof(int);
-                    const bool fits = LN_SMEM_BASE + isz <= 224 * 1024 && !p.lanes_idx_global;
-                    k_solve_lanes<<<(w.ngroups + 31) / 32, LN_WARPS * 32, LN_SMEM_BASE + (fits ? isz : 0), st>>>(p, w, fits ? 1 : 0);
-                }
             } else if (G == 1) {
                 k_solve_flat<FLAT_WPB><<<(w.ngroups + FLAT_WPB - 1) / FLAT_WPB, FLAT_WPB * 32, 0, st>>>(p, w, 0);
             } else {
@@ -2864,8 +2564,6 @@ int helm_plan_create(const helm_grid_host *g, helm_plan **out) {
             static size_t csm_set = 48 * 1024;
             pl->d.use_cta_solve = (csm <= 225 * 1024) && getenv("HELM_B200_NO_CTA_SOLVE") == nullptr;
             pl->d.cta_solve_max_groups = getenv("HELM_B200_CTA_SOLVE_MAX") ? atoi(getenv("HELM_B200_CTA_SOLVE_MAX")) : 888;
-            pl->d.use_lane_solve = getenv("HELM_B200_LANE_SOLVE") ? atoi(getenv("HELM_B200_LANE_SOLVE")) : 0;
-            pl->d.lanes_idx_global = getenv("HELM_B200_LANE_IDX_GLOBAL") != nullptr;
             {
                 const size_t osm = one_layout(pl->d.N, pl->d.nwaves, pl->d.nsegs, pl->d.nonelist).total;
                 static size_t osm_set = 48 * 1024;
@@ -2878,13 +2576,6 @@ int helm_plan_create(const helm_grid_host *g, helm_plan **out) {
             if (pl->d.use_cta_solve && csm > csm_set) {
                 CUDA_TRY(cudaFuncSetAttribute(k_solve_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
                 csm_set = csm;
-            }
-        }
-        {
-            static bool lanes_attr = false;
-            if (!lanes_attr) {
-                CUDA_TRY(cudaFuncSetAttribute(k_solve_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-                lanes_attr = true;
             }
         }
         // the attribute is per function, not per plan: only ever raise it
@@ -3045,7 +2736,6 @@ int helm_solve_batch_device(helm_plan *pl, int32_t B, const double *d_scale, con
         int *ints = (int *)((char *)d_ws + L.off_shprep);
         WorkDev w2 = w;
         w2.lu = (double2 *)((char *)d_ws + L.off_lu_shared);
-        w2.lu_il = nullptr;
         w2.btype = const_cast<unsigned char *>(p.btype0);
         w2.fact_count = ints; w2.fact_list = ints + 4; w2.parity = 0;
         w2.o_b = ints + 8; w2.s_status = ints + 9; w2.g_flags = ints + 10; w2.s_npass = ints + 11;
@@ -3088,7 +2778,7 @@ int helm_solve_batch_device(helm_plan *pl, int32_t B, const double *d_scale, con
         memcpy(&mm, &prm->mismatch, sizeof(mm));
         const std::vector<unsigned long long> key = {
             u(d_ws), (unsigned long long)ws_bytes, (unsigned long long)B, u(d_scale), u(d_vout), u(d_status), u(d_ncoef), u(d_nswitch),
-            u(st), u(w.outage_in), u(w.lu_shared), u(w.lu_il), u(w.tl), mm, (unsigned long long)prm->max_coefficients,
+            u(st), u(w.outage_in), u(w.lu_shared), u(w.tl), mm, (unsigned long long)prm->max_coefficients,
             (unsigned long long)prm->enforce_q_limits, (unsigned long long)L.G, (unsigned long long)L.ngroups,
             (unsigned long long)prm->pv_bus_model, (unsigned long long)prm->dsb_method, (unsigned long long)prm->dsb_model,
             (unsigned long long)prm->record_switches, (unsigned long long)depth, (unsigned long long)poll_every,

@@ -185,15 +185,19 @@ def test_unstaged_kernels_agree(hb, monkeypatch):
         "print(json.dumps([r.V.real.tolist(), r.V.imag.tolist(), r.ncoef.tolist()]))"
     ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
     outs = []
-    for env_extra in ({}, {'HELM_B200_NO_COOP_FACTOR': '1', 'HELM_B200_NO_CTA_SOLVE': '1'}):
+    # default (k_solve_one, CTA-cooperative factorization) / generic kernels / the TMA-ring CTA solve and the
+    # warp-per-scenario factorization
+    for env_extra in ({}, {'HELM_B200_NO_COOP_FACTOR': '1', 'HELM_B200_NO_CTA_SOLVE': '1', 'HELM_B200_ONE_SOLVE': '0'},
+                      {'HELM_B200_ONE_SOLVE': '0', 'HELM_B200_NO_FACTOR_CTA': '1'}):
         env = dict(os.environ, **env_extra)
         out = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=300)
         assert out.returncode == 0, out.stderr[-2000:]
         outs.append(json.loads(out.stdout.strip().splitlines()[-1]))
-    a, b = outs
-    assert a[2] == b[2]
-    assert np.max(np.abs(np.array(a[0]) - np.array(b[0]))) < 1e-11
-    assert np.max(np.abs(np.array(a[1]) - np.array(b[1]))) < 1e-11
+    a = outs[0]
+    for b in outs[1:]:
+        assert a[2] == b[2]
+        assert np.max(np.abs(np.array(a[0]) - np.array(b[0]))) < 1e-11
+        assert np.max(np.abs(np.array(a[1]) - np.array(b[1]))) < 1e-11
 
 
 def _numbers(text):
