@@ -148,7 +148,8 @@ def symbolic_arrays(adj_ptr, adj_idx, bus_type=None):
         for name in ("perm", "iperm", "adj_ptr", "adj_idx", "adj_src", "adj_slot", "lptr", "lcol",
                      "llev_ptr", "urow", "qof", "ulev_ptr", "uptr", "ucol", "dslot", "fptr",
                      "fsrc", "fdst", "fdst_local", "fchunk_row", "fchunk_lpr", "flev_chunk", "frow_off",
-                     "slot_src", "slot_row", "slot_col", "wave_tab", "smeta", "scm", "solve_chunks", "solve_segs", "one_lists"):
+                     "slot_src", "slot_row", "slot_col", "wave_tab", "smeta", "scm", "solve_chunks", "solve_segs", "one_lists",
+                     "rl_desc"):
             data = C.c_void_p()
             n = C.c_int32()
             rc = lib.helm_symbolic_array(h, name.encode(), C.byref(data), C.byref(n))

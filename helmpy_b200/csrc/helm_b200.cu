@@ -83,6 +83,8 @@ struct PlanDev {
     const int2 *solve_segs;
     const int *one_lists;
     int nsegs, use_one_solve, nonelist;
+    const int4 *rl_desc;
+    int rl_nwaves, use_rows_solve;
 };
 
 struct WorkDev {
@@ -926,6 +928,117 @@ __global__ void __maxnreg__(64) k_solve_flat(PlanDev p, WorkDev w, int side) {
                 xg = xgn; bs = bsn;
             }
         }
+    }
+}
+
+// ---- K2 (G = 1, large batches), row-lane solve -----------------------------------------------------
+// One warp per scenario, as k_solve_flat, but the work of a wave is laid out by ROWS (symbolic.cpp
+// 4b-rows): every row of a level owns a power-of-two group of k lanes and a lane walks every k-th block
+// of its row, at most three of them.  A wave so covers up to 96 blocks with three 32-byte loads, three
+// gathers and six DFMA pairs per lane, and pays ONE segmented sum over the lane groups (none at all
+// in the wide levels, where k = 1) -- the wave solve pays a five-round segmented sum and its bookkeeping
+// for every 32 blocks, which is what bounds it.  Everything a lane needs to know about
+// a wave is one 16-byte record shared by all scenarios and fetched one wave ahead: four 16-bit columns,
+// the first slot, and {row, lanes per row, span, flags}.  The factor blocks of wave w+1 do not depend on
+// x: they are requested right after the products of wave w, before its sum and its store.
+struct __align__(32) Blk256 { double a, b, c, d; };
+__device__ __forceinline__ Blk256 ld_blk_stream(const double2 *lu, int slot) {
+    Blk256 r;
+    asm volatile("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(r.a), "=d"(r.b), "=d"(r.c), "=d"(r.d) : "l"(lu + 2 * (size_t)slot));
+    return r;
+}
+
+#ifndef ROWS_REGS
+#define ROWS_REGS 64       // 28 warps per SM and room for a factorization CTA beside them, as k_solve_flat
+#endif
+#define ROWS_NB (helm::Symbolic::RL_BLOCKS)      // blocks per lane and wave
+#ifndef ROWS_PIN
+#define ROWS_PIN 1
+#endif
+#ifndef ROWS_UNROLL
+#define ROWS_UNROLL 2
+#endif
+constexpr int ROWS_WPB = 7;
+constexpr int ROWS_UNROLL_N = ROWS_UNROLL;
+
+// blocks t = T0 .. 3 of the lane (absent ones are skipped)
+template <int T0>
+__device__ __forceinline__ void rows_fetch(const double2 *lu, const int4 d, Blk256 (&m)[4]) {
+    using Sy = helm::Symbolic;
+    const int k = 1 << ((d.w >> 16) & 7);
+    const unsigned c0 = (unsigned)d.x & 0xFFFFu, c1 = (unsigned)d.x >> 16, c2 = (unsigned)d.y & 0xFFFFu, c3 = (unsigned)d.y >> 16;
+    if (T0 == 0 && c0 != Sy::RL_NONE) m[0] = ld_blk_stream(lu, d.z);
+    if (c1 != Sy::RL_NONE) m[1] = ld_blk_stream(lu, d.z + k);
+    if (c2 != Sy::RL_NONE) m[2] = ld_blk_stream(lu, d.z + 2 * k);
+    if (ROWS_NB > 3 && c3 != Sy::RL_NONE) m[3] = ld_blk_stream(lu, d.z + 3 * k);
+}
+
+template <int WPB>
+__global__ void __maxnreg__(ROWS_REGS) k_solve_rows(PlanDev p, WorkDev w) {
+    using Sy = helm::Symbolic;
+    TL_SCOPE(w, 2);
+    int grp = blockIdx.x * WPB + (threadIdx.x >> 5);
+    if (grp >= w.solve_count[w.parity]) return;              // one warp per entry of the step's solve list
+    grp = w.solve_list[(size_t)w.parity * w.ngroups + grp];
+    if (w.s_status[grp] != ST_ACTIVE) return;
+    const int lane = threadIdx.x & 31;
+#if ROWS_PIN
+    const double2 *lu = pin_ptr(lu_of(p, w, grp));
+    const double2 *rhs = pin_ptr(w.rhs + (size_t)grp * p.N);
+    double2 *xb = pin_ptr(w.xb + (size_t)grp * p.N);
+    const int4 *desc = pin_ptr(p.rl_desc + lane);
+    __builtin_assume(__isGlobal(lu));
+    __builtin_assume(__isGlobal(rhs));
+    __builtin_assume(__isGlobal(xb));
+    __builtin_assume(__isGlobal(desc));
+#else
+    const double2 *lu = lu_of(p, w, grp);
+    const double2 *rhs = w.rhs + (size_t)grp * p.N;
+    double2 *xb = w.xb + (size_t)grp * p.N;
+    const int4 *desc = p.rl_desc + lane;
+#endif
+    int4 d = __ldg(desc);
+    Blk256 m[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) m[t] = Blk256{0.0, 0.0, 0.0, 0.0};
+    rows_fetch<0>(lu, d, m);
+    for (int r = lane; r < p.n_rows_nol; r += 32) xb[r] = rhs[r];     // rows without L entries: y = rhs
+#pragma unroll ROWS_UNROLL_N
+    while (!(d.w & Sy::RL_STOP)) {                                    // the table ends with an idle wave that says stop
+        desc += 32;
+        const int4 dn = __ldg(desc);
+        if (d.w & Sy::RL_SYNC) __syncwarp();
+        const unsigned c0 = (unsigned)d.x & 0xFFFFu, c1 = (unsigned)d.x >> 16, c2 = (unsigned)d.y & 0xFFFFu, c3 = (unsigned)d.y >> 16;
+        const bool isu = (d.w & Sy::RL_ISU) != 0, head = (d.w & Sy::RL_HEAD) != 0;
+        const int row = d.w & 0xFFFF;
+        double2 x0 = make_double2(0.0, 0.0), x1 = x0, x2 = x0, x3 = x0;
+        // v = (first lane of a row: what the row sum is subtracted from) - sum of the lane's blocks
+        double2 v = x0;
+        if (c0 < Sy::RL_DIAG) x0 = xb[c0];
+        if (c1 != Sy::RL_NONE) x1 = xb[c1];
+        if (c2 != Sy::RL_NONE) x2 = xb[c2];
+        if (ROWS_NB > 3 && c3 != Sy::RL_NONE) x3 = xb[c3];
+        if (head) v = isu ? xb[row] : rhs[row];
+        if (c0 < Sy::RL_DIAG) { v.x -= m[0].a * x0.x + m[0].b * x0.y; v.y -= m[0].c * x0.x + m[0].d * x0.y; }
+        if (c1 != Sy::RL_NONE) { v.x -= m[1].a * x1.x + m[1].b * x1.y; v.y -= m[1].c * x1.x + m[1].d * x1.y; }
+        if (c2 != Sy::RL_NONE) { v.x -= m[2].a * x2.x + m[2].b * x2.y; v.y -= m[2].c * x2.x + m[2].d * x2.y; }
+        if (ROWS_NB > 3 && c3 != Sy::RL_NONE) { v.x -= m[3].a * x3.x + m[3].b * x3.y; v.y -= m[3].c * x3.x + m[3].d * x3.y; }
+        rows_fetch<1>(lu, dn, m);                                     // m[0] may still be this wave's pivot
+        const int span = (d.w >> 19) & 31, rounds = (d.w >> 27) & 7;
+        for (int r = 0; r < rounds; ++r) {
+            const int o = 1 << r;
+            const double tx = __shfl_down_sync(0xFFFFFFFFu, v.x, o);
+            const double ty = __shfl_down_sync(0xFFFFFFFFu, v.y, o);
+            add_if_le(v, tx, ty, o, span);
+        }
+        if (head) {
+            // U rows: the head lane's first block is the inverted pivot
+            if (isu) v = make_double2(m[0].a * v.x + m[0].b * v.y, m[0].c * v.x + m[0].d * v.y);
+            xb[row] = v;
+        }
+        if (((unsigned)dn.x & 0xFFFFu) != Sy::RL_NONE) m[0] = ld_blk_stream(lu, dn.z);
+        d = dn;
     }
 }
 
@@ -2297,6 +2410,8 @@ void launch_kernel(int which, const PlanDev &p, const WorkDev &w, cudaStream_t s
                 else k_solve_one<<<w.ngroups, ONE_T, one_layout(p.N, p.nwaves, p.nsegs, p.nonelist).total, st>>>(p, w, 2);
             } else if (G == 1 && p.use_cta_solve && w.ngroups <= p.cta_solve_max_groups) {
                 k_solve_cta<<<w.ngroups, CS_T, cta_solve_layout(p.N, p.nwaves, p.nschunks).total, st>>>(p, w, 0);
+            } else if (G == 1 && p.use_rows_solve) {
+                k_solve_rows<ROWS_WPB><<<(w.ngroups + ROWS_WPB - 1) / ROWS_WPB, ROWS_WPB * 32, 0, st>>>(p, w);
             } else if (G == 1) {
                 k_solve_flat<FLAT_WPB><<<(w.ngroups + FLAT_WPB - 1) / FLAT_WPB, FLAT_WPB * 32, 0, st>>>(p, w, 0);
             } else {
@@ -2538,6 +2653,13 @@ int helm_plan_create(const helm_grid_host *g, helm_plan **out) {
         d.solve_chunks = (const int4 *)ct;
     }
     d.nschunks = (int)S.solve_chunks.size() / 4;
+    {
+        const int *rd = nullptr;
+        if ((rc = upload(pl, S.rl_desc, &rd)) != HELM_OK) { helm_plan_destroy(pl); return rc; }
+        d.rl_desc = (const int4 *)rd;
+        d.rl_nwaves = S.rl_nwaves;
+        d.use_rows_solve = S.rl_nwaves > 0 && (getenv("HELM_B200_ROWS_SOLVE") ? atoi(getenv("HELM_B200_ROWS_SOLVE")) : 1);
+    }
     {
         const int *sg = nullptr;
         if ((rc = upload(pl, S.solve_segs, &sg)) != HELM_OK) { helm_plan_destroy(pl); return rc; }

@@ -474,6 +474,101 @@ bool build_symbolic(int N, const int32_t *adj_ptr, const int32_t *adj_idx, const
             }
     }
 
+    // ---- 4b-rows. row-lane solve schedule -----------------------------------------------------
+    // Every row of a level gets a power-of-two group of k lanes, k ~ blocks / RL_BLOCKS, and a lane walks at
+    // most RL_BLOCKS (<= 4) blocks of its row, every k-th one (U rows: the inverted pivot is the first block of the row's
+    // first lane).  So the blocks of a wave are fetched with up to four 32-byte loads per lane and summed
+    // ONCE per wave (segmented over the lane groups) instead of once per 32 blocks, and a level of few
+    // long rows still spreads over the warp.  Rows are placed largest group first, which aligns every
+    // group to its own size.
+    {
+        static_assert(Symbolic::RL_BLOCKS >= 1 && Symbolic::RL_BLOCKS <= 4, "the record holds four columns");
+        const int RL_T = getenv("HELM_B200_ROWS_T") ? std::max(1, std::min(Symbolic::RL_BLOCKS, atoi(getenv("HELM_B200_ROWS_T")))) : Symbolic::RL_BLOCKS;
+        S.rl_desc.clear();
+        S.rl_nwaves = 0;
+        struct Row { int slot0, n, row, k, diag; const int *cols; };
+        bool ok = N < Symbolic::RL_DIAG;
+        auto emit_level = [&](std::vector<Row> &rows, bool isU) {
+            for (Row &r : rows) {
+                int want = (r.n + RL_T - 1) / RL_T, k = 1;
+                while (k < want && k < 32) k <<= 1;
+                r.k = k;
+                if (r.n > RL_T * k) ok = false;
+            }
+            std::stable_sort(rows.begin(), rows.end(), [](const Row &a, const Row &b) { return a.k > b.k; });
+            size_t i = 0;
+            bool first = true;
+            while (i < rows.size()) {
+                int lanes = 0, maxk = 1;
+                const size_t i0 = i;
+                while (i < rows.size() && lanes + rows[i].k <= 32) {
+                    maxk = std::max(maxk, rows[i].k);
+                    lanes += rows[i].k;
+                    ++i;
+                }
+                int rounds = 0;
+                while ((1 << rounds) < maxk) ++rounds;
+                const int wflags = (first ? Symbolic::RL_SYNC : 0) | (isU ? Symbolic::RL_ISU : 0) | (rounds << 27);
+                first = false;
+                const size_t d0 = S.rl_desc.size();
+                S.rl_desc.resize(d0 + 4 * 32, 0);
+                int lane = 0;
+                for (size_t j = i0; j < i; ++j) {
+                    const Row &r = rows[j];
+                    int klog = 0;
+                    while ((1 << klog) < r.k) ++klog;
+                    for (int sub = 0; sub < r.k; ++sub, ++lane) {
+                        int c[4];
+                        for (int t = 0; t < 4; ++t) {
+                            const int b = sub + t * r.k;           // block of the row: [pivot |] entries
+                            if (b >= r.n) c[t] = Symbolic::RL_NONE;
+                            else if (r.diag && b == 0) c[t] = Symbolic::RL_DIAG;
+                            else c[t] = r.cols[b - r.diag];
+                        }
+                        int *d = &S.rl_desc[d0 + 4 * lane];
+                        d[0] = c[0] | (c[1] << 16);
+                        d[1] = c[2] | (c[3] << 16);
+                        d[2] = r.slot0 + sub;
+                        d[3] = (sub == 0 ? r.row : Symbolic::RL_NONE) | (klog << 16) | ((r.k - 1 - sub) << 19) |
+                               (sub == 0 ? Symbolic::RL_HEAD : 0) | wflags;
+                    }
+                }
+                for (; lane < 32; ++lane) {            // idle lanes: nothing to load, nothing to store
+                    int *d = &S.rl_desc[d0 + 4 * lane];
+                    d[0] = d[1] = (int)0xFFFFFFFFu;
+                    d[2] = 0;
+                    d[3] = Symbolic::RL_NONE | wflags;
+                }
+            }
+        };
+        std::vector<Row> rows;
+        for (int l = 0; l < nLlev; ++l) {
+            rows.clear();
+            for (int r = S.llev_ptr[l]; r < S.llev_ptr[l + 1]; ++r) {
+                const int n = S.lptr[r + 1] - S.lptr[r];
+                if (n > 0) rows.push_back(Row{S.lptr[r], n, r, 1, 0, S.lcol.data() + S.lptr[r]});
+            }
+            emit_level(rows, false);
+        }
+        for (int l = 0; l < nUlev; ++l) {
+            rows.clear();
+            for (int q = S.ulev_ptr[l]; q < S.ulev_ptr[l + 1]; ++q)
+                rows.push_back(Row{S.slotD(q), 1 + S.uptr[q + 1] - S.uptr[q], S.urow[q], 1, 1, S.ucol.data() + S.uptr[q]});
+            emit_level(rows, true);
+        }
+        if (ok) {
+            S.rl_nwaves = (int)S.rl_desc.size() / (4 * 32);
+            S.rl_desc.resize(S.rl_desc.size() + 4 * 32, 0);          // look-ahead past the last wave: an idle wave
+            for (int lane = 0; lane < 32; ++lane) {
+                int *d = &S.rl_desc[(size_t)S.rl_nwaves * 4 * 32 + 4 * lane];
+                d[0] = d[1] = (int)0xFFFFFFFFu;
+                d[3] = Symbolic::RL_NONE | Symbolic::RL_STOP;
+            }
+        } else {
+            S.rl_desc.clear();
+        }
+    }
+
     // ---- 4c. adjacency in the new numbering + assembly map -------------------------
     S.adj_ptr.assign(N + 1, 0);
     for (int r = 0; r < N; ++r) {

@@ -58,6 +58,22 @@ struct Symbolic {
     static constexpr int WAVE_ONEROW = 1 << 15;  // all blocks of the wave belong to one row (one piece of it)
     static constexpr int META_HEAD = 32, META_ROWSTART = 64, META_ROWEND = 128, META_DIAG = 256;  // span in bits 0-4
 
+    // row-lane solve schedule (k_solve_rows, symbolic.cpp 4b-rows): every row of a level gets a
+    // power-of-two group of k lanes; a lane walks every k-th block of its row, at most RL_BLOCKS.
+    // rl_desc: 4 ints per (wave, lane): {c0 | c1 << 16, c2 | c3 << 16, first slot, row | flags}
+    // c_t: column of the lane's t-th block (RL_NONE: no block, RL_DIAG: the row's inverted pivot);
+    // flags: lanes-per-row log2 in bits 16-18, span (lanes after this one in the row's group) in
+    // bits 19-23, then RL_HEAD / RL_SYNC / RL_ISU, shuffle rounds of the wave in bits 27-29.
+    // Empty (rl_nwaves = 0) when a row or the grid is too large for the packed record.
+    std::vector<int> rl_desc;
+    int rl_nwaves = 0;
+#ifndef HELM_RL_BLOCKS
+#define HELM_RL_BLOCKS 3       // measured: 3 blocks per lane fit 64 registers without spills (4 need 72)
+#endif
+    static constexpr int RL_BLOCKS = HELM_RL_BLOCKS;
+    static constexpr int RL_NONE = 0xFFFF, RL_DIAG = 0xFFFE;
+    static constexpr int RL_HEAD = 1 << 24, RL_SYNC = 1 << 25, RL_ISU = 1 << 26, RL_STOP = 1 << 30;
+
     inline int slotD(int q) const { return nL + uptr[q] + q; }
     inline int slotU(int q, int t) const { return nL + uptr[q] + q + 1 + t; }
 };

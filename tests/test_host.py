@@ -277,6 +277,105 @@ def test_flat_wave_schedule_solves(name):
     assert np.allclose(y, x, rtol=1e-9, atol=1e-9)
 
 
+@pytest.mark.parametrize('name', ['case9', 'case118', 'case1354pegase', 'case2869pegase', 'tiled'])
+def test_row_lane_schedule_solves(name):
+    """The packed per-lane records of k_solve_rows (symbolic.cpp 4b-rows), emulated lane by lane on the
+    host: every L entry, pivot and U entry is used exactly once, no lane gathers a value written inside
+    its own level, and x equals the plain row-by-row block solve."""
+    if name == 'tiled':
+        import synth
+        case = synth.tiled_case(['case1354pegase', 'case2869pegase', 'case118'])
+    else:
+        case = load_case(name)
+    S = _lib.symbolic_arrays(case.adj_ptr, case.adj_idx, case.bus_types_code())
+    N = case.N
+    lptr, lcol, uptr, ucol, urow = S['lptr'], S['lcol'], S['uptr'], S['ucol'], S['urow']
+    nL = int(lptr[-1])
+    nslots = nL + int(uptr[-1]) + N
+    desc = S['rl_desc'].reshape(-1, 32, 4)
+    assert len(desc) >= 2
+    nw = len(desc) - 1                      # the last record is the idle look-ahead wave
+    assert (desc[nw, :, 0] == -1).all() and (desc[nw, :, 3] == (0xFFFF | (1 << 30))).all()      # ... and says stop
+    assert not (desc[:nw, :, 3] & (1 << 30)).any()
+    rng = np.random.default_rng(5)
+    lu = rng.standard_normal((nslots, 2, 2))
+    rhs = rng.standard_normal((N, 2))
+    x = rhs.copy()
+    for r in range(N):
+        for e in range(lptr[r], lptr[r + 1]):
+            x[r] -= lu[e] @ x[lcol[e]]
+    for q in range(N):
+        r = urow[q]
+        base = nL + uptr[q] + q
+        acc = x[r].copy()
+        for t in range(uptr[q + 1] - uptr[q]):
+            acc -= lu[base + 1 + t] @ x[ucol[uptr[q] + t]]
+        x[r] = lu[base] @ acc
+    covered = np.zeros(nslots, dtype=int)
+    y = np.full((N, 2), np.nan)
+    nol = 0
+    while nol < N and lptr[nol + 1] == lptr[nol]:
+        nol += 1
+    y[:nol] = rhs[:nol]
+    final_u = np.zeros(N, dtype=bool)
+    this_level = set()
+    slot_col = S['slot_col']
+    seen_u = False
+    for w in range(nw):
+        d = desc[w]
+        flags = d[:, 3]
+        is_u = bool(flags[0] & (1 << 26))
+        assert ((flags >> 25) & 3 == (flags[0] >> 25) & 3).all() and ((flags >> 27) & 7 == (flags[0] >> 27) & 7).all()
+        assert is_u or not seen_u
+        seen_u = is_u
+        rounds = (int(flags[0]) >> 27) & 7
+        if flags[0] & (1 << 25):
+            this_level = set()
+        part = np.zeros((32, 2))
+        dinv = {}
+        for lane in range(32):
+            k = 1 << ((int(flags[lane]) >> 16) & 7)
+            cs = [int(d[lane, 0]) & 0xFFFF, (int(d[lane, 0]) >> 16) & 0xFFFF, int(d[lane, 1]) & 0xFFFF, (int(d[lane, 1]) >> 16) & 0xFFFF]
+            for t, c in enumerate(cs):
+                if c == 0xFFFF:
+                    continue
+                slot = int(d[lane, 2]) + t * k
+                covered[slot] += 1
+                if c == 0xFFFE:
+                    assert is_u and t == 0 and (flags[lane] & (1 << 24))
+                    dinv[lane] = lu[slot]
+                    continue
+                assert slot_col[slot] == c
+                assert not np.isnan(y[c]).any(), 'gather of a value that is not yet final'
+                assert c not in this_level, 'gather inside the level that writes the value'
+                assert final_u[c] or not is_u
+                part[lane] += lu[slot] @ y[c]
+        lane = 0
+        while lane < 32:
+            f = int(flags[lane])
+            row = f & 0xFFFF
+            span = (f >> 19) & 31
+            if not f & (1 << 24):
+                assert row == 0xFFFF and span == 0 and (part[lane] == 0).all()
+                lane += 1
+                continue
+            k = 1 << ((f >> 16) & 7)
+            assert span == k - 1 and lane % k == 0 and k <= (1 << rounds)
+            for j in range(1, k):
+                assert ((int(flags[lane + j]) >> 19) & 31) == k - 1 - j and not flags[lane + j] & (1 << 24)
+                assert ((int(flags[lane + j]) >> 16) & 7) == ((f >> 16) & 7)
+            v = part[lane:lane + k].sum(axis=0)
+            b = y[row] if is_u else rhs[row]
+            acc = b - v
+            y[row] = dinv[lane] @ acc if is_u else acc
+            this_level.add(row)
+            final_u[row] = is_u
+            lane += k
+    assert (covered == 1).all()
+    assert final_u.all()
+    assert np.allclose(y, x, rtol=1e-9, atol=1e-9)
+
+
 def _write_matpower(path, name, buses, branches, gens, base=100.0):
     def mat(a):
         return '\n'.join('\t' + '\t'.join(repr(float(v)) for v in row) + ';' for row in a)
