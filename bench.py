@@ -572,7 +572,7 @@ def roofline_model(info, ncoef, stats, N, shared_first_pass=True):
     b_eps_8d = (16.0 * sum_j_even + 32.0 * orders_even) * N    # sum over the even orders of 16 (m + 1), m = j + 1 terms
     # K2f factor: assembly (write) + factorization (read, write), 32 B per slot each, per factorized pass
     b_fac = passes_factored * (64.0 + 32.0) * nslots
-    knames = {'solve': 'k_solve_flat', 'rhs_conv': 'k_rhs_conv', 'eps': 'k_eps', 'factor': 'k_factor_coop'}
+    knames = {'solve': 'k_solve_rows', 'rhs_conv': 'k_rhs_conv', 'eps': 'k_eps', 'factor': 'k_factor_coop'}
     models = {
         'solve': 'SURVEY 8(d): 32 B per LU block / R + 32 B per bus, R = scenarios sharing the factors '
                  '(first-pass orders read one shared copy: charged no factor bytes)',

@@ -149,7 +149,7 @@ def symbolic_arrays(adj_ptr, adj_idx, bus_type=None):
                      "llev_ptr", "urow", "qof", "ulev_ptr", "uptr", "ucol", "dslot", "fptr",
                      "fsrc", "fdst", "fdst_local", "fchunk_row", "fchunk_lpr", "flev_chunk", "frow_off",
                      "slot_src", "slot_row", "slot_col", "wave_tab", "smeta", "scm", "solve_chunks", "solve_segs", "one_lists",
-                     "rl_desc"):
+                     "rl_desc", "rc_lists", "rc_segend", "rc_desc", "rc_seg"):
             data = C.c_void_p()
             n = C.c_int32()
             rc = lib.helm_symbolic_array(h, name.encode(), C.byref(data), C.byref(n))

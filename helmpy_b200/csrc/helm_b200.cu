@@ -85,6 +85,9 @@ struct PlanDev {
     int nsegs, use_one_solve, nonelist;
     const int4 *rl_desc;
     int rl_nwaves, use_rows_solve;
+    const int *rc_lists, *rc_segend, *rc_seg;
+    const int4 *rc_desc;
+    int rc_nsegs, use_rows_cta, use_rows_deep;
 };
 
 struct WorkDev {
@@ -942,10 +945,17 @@ __global__ void __maxnreg__(64) k_solve_flat(PlanDev p, WorkDev w, int side) {
 // the first slot, and {row, lanes per row, span, flags}.  The factor blocks of wave w+1 do not depend on
 // x: they are requested right after the products of wave w, before its sum and its store.
 struct __align__(32) Blk256 { double a, b, c, d; };
+// STREAM: evict-first (large batches read every private factor block once per solve); otherwise the
+// default policy, so that the factors of a few scenarios stay in L2 from one order to the next
+template <bool STREAM = true>
 __device__ __forceinline__ Blk256 ld_blk_stream(const double2 *lu, int slot) {
     Blk256 r;
-    asm volatile("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];"
-                 : "=d"(r.a), "=d"(r.b), "=d"(r.c), "=d"(r.d) : "l"(lu + 2 * (size_t)slot));
+    if (STREAM)
+        asm volatile("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];"
+                     : "=d"(r.a), "=d"(r.b), "=d"(r.c), "=d"(r.d) : "l"(lu + 2 * (size_t)slot));
+    else
+        asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+                     : "=d"(r.a), "=d"(r.b), "=d"(r.c), "=d"(r.d) : "l"(lu + 2 * (size_t)slot));
     return r;
 }
 
@@ -962,16 +972,14 @@ __device__ __forceinline__ Blk256 ld_blk_stream(const double2 *lu, int slot) {
 constexpr int ROWS_WPB = 7;
 constexpr int ROWS_UNROLL_N = ROWS_UNROLL;
 
-// blocks t = T0 .. 3 of the lane (absent ones are skipped)
-template <int T0>
-__device__ __forceinline__ void rows_fetch(const double2 *lu, const int4 d, Blk256 (&m)[4]) {
-    using Sy = helm::Symbolic;
-    const int k = 1 << ((d.w >> 16) & 7);
-    const unsigned c0 = (unsigned)d.x & 0xFFFFu, c1 = (unsigned)d.x >> 16, c2 = (unsigned)d.y & 0xFFFFu, c3 = (unsigned)d.y >> 16;
-    if (T0 == 0 && c0 != Sy::RL_NONE) m[0] = ld_blk_stream(lu, d.z);
-    if (c1 != Sy::RL_NONE) m[1] = ld_blk_stream(lu, d.z + k);
-    if (c2 != Sy::RL_NONE) m[2] = ld_blk_stream(lu, d.z + 2 * k);
-    if (ROWS_NB > 3 && c3 != Sy::RL_NONE) m[3] = ld_blk_stream(lu, d.z + 3 * k);
+// blocks t = T0 .. of the lane, from the record's fetch word (slot | lanes-per-row log2 << 24 | blocks << 27)
+template <int T0, bool STREAM = true>
+__device__ __forceinline__ void rows_fetch(const double2 *lu, const int f, Blk256 (&m)[4]) {
+    const int k = 1 << ((f >> 24) & 7), cnt = (f >> 27) & 7, slot = f & 0xFFFFFF;
+    if (T0 == 0 && cnt > 0) m[0] = ld_blk_stream<STREAM>(lu, slot);
+    if (cnt > 1) m[1] = ld_blk_stream<STREAM>(lu, slot + k);
+    if (cnt > 2) m[2] = ld_blk_stream<STREAM>(lu, slot + 2 * k);
+    if (ROWS_NB > 3 && cnt > 3) m[3] = ld_blk_stream<STREAM>(lu, slot + 3 * k);
 }
 
 template <int WPB>
@@ -1002,12 +1010,16 @@ __global__ void __maxnreg__(ROWS_REGS) k_solve_rows(PlanDev p, WorkDev w) {
     Blk256 m[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) m[t] = Blk256{0.0, 0.0, 0.0, 0.0};
-    rows_fetch<0>(lu, d, m);
-    for (int r = lane; r < p.n_rows_nol; r += 32) xb[r] = rhs[r];     // rows without L entries: y = rhs
+    rows_fetch<0>(lu, d.z, m);
+    // (L2 evict-last hints on the accesses to x: 288 -> 283 ms per 16 384 scenarios, dropped)
+#define LDX(ptr) (*(ptr))
+#define STX(ptr, v) (*(ptr) = (v))
+    for (int r = lane; r < p.n_rows_nol; r += 32) STX(xb + r, __ldcs(rhs + r));     // rows without L entries: y = rhs
 #pragma unroll ROWS_UNROLL_N
-    while (!(d.w & Sy::RL_STOP)) {                                    // the table ends with an idle wave that says stop
+    while (!(d.w & Sy::RL_STOP)) {                                    // the table ends with idle waves that say stop
         desc += 32;
         const int4 dn = __ldg(desc);
+        const int f1 = dn.z;                                          // (reading the fetch word two waves ahead was measured slower)
         if (d.w & Sy::RL_SYNC) __syncwarp();
         const unsigned c0 = (unsigned)d.x & 0xFFFFu, c1 = (unsigned)d.x >> 16, c2 = (unsigned)d.y & 0xFFFFu, c3 = (unsigned)d.y >> 16;
         const bool isu = (d.w & Sy::RL_ISU) != 0, head = (d.w & Sy::RL_HEAD) != 0;
@@ -1015,16 +1027,16 @@ __global__ void __maxnreg__(ROWS_REGS) k_solve_rows(PlanDev p, WorkDev w) {
         double2 x0 = make_double2(0.0, 0.0), x1 = x0, x2 = x0, x3 = x0;
         // v = (first lane of a row: what the row sum is subtracted from) - sum of the lane's blocks
         double2 v = x0;
-        if (c0 < Sy::RL_DIAG) x0 = xb[c0];
-        if (c1 != Sy::RL_NONE) x1 = xb[c1];
-        if (c2 != Sy::RL_NONE) x2 = xb[c2];
-        if (ROWS_NB > 3 && c3 != Sy::RL_NONE) x3 = xb[c3];
-        if (head) v = isu ? xb[row] : rhs[row];
+        if (c0 < Sy::RL_DIAG) x0 = LDX(xb + c0);
+        if (c1 != Sy::RL_NONE) x1 = LDX(xb + c1);
+        if (c2 != Sy::RL_NONE) x2 = LDX(xb + c2);
+        if (ROWS_NB > 3 && c3 != Sy::RL_NONE) x3 = LDX(xb + c3);
+        if (head) v = isu ? LDX(xb + row) : __ldcs(rhs + row);
         if (c0 < Sy::RL_DIAG) { v.x -= m[0].a * x0.x + m[0].b * x0.y; v.y -= m[0].c * x0.x + m[0].d * x0.y; }
         if (c1 != Sy::RL_NONE) { v.x -= m[1].a * x1.x + m[1].b * x1.y; v.y -= m[1].c * x1.x + m[1].d * x1.y; }
         if (c2 != Sy::RL_NONE) { v.x -= m[2].a * x2.x + m[2].b * x2.y; v.y -= m[2].c * x2.x + m[2].d * x2.y; }
         if (ROWS_NB > 3 && c3 != Sy::RL_NONE) { v.x -= m[3].a * x3.x + m[3].b * x3.y; v.y -= m[3].c * x3.x + m[3].d * x3.y; }
-        rows_fetch<1>(lu, dn, m);                                     // m[0] may still be this wave's pivot
+        rows_fetch<1>(lu, f1, m);                                     // m[0] may still be this wave's pivot
         const int span = (d.w >> 19) & 31, rounds = (d.w >> 27) & 7;
         for (int r = 0; r < rounds; ++r) {
             const int o = 1 << r;
@@ -1035,11 +1047,261 @@ __global__ void __maxnreg__(ROWS_REGS) k_solve_rows(PlanDev p, WorkDev w) {
         if (head) {
             // U rows: the head lane's first block is the inverted pivot
             if (isu) v = make_double2(m[0].a * v.x + m[0].b * v.y, m[0].c * v.x + m[0].d * v.y);
-            xb[row] = v;
+            STX(xb + row, v);
         }
-        if (((unsigned)dn.x & 0xFFFFu) != Sy::RL_NONE) m[0] = ld_blk_stream(lu, dn.z);
+        if (f1 >> 27) m[0] = ld_blk_stream(lu, f1 & 0xFFFFFF);
         d = dn;
     }
+#undef LDX
+#undef STX
+}
+
+// ---- K2 (G = 1), row-lane solve with x in shared memory ---------------------------------------------
+// One CTA of RC_WARPS warps per scenario; x (16 B per bus) lives in shared memory, so the gathers, the
+// row stores and the ordering between levels never leave the SM and a solve moves nothing but its
+// factors, rhs in and x out (k_solve_rows re-reads 2/3 of its gathers from DRAM: the x of the resident
+// scenarios, 188 MB, does not stay in L2 beside the factor stream).  Same packed records as
+// k_solve_rows; the host deals the waves of a level with several waves to the warps (a SEGMENT, one
+// block barrier after it) and gives a run of one-wave levels to warp 0, which walks it with warp barriers
+// only (symbolic.cpp, rc_lists).  A warp fetches the record and the factor blocks of its NEXT wave before
+// it waits for anything, and one thread keeps an L2 prefetch of the scenario's factor stream a fixed
+// distance ahead of the segment being solved.
+constexpr int RC_WARPS = helm::Symbolic::RC_WARPS;
+constexpr int RC_T = RC_WARPS * 32;
+#ifndef RC_PF_SLOTS
+#define RC_PF_SLOTS 2048      // L2 prefetch distance of the factor stream, in 32-byte slots
+#endif
+
+__device__ __forceinline__ void bulk_prefetch_l2(const void *gsrc, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
+
+// one wave of a warp of k_solve_rows_cta: record d, blocks m (m[0] of the NEXT wave is requested at the end,
+// the others right after the products), fn = fetch word of the next wave
+__device__ __forceinline__ void prefetch_l1(const void *ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
+
+// fnn = fetch word two waves ahead: small batches (default cache policy) pull those blocks into L1 now, so
+// that the request one wave ahead costs an L1 hit instead of an L2 round trip on the dependent chain
+template <bool STREAM>
+__device__ __forceinline__ void rc_wave(const double2 *lu, double2 *xs, const int4 d, int fn, const int fnn, Blk256 (&m)[4], const int abl = 0) {
+    using Sy = helm::Symbolic;
+    if (abl & 2) fn &= 0xFFFFFF;                                      // timing ablation: no factor loads
+    if (false) {                                                      // measured: 115 vs 98 us per solve alone, slower
+        const int k = 1 << ((fnn >> 24) & 7), cnt = (fnn >> 27) & 7, slot = fnn & 0xFFFFFF;
+        if (cnt > 0) prefetch_l1(lu + 2 * (size_t)slot);
+        if (cnt > 1) prefetch_l1(lu + 2 * (size_t)(slot + k));
+        if (cnt > 2) prefetch_l1(lu + 2 * (size_t)(slot + 2 * k));
+        if (ROWS_NB > 3 && cnt > 3) prefetch_l1(lu + 2 * (size_t)(slot + 3 * k));
+    }
+    if (d.w & Sy::RL_SYNC) __syncwarp();                              // a run of one-wave levels: ordered inside the warp
+    const unsigned c0 = (unsigned)d.x & 0xFFFFu, c1 = (unsigned)d.x >> 16, c2 = (unsigned)d.y & 0xFFFFu, c3 = (unsigned)d.y >> 16;
+    const bool isu = (d.w & Sy::RL_ISU) != 0, head = (d.w & Sy::RL_HEAD) != 0;
+    const int row = d.w & 0xFFFF;
+    double2 x0 = make_double2(0.0, 0.0), x1 = x0, x2 = x0, x3 = x0;
+    double2 v = x0;
+    if (!(abl & 4)) {
+    if (c0 < Sy::RL_DIAG) x0 = xs[c0];
+    if (c1 != Sy::RL_NONE) x1 = xs[c1];
+    if (c2 != Sy::RL_NONE) x2 = xs[c2];
+    if (ROWS_NB > 3 && c3 != Sy::RL_NONE) x3 = xs[c3];
+    }
+    if (head) v = xs[row];                                            // rhs (forward) or y (backward), solved in place
+    if (c0 < Sy::RL_DIAG) { v.x -= m[0].a * x0.x + m[0].b * x0.y; v.y -= m[0].c * x0.x + m[0].d * x0.y; }
+    if (c1 != Sy::RL_NONE) { v.x -= m[1].a * x1.x + m[1].b * x1.y; v.y -= m[1].c * x1.x + m[1].d * x1.y; }
+    if (c2 != Sy::RL_NONE) { v.x -= m[2].a * x2.x + m[2].b * x2.y; v.y -= m[2].c * x2.x + m[2].d * x2.y; }
+    if (ROWS_NB > 3 && c3 != Sy::RL_NONE) { v.x -= m[3].a * x3.x + m[3].b * x3.y; v.y -= m[3].c * x3.x + m[3].d * x3.y; }
+    rows_fetch<1, STREAM>(lu, fn, m);                                 // m[0] may still be this wave's pivot
+    const int span = (d.w >> 19) & 31, rounds = (abl & 1) ? 0 : (d.w >> 27) & 7;
+    for (int r = 0; r < rounds; ++r) {
+        const int o = 1 << r;
+        const double tx = __shfl_down_sync(0xFFFFFFFFu, v.x, o);
+        const double ty = __shfl_down_sync(0xFFFFFFFFu, v.y, o);
+        add_if_le(v, tx, ty, o, span);
+    }
+    if (head) {
+        if (isu) v = make_double2(m[0].a * v.x + m[0].b * v.y, m[0].c * v.x + m[0].d * v.y);
+        xs[row] = v;
+    }
+    if (fn >> 27) m[0] = ld_blk_stream<STREAM>(lu, fn & 0xFFFFFF);
+}
+
+template <bool STREAM>
+__global__ void __launch_bounds__(RC_T, 4) k_solve_rows_cta(PlanDev p, WorkDev w, int mode) {
+    using Sy = helm::Symbolic;
+    TL_SCOPE(w, 2);
+    extern __shared__ __align__(16) double2 xs_rc[];
+    const int abl = mode >> 8;                               // timing ablations (helm_debug_solve_time); 0 in production
+    mode &= 255;
+    int grp;
+    if (mode == 2) {                                         // one CTA per entry of the step's solve list
+        if ((int)blockIdx.x >= w.solve_count[w.parity]) return;
+        grp = w.solve_list[(size_t)w.parity * w.ngroups + blockIdx.x];
+    } else {
+        grp = blockIdx.x;
+        const int gfl = w.g_flags[grp];
+        if (mode ? !(gfl & GF_FACTORING) : (gfl & (GF_DONE | GF_FACTORING)) != 0) return;
+    }
+    if (w.s_status[grp] != ST_ACTIVE) return;
+    const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+    const int N = p.N, nsegs = p.rc_nsegs;
+    double2 *xs = xs_rc;
+    const double2 *lu = lu_of(p, w, grp);
+    const double2 *rhs = w.rhs + (size_t)grp * N;
+    double2 *xb = w.xb + (size_t)grp * N;
+    const bool stream = STREAM && lu != w.lu_shared;         // the shared first-pass factors sit in L2 anyway
+    int pf = 0;                                              // prefetch frontier (slot)
+    if (tid == 0 && stream) {
+        pf = min(RC_PF_SLOTS, p.nslots);
+        bulk_prefetch_l2(lu, (unsigned)pf * 32u);
+    }
+    // the warp's program: its records in order, ending with two idle waves that say stop
+    const int first = __ldg(p.rc_lists + wp);
+    const int4 *desc = p.rc_desc + (size_t)first * 32 + lane;
+    const int *sgp = p.rc_seg + first;
+    int4 da = __ldg(desc), db;
+    int fa, fb = __ldg(&desc[32].z), fc;                              // fetch word of the next wave
+    int sa = __ldg(sgp), sb;
+    Blk256 m[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) m[t] = Blk256{0.0, 0.0, 0.0, 0.0};
+    rows_fetch<0, STREAM>(lu, da.z, m);
+    for (int i = tid; i < N; i += RC_T) xs[i] = __ldcs(rhs + i);      // rows without L entries: y = rhs
+    __syncthreads();
+    int seg = 0;
+    auto barriers = [&](int upto) {                                   // block barriers up to the wave's segment
+        while (seg < upto) {
+            if (!(abl & 8)) __syncthreads();
+            ++seg;
+            if (tid == 0 && stream) {
+                const int end = min(__ldg(p.rc_segend + min(seg, nsegs - 1)) + RC_PF_SLOTS, p.nslots);
+                if (end > pf) { bulk_prefetch_l2(lu + 2 * (size_t)pf, (unsigned)(end - pf) * 32u); pf = end; }
+            }
+        }
+    };
+    // two waves per trip, so that no look-ahead value is ever copied from one register to another
+    // (a copy waits for the load it copies)
+    while (true) {
+        if (da.w & Sy::RL_STOP) break;
+        db = __ldg(desc + 32); fa = __ldg(&desc[64].z); sb = __ldg(sgp + 1);
+        fc = __ldg(&desc[96].z);                                      // (may read into the next warp's stream: the table is padded)
+        barriers(sa);
+        if (!(abl & 16)) rc_wave<STREAM>(lu, xs, da, fb, fa, m, abl);
+        if (db.w & Sy::RL_STOP) break;
+        desc += 64; sgp += 2;
+        da = __ldg(desc); sa = __ldg(sgp);
+        barriers(sb);
+        if (!(abl & 16)) rc_wave<STREAM>(lu, xs, db, fa, fc, m, abl);
+        fb = fc;
+    }
+    barriers(nsegs);                                                  // every warp passes every barrier
+    for (int i = tid; i < N; i += RC_T) xb[i] = xs[i];
+}
+
+// Latency variant for small batches and the single-case path (one CTA per SM at most, registers are
+// free): the records of a warp's next FOUR waves and the factor blocks of its next TWO waves are in
+// registers, so nothing on the dependent chain of a run of one-wave levels waits for a table or a factor
+// (ablation of k_solve_rows_cta alone, tools/solve_time.py: walking the records one wave ahead costs 31 of
+// 98 us, the factor requests one wave ahead 16).
+struct RcDeep {
+    const double2 *lu;
+    double2 *xs;
+};
+__device__ __forceinline__ void rcd_fetch_rest(const double2 *lu, const int f, Blk256 (&m)[4]) { rows_fetch<1, false>(lu, f, m); }
+
+// one wave: record d, its blocks in m; f2 = fetch word two waves ahead, whose blocks replace m
+__device__ __forceinline__ void rcd_wave(const RcDeep &c, const int4 d, const int f2, Blk256 (&m)[4]) {
+    using Sy = helm::Symbolic;
+    double2 *xs = c.xs;
+    if (d.w & Sy::RL_SYNC) __syncwarp();
+    const unsigned c0 = (unsigned)d.x & 0xFFFFu, c1 = (unsigned)d.x >> 16, c2 = (unsigned)d.y & 0xFFFFu, c3 = (unsigned)d.y >> 16;
+    const bool isu = (d.w & Sy::RL_ISU) != 0, head = (d.w & Sy::RL_HEAD) != 0;
+    const int row = d.w & 0xFFFF;
+    double2 x0 = make_double2(0.0, 0.0), x1 = x0, x2 = x0, x3 = x0;
+    double2 v = x0;
+    if (c0 < Sy::RL_DIAG) x0 = xs[c0];
+    if (c1 != Sy::RL_NONE) x1 = xs[c1];
+    if (c2 != Sy::RL_NONE) x2 = xs[c2];
+    if (ROWS_NB > 3 && c3 != Sy::RL_NONE) x3 = xs[c3];
+    if (head) v = xs[row];
+    if (c0 < Sy::RL_DIAG) { v.x -= m[0].a * x0.x + m[0].b * x0.y; v.y -= m[0].c * x0.x + m[0].d * x0.y; }
+    if (c1 != Sy::RL_NONE) { v.x -= m[1].a * x1.x + m[1].b * x1.y; v.y -= m[1].c * x1.x + m[1].d * x1.y; }
+    if (c2 != Sy::RL_NONE) { v.x -= m[2].a * x2.x + m[2].b * x2.y; v.y -= m[2].c * x2.x + m[2].d * x2.y; }
+    if (ROWS_NB > 3 && c3 != Sy::RL_NONE) { v.x -= m[3].a * x3.x + m[3].b * x3.y; v.y -= m[3].c * x3.x + m[3].d * x3.y; }
+    rcd_fetch_rest(c.lu, f2, m);
+    const int span = (d.w >> 19) & 31, rounds = (d.w >> 27) & 7;
+    for (int r = 0; r < rounds; ++r) {
+        const int o = 1 << r;
+        const double tx = __shfl_down_sync(0xFFFFFFFFu, v.x, o);
+        const double ty = __shfl_down_sync(0xFFFFFFFFu, v.y, o);
+        add_if_le(v, tx, ty, o, span);
+    }
+    if (head) {
+        if (isu) v = make_double2(m[0].a * v.x + m[0].b * v.y, m[0].c * v.x + m[0].d * v.y);
+        xs[row] = v;
+    }
+    if (f2 >> 27) m[0] = ld_blk_stream<false>(c.lu, f2 & 0xFFFFFF);
+}
+
+__global__ void __launch_bounds__(RC_T, 1) k_solve_rows_deep(PlanDev p, WorkDev w, int mode) {
+    using Sy = helm::Symbolic;
+    TL_SCOPE(w, 2);
+    extern __shared__ __align__(16) double2 xs_rc[];
+    int grp;
+    if (mode == 2) {
+        if ((int)blockIdx.x >= w.solve_count[w.parity]) return;
+        grp = w.solve_list[(size_t)w.parity * w.ngroups + blockIdx.x];
+    } else {
+        grp = blockIdx.x;
+        const int gfl = w.g_flags[grp];
+        if (mode ? !(gfl & GF_FACTORING) : (gfl & (GF_DONE | GF_FACTORING)) != 0) return;
+    }
+    if (w.s_status[grp] != ST_ACTIVE) return;
+    const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+    const int N = p.N, nsegs = p.rc_nsegs;
+    RcDeep c;
+    c.lu = lu_of(p, w, grp);
+    c.xs = xs_rc;
+    const double2 *rhs = w.rhs + (size_t)grp * N;
+    double2 *xb = w.xb + (size_t)grp * N;
+    const int first = __ldg(p.rc_lists + wp);
+    const int4 *desc = p.rc_desc + (size_t)first * 32 + lane;
+    const int *sgp = p.rc_seg + first;
+    int4 r0 = __ldg(desc), r1 = __ldg(desc + 32), r2 = __ldg(desc + 64), r3 = __ldg(desc + 96);
+    int s0 = __ldg(sgp), s1 = __ldg(sgp + 1), s2 = __ldg(sgp + 2), s3 = __ldg(sgp + 3);
+    Blk256 ma[4], mb[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) ma[t] = mb[t] = Blk256{0.0, 0.0, 0.0, 0.0};
+    rows_fetch<0, false>(c.lu, r0.z, ma);
+    rows_fetch<0, false>(c.lu, r1.z, mb);
+    for (int i = tid; i < N; i += RC_T) c.xs[i] = rhs[i];             // rows without L entries: y = rhs
+    __syncthreads();
+    int seg = 0;
+    auto barriers = [&](int upto) {
+        while (seg < upto) { __syncthreads(); ++seg; }
+    };
+    // four waves per trip: a record is reloaded (four waves ahead) right after its wave, a block set
+    // (two waves ahead) inside its wave
+    while (true) {
+        if (r0.w & Sy::RL_STOP) break;
+        barriers(s0);
+        rcd_wave(c, r0, r2.z, ma);
+        r0 = __ldg(desc + 128); s0 = __ldg(sgp + 4);
+        if (r1.w & Sy::RL_STOP) break;
+        barriers(s1);
+        rcd_wave(c, r1, r3.z, mb);
+        r1 = __ldg(desc + 160); s1 = __ldg(sgp + 5);
+        if (r2.w & Sy::RL_STOP) break;
+        barriers(s2);
+        rcd_wave(c, r2, r0.z, ma);
+        r2 = __ldg(desc + 192); s2 = __ldg(sgp + 6);
+        if (r3.w & Sy::RL_STOP) break;
+        barriers(s3);
+        rcd_wave(c, r3, r1.z, mb);
+        r3 = __ldg(desc + 224); s3 = __ldg(sgp + 7);
+        desc += 128; sgp += 4;
+    }
+    barriers(nsegs);                                                  // every warp passes every barrier
+    for (int i = tid; i < N; i += RC_T) xb[i] = c.xs[i];
 }
 
 // ---- K2 (G = 1), shared-memory wave solve --------------------------------------------------------
@@ -2405,11 +2667,15 @@ void launch_kernel(int which, const PlanDev &p, const WorkDev &w, cudaStream_t s
         case KI_SOLVE:
             // small batches: CTA per scenario with x in shared memory (shortest dependency chain);
             // large batches: warp per scenario, all resident scenarios in one round
-            if (G == 1 && p.use_one_solve && (w.ngroups <= p.cta_solve_max_groups || p.use_one_solve == 2)) {
+            if (G == 1 && p.use_rows_deep && w.ngroups <= p.cta_solve_max_groups) {
+                k_solve_rows_deep<<<w.ngroups, RC_T, (size_t)p.N * sizeof(double2), st>>>(p, w, 0);
+            } else if (G == 1 && p.use_one_solve && (w.ngroups <= p.cta_solve_max_groups || p.use_one_solve == 2)) {
                 if (w.ngroups <= p.cta_solve_max_groups) k_solve_one<<<w.ngroups, ONE_T, one_layout(p.N, p.nwaves, p.nsegs, p.nonelist).total, st>>>(p, w, 0);
                 else k_solve_one<<<w.ngroups, ONE_T, one_layout(p.N, p.nwaves, p.nsegs, p.nonelist).total, st>>>(p, w, 2);
             } else if (G == 1 && p.use_cta_solve && w.ngroups <= p.cta_solve_max_groups) {
                 k_solve_cta<<<w.ngroups, CS_T, cta_solve_layout(p.N, p.nwaves, p.nschunks).total, st>>>(p, w, 0);
+            } else if (G == 1 && p.use_rows_cta) {
+                k_solve_rows_cta<true><<<w.ngroups, RC_T, (size_t)p.N * sizeof(double2), st>>>(p, w, 2);
             } else if (G == 1 && p.use_rows_solve) {
                 k_solve_rows<ROWS_WPB><<<(w.ngroups + ROWS_WPB - 1) / ROWS_WPB, ROWS_WPB * 32, 0, st>>>(p, w);
             } else if (G == 1) {
@@ -2659,6 +2925,23 @@ int helm_plan_create(const helm_grid_host *g, helm_plan **out) {
         d.rl_desc = (const int4 *)rd;
         d.rl_nwaves = S.rl_nwaves;
         d.use_rows_solve = S.rl_nwaves > 0 && (getenv("HELM_B200_ROWS_SOLVE") ? atoi(getenv("HELM_B200_ROWS_SOLVE")) : 1);
+        UP(S.rc_lists, rc_lists) UP(S.rc_segend, rc_segend) UP(S.rc_seg, rc_seg)
+        {
+            const int *rq = nullptr;
+            if ((rc = upload(pl, S.rc_desc, &rq)) != HELM_OK) { helm_plan_destroy(pl); return rc; }
+            d.rc_desc = (const int4 *)rq;
+        }
+        d.rc_nsegs = S.rc_nsegs;
+        const size_t xsm = (size_t)N * sizeof(double2);
+        d.use_rows_cta = S.rl_nwaves > 0 && xsm <= 225 * 1024 && (getenv("HELM_B200_ROWS_CTA") ? atoi(getenv("HELM_B200_ROWS_CTA")) : 0);
+        d.use_rows_deep = S.rl_nwaves > 0 && xsm <= 225 * 1024 && (getenv("HELM_B200_ROWS_DEEP") ? atoi(getenv("HELM_B200_ROWS_DEEP")) : 1);
+        static size_t xsm_set = 48 * 1024;
+        if (S.rl_nwaves > 0 && xsm <= 225 * 1024 && xsm > xsm_set) {
+            CUDA_TRY(cudaFuncSetAttribute(k_solve_rows_cta<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xsm));
+            CUDA_TRY(cudaFuncSetAttribute(k_solve_rows_cta<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xsm));
+            CUDA_TRY(cudaFuncSetAttribute(k_solve_rows_deep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xsm));
+            xsm_set = xsm;
+        }
     }
     {
         const int *sg = nullptr;
@@ -3220,7 +3503,8 @@ int helm_debug_factor_solve(helm_plan *pl, int32_t B, int32_t group, const uint8
 
 int helm_debug_solve_time(helm_plan *pl, int32_t kernel, int32_t ablation, int32_t reps, double *ms_per_solve) {
     // one scenario, base bus types, random right-hand side: factorize once, then time `reps` launches
-    // of one triangular-solve kernel (0: k_solve_one, 1: k_solve_cta, 2: k_solve_flat) with CUDA events
+    // of one triangular-solve kernel (0: k_solve_one, 1: k_solve_cta, 2: k_solve_flat, 3: k_solve_rows_cta,
+    // 4: k_solve_rows) with CUDA events
     if (!pl || !ms_per_solve || reps <= 0) { g_err = "null/invalid argument"; return HELM_E_ARG; }
     helm_params prm;
     memset(&prm, 0, sizeof(prm));
@@ -3246,6 +3530,11 @@ int helm_debug_solve_time(helm_plan *pl, int32_t kernel, int32_t ablation, int32
     auto launch = [&]() {
         if (kernel == 0) k_solve_one<<<1, ONE_T, one_layout(p.N, p.nwaves, p.nsegs, p.nonelist).total>>>(p, w, ablation << 8);
         else if (kernel == 1) k_solve_cta<<<1, CS_T, cta_solve_layout(p.N, p.nwaves, p.nschunks).total>>>(p, w, 0);
+        else if (kernel == 3 && p.rl_nwaves > 0) {
+            k_solve_rows_cta<false><<<1, RC_T, (size_t)p.N * sizeof(double2)>>>(p, w, ablation << 8);
+        }
+        else if (kernel == 4 && p.rl_nwaves > 0) k_solve_rows<ROWS_WPB><<<1, ROWS_WPB * 32>>>(p, w);
+        else if (kernel == 5 && p.rl_nwaves > 0) k_solve_rows_deep<<<1, RC_T, (size_t)p.N * sizeof(double2)>>>(p, w, 0);
         else k_solve_flat<FLAT_WPB><<<1, FLAT_WPB * 32>>>(p, w, 0);
     };
     for (int i = 0; i < 3; ++i) launch();

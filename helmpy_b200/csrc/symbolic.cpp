@@ -487,7 +487,7 @@ bool build_symbolic(int N, const int32_t *adj_ptr, const int32_t *adj_idx, const
         S.rl_desc.clear();
         S.rl_nwaves = 0;
         struct Row { int slot0, n, row, k, diag; const int *cols; };
-        bool ok = N < Symbolic::RL_DIAG;
+        bool ok = N < Symbolic::RL_DIAG && S.nslots < (1 << 24);
         auto emit_level = [&](std::vector<Row> &rows, bool isU) {
             for (Row &r : rows) {
                 int want = (r.n + RL_T - 1) / RL_T, k = 1;
@@ -528,7 +528,9 @@ bool build_symbolic(int N, const int32_t *adj_ptr, const int32_t *adj_idx, const
                         int *d = &S.rl_desc[d0 + 4 * lane];
                         d[0] = c[0] | (c[1] << 16);
                         d[1] = c[2] | (c[3] << 16);
-                        d[2] = r.slot0 + sub;
+                        int cnt = 0;
+                        while (cnt < 4 && c[cnt] != Symbolic::RL_NONE) ++cnt;
+                        d[2] = (r.slot0 + sub) | (klog << 24) | (cnt << 27);
                         d[3] = (sub == 0 ? r.row : Symbolic::RL_NONE) | (klog << 16) | ((r.k - 1 - sub) << 19) |
                                (sub == 0 ? Symbolic::RL_HEAD : 0) | wflags;
                     }
@@ -558,14 +560,71 @@ bool build_symbolic(int N, const int32_t *adj_ptr, const int32_t *adj_idx, const
         }
         if (ok) {
             S.rl_nwaves = (int)S.rl_desc.size() / (4 * 32);
-            S.rl_desc.resize(S.rl_desc.size() + 4 * 32, 0);          // look-ahead past the last wave: an idle wave
-            for (int lane = 0; lane < 32; ++lane) {
+            S.rl_desc.resize(S.rl_desc.size() + 2 * 4 * 32, 0);      // look-ahead past the last wave: two idle waves
+            for (int lane = 0; lane < 64; ++lane) {
                 int *d = &S.rl_desc[(size_t)S.rl_nwaves * 4 * 32 + 4 * lane];
                 d[0] = d[1] = (int)0xFFFFFFFFu;
                 d[3] = Symbolic::RL_NONE | Symbolic::RL_STOP;
             }
         } else {
             S.rl_desc.clear();
+        }
+        // per-warp programs of the CTA variant
+        S.rc_lists.clear();
+        S.rc_desc.clear();
+        S.rc_seg.clear();
+        S.rc_segend.clear();
+        S.rc_nsegs = 0;
+        if (ok) {
+            const int W = Symbolic::RC_WARPS, nw = S.rl_nwaves;
+            auto is_sync = [&](int wv) { return wv >= nw || (S.rl_desc[((size_t)wv * 32) * 4 + 3] & Symbolic::RL_SYNC) != 0; };
+            std::vector<std::vector<int>> lists(W);
+            int wv = 0, seg = 0;
+            while (wv < nw) {
+                int e = wv + 1;
+                while (!is_sync(e)) ++e;                      // waves [wv, e) are one level
+                if (e - wv == 1) {                            // a run of one-wave levels
+                    while (e < nw && is_sync(e + 1)) ++e;
+                    for (int j = wv; j < e; ++j) { lists[0].push_back(j); lists[0].push_back(seg); }
+                } else {
+                    for (int j = wv; j < e; ++j) { lists[(j - wv) % W].push_back(j); lists[(j - wv) % W].push_back(seg); }
+                }
+                // last slot of the segment: the largest slot any of its lanes touches
+                int last = 0;
+                for (int j = wv; j < e; ++j)
+                    for (int lane = 0; lane < 32; ++lane) {
+                        const int *d = &S.rl_desc[((size_t)j * 32 + lane) * 4];
+                        const int k = 1 << ((d[2] >> 24) & 7), cnt = (d[2] >> 27) & 7;
+                        if (cnt > 0) last = std::max(last, (d[2] & 0xFFFFFF) + (cnt - 1) * k + 1);
+                    }
+                S.rc_segend.push_back(std::max(last, S.rc_segend.empty() ? 0 : S.rc_segend.back()));
+                wv = e;
+                ++seg;
+            }
+            S.rc_nsegs = seg;
+            S.rc_lists.assign(W + 1, 0);
+            for (int q = 0; q < W; ++q) {
+                lists[q].push_back(nw);
+                lists[q].push_back(seg);
+                lists[q].push_back(nw + 1);
+                lists[q].push_back(seg);
+                S.rc_lists[q + 1] = S.rc_lists[q] + (int)lists[q].size() / 2;
+            }
+            for (int q = 0; q < W; ++q) S.rc_lists.insert(S.rc_lists.end(), lists[q].begin(), lists[q].end());
+            S.rc_desc.clear();
+            S.rc_seg.clear();
+            for (int q = 0; q < W; ++q)
+                for (size_t j = 0; j + 1 < lists[q].size(); j += 2) {
+                    const int *src = &S.rl_desc[(size_t)lists[q][j] * 4 * 32];
+                    S.rc_desc.insert(S.rc_desc.end(), src, src + 4 * 32);
+                    S.rc_seg.push_back(lists[q][j + 1]);
+                }
+            for (int rep = 0; rep < 4; ++rep) {               // the look-ahead of the last warp reads up to eight records further
+                std::vector<int> idle(S.rl_desc.begin() + (size_t)nw * 4 * 32, S.rl_desc.begin() + (size_t)(nw + 2) * 4 * 32);
+                S.rc_desc.insert(S.rc_desc.end(), idle.begin(), idle.end());
+                S.rc_seg.push_back(seg);
+                S.rc_seg.push_back(seg);
+            }
         }
     }
 

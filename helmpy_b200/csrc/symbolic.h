@@ -60,13 +60,28 @@ struct Symbolic {
 
     // row-lane solve schedule (k_solve_rows, symbolic.cpp 4b-rows): every row of a level gets a
     // power-of-two group of k lanes; a lane walks every k-th block of its row, at most RL_BLOCKS.
-    // rl_desc: 4 ints per (wave, lane): {c0 | c1 << 16, c2 | c3 << 16, first slot, row | flags}
+    // rl_desc: 4 ints per (wave, lane): {c0 | c1 << 16, c2 | c3 << 16, fetch word, row | flags}
+    // fetch word: first slot | lanes-per-row log2 << 24 | number of blocks << 27 (all a lane needs to
+    // request its factor blocks; the kernels read it two waves ahead of the rest of the record);
     // c_t: column of the lane's t-th block (RL_NONE: no block, RL_DIAG: the row's inverted pivot);
     // flags: lanes-per-row log2 in bits 16-18, span (lanes after this one in the row's group) in
     // bits 19-23, then RL_HEAD / RL_SYNC / RL_ISU, shuffle rounds of the wave in bits 27-29.
+    // The table ends with two idle waves (look-ahead), the first of which says RL_STOP.
     // Empty (rl_nwaves = 0) when a row or the grid is too large for the packed record.
     std::vector<int> rl_desc;
     int rl_nwaves = 0;
+    // k_solve_rows_cta (one CTA of RC_WARPS warps per scenario, x in shared memory): the waves of a level
+    // with several waves are dealt to the warps (one SEGMENT, a block barrier after it); a run of
+    // consecutive one-wave levels is one segment that warp 0 walks alone.  rc_lists: RC_WARPS + 1 offsets
+    // (in entries), then 2 ints per entry {wave, segment}; every warp's list ends with the two idle waves.
+    // rc_desc / rc_seg: the records of every warp's waves copied out in the warp's program order (so the
+    // look-ahead is a plain sequential read) and the segment of each; warp q's stream starts at record
+    // rc_lists[q] and ends with the two idle waves.
+    static constexpr int RC_WARPS = 7;
+    std::vector<int> rc_desc, rc_seg;
+    std::vector<int> rc_lists;
+    std::vector<int> rc_segend;                  // per segment: one past the last LU slot it consumes (slots are consumed in storage order)
+    int rc_nsegs = 0;
 #ifndef HELM_RL_BLOCKS
 #define HELM_RL_BLOCKS 3       // measured: 3 blocks per lane fit 64 registers without spills (4 need 72)
 #endif

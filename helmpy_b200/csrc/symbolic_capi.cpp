@@ -33,7 +33,7 @@ int helm_symbolic_array(const helm_symbolic *h, const char *name, const int32_t 
     const std::vector<int> *v = nullptr;
 #define F(n) if (!strcmp(name, #n)) v = &S.n;
     F(perm) F(iperm) F(adj_ptr) F(adj_idx) F(adj_src) F(adj_slot) F(lptr) F(lcol) F(llev_ptr)
-    F(urow) F(qof) F(ulev_ptr) F(uptr) F(ucol) F(dslot) F(fptr) F(fsrc) F(fdst) F(fdst_local) F(fchunk_row) F(fchunk_lpr) F(flev_chunk) F(frow_off) F(slot_src) F(slot_row) F(slot_col) F(wave_tab) F(smeta) F(scm) F(solve_chunks) F(solve_segs) F(one_lists) F(rl_desc)
+    F(urow) F(qof) F(ulev_ptr) F(uptr) F(ucol) F(dslot) F(fptr) F(fsrc) F(fdst) F(fdst_local) F(fchunk_row) F(fchunk_lpr) F(flev_chunk) F(frow_off) F(slot_src) F(slot_row) F(slot_col) F(wave_tab) F(smeta) F(scm) F(solve_chunks) F(solve_segs) F(one_lists) F(rl_desc) F(rc_lists) F(rc_segend) F(rc_desc) F(rc_seg)
 #undef F
     if (!v) return HELM_E_ARG;
     *data = v->data();

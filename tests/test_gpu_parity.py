@@ -185,10 +185,11 @@ def test_unstaged_kernels_agree(hb, monkeypatch):
         "print(json.dumps([r.V.real.tolist(), r.V.imag.tolist(), r.ncoef.tolist()]))"
     ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
     outs = []
-    # default (k_solve_one, CTA-cooperative factorization) / generic kernels / the TMA-ring CTA solve and the
-    # warp-per-scenario factorization
-    for env_extra in ({}, {'HELM_B200_NO_COOP_FACTOR': '1', 'HELM_B200_NO_CTA_SOLVE': '1', 'HELM_B200_ONE_SOLVE': '0'},
-                      {'HELM_B200_ONE_SOLVE': '0', 'HELM_B200_NO_FACTOR_CTA': '1'}):
+    # default (k_solve_rows_deep, CTA-cooperative factorization) / generic kernels / the static-schedule one-CTA
+    # solve / the TMA-ring CTA solve and the warp-per-scenario factorization
+    for env_extra in ({}, {'HELM_B200_NO_COOP_FACTOR': '1', 'HELM_B200_NO_CTA_SOLVE': '1', 'HELM_B200_ONE_SOLVE': '0', 'HELM_B200_ROWS_DEEP': '0'},
+                      {'HELM_B200_ROWS_DEEP': '0'},
+                      {'HELM_B200_ONE_SOLVE': '0', 'HELM_B200_NO_FACTOR_CTA': '1', 'HELM_B200_ROWS_DEEP': '0'}):
         env = dict(os.environ, **env_extra)
         out = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=300)
         assert out.returncode == 0, out.stderr[-2000:]
@@ -198,6 +199,34 @@ def test_unstaged_kernels_agree(hb, monkeypatch):
         assert a[2] == b[2]
         assert np.max(np.abs(np.array(a[0]) - np.array(b[0]))) < 1e-11
         assert np.max(np.abs(np.array(a[1]) - np.array(b[1]))) < 1e-11
+
+
+@pytest.mark.gpu
+def test_large_batch_solve_kernels_agree(hb):
+    """The three triangular solves for large batches -- row-lane solve (k_solve_rows, default), its CTA
+    variant with x in shared memory (k_solve_rows_cta) and the wave solve (k_solve_flat) -- give the same
+    passes and the same voltages to rounding on a batch with slot refill and Q-limit passes."""
+    import subprocess, sys, os, json
+    code = (
+        "import sys, json; sys.path.insert(0, %r); sys.path.insert(0, %r);"
+        "import numpy as np; from common import load_case; import helmpy_b200;"
+        "c = load_case('case1354pegase');"
+        "s = np.random.default_rng(21).uniform(0.9, 1.03, 1400);"
+        "r = helmpy_b200.helm_batch(c, s, mismatch=1e-8, max_coefficients=40, max_resident=1000);"
+        "print(json.dumps([r.V[::50].real.tolist(), r.V[::50].imag.tolist(), r.ncoef.tolist(), r.status.tolist()]))"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for env_extra in ({}, {'HELM_B200_ROWS_CTA': '1'}, {'HELM_B200_ROWS_SOLVE': '0'}):
+        env = dict(os.environ, **env_extra)
+        out = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        outs.append(json.loads(out.stdout.strip().splitlines()[-1]))
+    a = outs[0]
+    assert all(st == 2 for st in a[3])          # ST_CONVERGED
+    for b in outs[1:]:
+        assert a[2] == b[2] and a[3] == b[3]
+        assert np.max(np.abs(np.array(a[0]) - np.array(b[0]))) < 1e-10
+        assert np.max(np.abs(np.array(a[1]) - np.array(b[1]))) < 1e-10
 
 
 def _numbers(text):
@@ -585,7 +614,7 @@ def test_per_order_coefficients_match_oracle(hb, name, scale):
 
 def test_benchmark_path_matches_oracle(hb):
     """The path bench.py times — case2869pegase, more scenarios than slots (continuous batching with
-    slot refill), > 888 resident so the warp-per-scenario wave solve (k_solve_flat) runs, shared
+    slot refill), > 888 resident so the warp-per-scenario row-lane solve (k_solve_rows) runs, shared
     first-pass factors, two-step factorization pipeline — against the oracle on sampled scenarios:
     status, coefficients per pass, switch count, |dV| and d(angle) <= 1e-8 (reference helm.py:896-985)."""
     case = load_case('case2869pegase')

@@ -294,9 +294,9 @@ def test_row_lane_schedule_solves(name):
     nslots = nL + int(uptr[-1]) + N
     desc = S['rl_desc'].reshape(-1, 32, 4)
     assert len(desc) >= 2
-    nw = len(desc) - 1                      # the last record is the idle look-ahead wave
-    assert (desc[nw, :, 0] == -1).all() and (desc[nw, :, 3] == (0xFFFF | (1 << 30))).all()      # ... and says stop
-    assert not (desc[:nw, :, 3] & (1 << 30)).any()
+    nw = len(desc) - 2                      # the last two records are the idle look-ahead waves
+    assert (desc[nw:, :, 0] == -1).all() and (desc[nw:, :, 3] == (0xFFFF | (1 << 30))).all()     # ... and say stop
+    assert (desc[nw:, :, 2] == 0).all() and not (desc[:nw, :, 3] & (1 << 30)).any()
     rng = np.random.default_rng(5)
     lu = rng.standard_normal((nslots, 2, 2))
     rhs = rng.standard_normal((N, 2))
@@ -335,11 +335,14 @@ def test_row_lane_schedule_solves(name):
         dinv = {}
         for lane in range(32):
             k = 1 << ((int(flags[lane]) >> 16) & 7)
+            fw = int(d[lane, 2])                    # fetch word: slot | lanes-per-row log2 << 24 | blocks << 27
+            assert (fw >> 24) & 7 == (int(flags[lane]) >> 16) & 7
             cs = [int(d[lane, 0]) & 0xFFFF, (int(d[lane, 0]) >> 16) & 0xFFFF, int(d[lane, 1]) & 0xFFFF, (int(d[lane, 1]) >> 16) & 0xFFFF]
+            assert (fw >> 27) & 7 == sum(c != 0xFFFF for c in cs) and all(c != 0xFFFF for c in cs[:(fw >> 27) & 7])
             for t, c in enumerate(cs):
                 if c == 0xFFFF:
                     continue
-                slot = int(d[lane, 2]) + t * k
+                slot = (fw & 0xFFFFFF) + t * k
                 covered[slot] += 1
                 if c == 0xFFFE:
                     assert is_u and t == 0 and (flags[lane] & (1 << 24))
