@@ -58,7 +58,7 @@ class Stats(C.Structure):
     ]
 
 
-KERNEL_NAMES = ("assemble", "factor", "solve", "rhs_conv", "advance", "qlimit", "pass_end", "init", "eps")
+KERNEL_NAMES = ("assemble", "factor", "solve", "rhs_conv", "advance", "qlimit", "pass_end", "init", "eps", "fcache")
 
 EXPORTED_SYMBOLS = (
     "helm_last_error", "helm_plan_create", "helm_plan_destroy", "helm_plan_get_info",
@@ -362,6 +362,8 @@ def stats_dict(stats):
         "steps": int(stats.steps), "kernel_launches": int(stats.kernel_launches),
         "graph_launches": int(stats.graph_launches), "ms_total": float(stats.ms_total),
         "ms_kernel": {KERNEL_NAMES[i]: float(stats.ms_kernel[i]) for i in range(len(KERNEL_NAMES))},
+        # factor cache: pass starts that found their factors already in the pool / factorizations performed
+        "factor_cache_hits": int(stats.ms_kernel[10]), "factorizations": int(stats.ms_kernel[11]),
     }
 
 

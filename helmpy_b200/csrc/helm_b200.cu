@@ -123,6 +123,17 @@ struct WorkDev {
     int skip_asm;                     // k_factor_coop: the LU slots already hold the matrix (Newton-Raphson Jacobian)
     int factor_cta;                   // k_factor_coop: the warps of a CTA share one scenario (few scenarios: latency path)
     int *out_status, *out_ncoef, *out_nswitch;   // per-scenario outputs, written when a scenario ends
+    // Factor cache (k_fcache): the matrix of a pass depends on the bus types only, and the scenarios of a
+    // load-scaling batch run through few distinct type vectors (176-188 per pass among 4096 scenarios of
+    // case2869pegase), so the buffers of `lu` are a POOL: lu_ix[slot] = buffer the slot's scenario solves
+    // with, found by a hash of its type vector; only the first scenario with a new vector factorizes.
+    // null: no cache, slot g owns buffer g.
+    int *lu_ix;                       // [ngroups] pool buffer (-1: none / shared first-pass factors)
+    int *fc_do;                       // [ngroups] 1: the slot's scenario factorizes its buffer in this side branch
+    int *fc_ref, *fc_stamp, *fc_sing; // [ngroups] per buffer: scenarios using it, step of its last release, singular matrix
+    int *fc_tbuf, *fc_pend, *fc_ctr;  // hash table values [T], pending list [ngroups], counters [16]
+    unsigned long long *fc_bkey, *fc_tkey, *fc_hash;   // key of a buffer [ngroups], table keys [T], keys of the step's list [ngroups]
+    int fc_tmask;                     // T - 1
     unsigned char *btype;             // [group][N][G]
     double *Qg, *VVant;               // [group][N][G]
     double2 *Pcur;                    // [group][N][G]
@@ -236,8 +247,10 @@ __device__ __forceinline__ size_t px(int N, int grp, int k, int i, int s) {
 __device__ __forceinline__ bool uses_shared_lu(const WorkDev &w, int grp) {
     return w.lu_shared != nullptr && w.s_npass[grp] == 0 && w.o_b[grp] < 0;
 }
+// G = 1: pool buffer holding the factors of the scenario in slot `grp`
+__device__ __forceinline__ int lu_buf(const WorkDev &w, int grp) { return w.lu_ix ? w.lu_ix[grp] : grp; }
 __device__ __forceinline__ const double2 *lu_of(const PlanDev &p, const WorkDev &w, int grp) {
-    return uses_shared_lu(w, grp) ? w.lu_shared : w.lu + (size_t)grp * p.nslots * 2;
+    return uses_shared_lu(w, grp) ? w.lu_shared : w.lu + (size_t)lu_buf(w, grp) * p.nslots * 2;
 }
 
 __device__ __forceinline__ OutageRef load_outage(const PlanDev &p, const WorkDev &w, int sg) {
@@ -332,7 +345,7 @@ __device__ __forceinline__ void asm_slot(const PlanDev &p, const WorkDev &w, int
             r1.x = diag ? 1.0 : 0.0;
         }
     }
-    double2 *dst = w.lu + ix<G>(grp, p.nslots, slot, s) * 2;
+    double2 *dst = w.lu + ix<G>(G == 1 ? lu_buf(w, grp) : grp, p.nslots, slot, s) * 2;
     dst[0] = r0;
     dst[1] = r1;
 }
@@ -613,10 +626,11 @@ __global__ void __launch_bounds__(WPB * 32) k_factor_coop(PlanDev p, WorkDev w) 
                 __syncthreads();
             }
             if (uses_shared_lu(w, grp)) continue;
+            if (w.lu_ix && !w.fc_do[grp]) continue;         // another scenario with the same bus types factorizes (or has factorized) the buffer
             for (int slot = threadIdx.x; slot < p.nslots; slot += WPB * 32) asm_slot<1>(p, w, grp, slot, 0);
         }
         __syncthreads();
-        double2 *lu = w.lu + (size_t)grp * p.nslots * 2;
+        double2 *lu = w.lu + (size_t)lu_buf(w, grp) * p.nslots * 2;
         bool singular = false;
         for (int l = 0; l < p.nLlev; ++l) {
             const int c0 = __ldg(p.flev_chunk + l), c1 = __ldg(p.flev_chunk + l + 1);
@@ -636,7 +650,10 @@ __global__ void __launch_bounds__(WPB * 32) k_factor_coop(PlanDev p, WorkDev w) 
             }
             __syncthreads();
         }
-        if (__syncthreads_or(singular) && threadIdx.x == 0) w.s_status[grp] = ST_SINGULAR;
+        if (__syncthreads_or(singular) && threadIdx.x == 0) {
+            w.s_status[grp] = ST_SINGULAR;
+            if (w.lu_ix) w.fc_sing[w.lu_ix[grp]] = 1;
+        }
         __syncthreads();
     }
     return;
@@ -652,13 +669,17 @@ __global__ void __launch_bounds__(WPB * 32) k_factor_coop(PlanDev p, WorkDev w) 
             __syncwarp();
         }
         if (uses_shared_lu(w, grp)) continue;               // first pass: the shared factors are used
+        if (w.lu_ix && !w.fc_do[grp]) continue;             // factor cache: the buffer is (being) factorized by another scenario
         for (int slot = lane; slot < p.nslots; slot += 32) asm_slot<1>(p, w, grp, slot, 0);
         __syncwarp();
     }
-    double2 *lu = w.lu + (size_t)grp * p.nslots * 2;
+    double2 *lu = w.lu + (size_t)lu_buf(w, grp) * p.nslots * 2;
     bool singular = false;
     for (int c = 0; c < p.nfchunks; ++c) factor_chunk(p, w, lu, grp, c, lane, sSrc, sDk, sRow, sDl, sUp, singular);
-    if (__any_sync(0xFFFFFFFFu, singular) && lane == 0) w.s_status[grp] = ST_SINGULAR;
+    if (__any_sync(0xFFFFFFFFu, singular) && lane == 0) {
+        w.s_status[grp] = ST_SINGULAR;
+        if (w.lu_ix) w.fc_sing[w.lu_ix[grp]] = 1;
+    }
     __syncwarp();
   }
 }
@@ -2318,6 +2339,155 @@ __global__ void k_pass_end(WorkDev w) {
 #include "helm_variants.cuh"
 #include "helm_nr.cuh"
 
+// ---- K_fcache: factor cache (see WorkDev::lu_ix).  One CTA, after k_step_begin: every scenario of the
+// step's factorization list gives its buffer back and gets the buffer of its new bus-type vector -- an
+// existing one (nothing to factorize) or, for a vector not seen before, the buffer that has been unused
+// for the longest time, which its scenario then factorizes in the side branch.  Scenarios with a branch
+// outage have their own matrix: a buffer of their own, not entered in the table.
+enum : int { FC_STEP = 0, FC_HITS = 1, FC_MISS = 2, FC_USED = 3 };   // fc_ctr: step counter, acquires served from the table, factorizations, non-empty table slots
+__device__ __forceinline__ unsigned long long fc_mix(unsigned long long x) {
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+    x ^= x >> 27; x *= 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+// slot of `key` in the table, or -1
+__device__ __forceinline__ int fc_find(const WorkDev &w, unsigned long long key) {
+    int slot = (int)(fc_mix(key) & (unsigned)w.fc_tmask);
+    for (int n = 0; n <= w.fc_tmask; ++n) {
+        const unsigned long long k = w.fc_tkey[slot];
+        if (k == key) return slot;
+        if (k == 0) return -1;
+        slot = (slot + 1) & w.fc_tmask;
+    }
+    return -1;
+}
+__device__ __forceinline__ void fc_insert(const WorkDev &w, unsigned long long key, int buf) {
+    int slot = (int)(fc_mix(key) & (unsigned)w.fc_tmask);
+    while (w.fc_tkey[slot] > 1) slot = (slot + 1) & w.fc_tmask;          // 0: empty, 1: deleted
+    if (w.fc_tkey[slot] == 0) w.fc_ctr[FC_USED] += 1;
+    w.fc_tkey[slot] = key;
+    w.fc_tbuf[slot] = buf;
+}
+
+__global__ void __launch_bounds__(1024) k_fcache(PlanDev p, WorkDev w) {
+    const int nfact = w.fact_count[w.parity];
+    if (nfact == 0) return;
+    const int *list = w.fact_list + (size_t)w.parity * w.ngroups;
+    const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+    const int P = w.ngroups, N = p.N;
+    __shared__ int s_npend, s_first, s_now;
+    __shared__ unsigned long long s_red[32];
+    if (tid == 0) { s_npend = 0; s_now = ++w.fc_ctr[FC_STEP]; }
+    // deleted entries pile up when buffers are recycled: rebuild the table from the buffers' keys
+    if (w.fc_ctr[FC_USED] > (w.fc_tmask + 1) / 2) {
+        __syncthreads();
+        for (int i = tid; i <= w.fc_tmask; i += 1024) w.fc_tkey[i] = 0;
+        __syncthreads();
+        if (tid == 0) {
+            w.fc_ctr[FC_USED] = 0;
+            for (int b = 0; b < P; ++b)
+                if (w.fc_bkey[b] > 1) fc_insert(w, w.fc_bkey[b], b);
+        }
+    }
+    __syncthreads();
+    const int now = s_now;
+    // A: give the old buffer back; key of the new bus-type vector (0: no buffer needed, 1: a buffer of its own)
+    for (int fi = wp; fi < nfact; fi += 32) {
+        const int grp = list[fi];
+        if (lane == 0) {
+            const int old = w.lu_ix[grp];
+            if (old >= 0) {
+                if (atomicSub(&w.fc_ref[old], 1) == 1) w.fc_stamp[old] = now;
+                w.lu_ix[grp] = -1;
+            }
+        }
+        unsigned long long key;
+        if (w.s_status[grp] != ST_ACTIVE || uses_shared_lu(w, grp)) key = 0;
+        else if (w.o_b[grp] >= 0) key = 1;
+        else {
+            const unsigned char *bt = w.btype + (size_t)grp * N;
+            unsigned long long h = 0;
+            for (int i = lane; i < N; i += 32) h += fc_mix(((unsigned long long)(i + 1) << 8) | bt[i]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xFFFFFFFFu, h, o);
+            key = h < 2 ? h + 2 : h;
+        }
+        if (lane == 0) w.fc_hash[fi] = key;
+    }
+    __syncthreads();
+    // B: vectors already in the table
+    for (int fi = tid; fi < nfact; fi += 1024) {
+        const unsigned long long key = w.fc_hash[fi];
+        const int grp = list[fi];
+        w.fc_do[grp] = 0;
+        if (key == 0) continue;
+        int slot = key > 1 ? fc_find(w, key) : -1;
+        if (slot >= 0) {
+            const int buf = w.fc_tbuf[slot];
+            atomicAdd(&w.fc_ref[buf], 1);
+            w.lu_ix[grp] = buf;
+            atomicAdd(&w.fc_ctr[FC_HITS], 1);
+        } else {
+            w.fc_pend[atomicAdd(&s_npend, 1)] = fi;
+        }
+    }
+    __syncthreads();
+    const int npend = s_npend;
+    // C: new vectors, one per round: the first pending scenario takes the least recently used free buffer
+    // and enters its key; every other pending scenario with that key then finds it
+    for (int round = 0; round <= npend; ++round) {
+        if (tid == 0) s_first = 0x7FFFFFFF;
+        __syncthreads();
+        for (int i = tid; i < npend; i += 1024) {
+            const int fi = w.fc_pend[i];
+            if (fi < 0) continue;
+            const unsigned long long key = w.fc_hash[fi];
+            const int slot = (round > 0 && key > 1) ? fc_find(w, key) : -1;
+            if (slot >= 0) {
+                const int buf = w.fc_tbuf[slot], grp = list[fi];
+                atomicAdd(&w.fc_ref[buf], 1);
+                w.lu_ix[grp] = buf;
+                atomicAdd(&w.fc_ctr[FC_HITS], 1);
+                w.fc_pend[i] = -1;
+            } else {
+                atomicMin(&s_first, i);
+            }
+        }
+        __syncthreads();
+        const int first = s_first;
+        if (first == 0x7FFFFFFF) break;
+        // free buffer with the oldest release stamp
+        unsigned long long best = ~0ull;
+        for (int b = tid; b < P; b += 1024)
+            if (w.fc_ref[b] == 0) best = min(best, ((unsigned long long)(unsigned)w.fc_stamp[b] << 32) | (unsigned)b);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xFFFFFFFFu, best, o));
+        if (lane == 0) s_red[wp] = best;
+        __syncthreads();
+        if (tid == 0) {
+            for (int k = 1; k < 32; ++k) best = min(best, s_red[k]);
+            const int fi = w.fc_pend[first], grp = list[fi];
+            const unsigned long long key = w.fc_hash[fi];
+            const int buf = (int)(best & 0xFFFFFFFFu);      // a free buffer exists: every scenario holds at most one, and this one holds none
+            const unsigned long long oldkey = w.fc_bkey[buf];
+            if (oldkey > 1) {
+                const int os = fc_find(w, oldkey);
+                if (os >= 0) w.fc_tkey[os] = 1;
+            }
+            w.fc_bkey[buf] = key > 1 ? key : 0;
+            if (key > 1) fc_insert(w, key, buf);
+            w.fc_ref[buf] = 1;
+            w.fc_sing[buf] = 0;
+            w.lu_ix[grp] = buf;
+            w.fc_do[grp] = 1;
+            w.fc_ctr[FC_MISS] += 1;
+            w.fc_pend[first] = -1;
+            __threadfence_block();
+        }
+        __syncthreads();
+    }
+}
+
 // ---- K_begin: start of a step.  Groups factorized during the previous step rejoin the main
 // branch; groups whose pass ended in the previous step move to the factorization branch.
 __global__ void k_step_begin(WorkDev w) {
@@ -2336,7 +2506,14 @@ __global__ void k_step_begin(WorkDev w) {
     if (gf & GF_FACTORING) {
         int age = w.g_fage[grp] - 1;
         w.g_fage[grp] = age;
-        if (age <= 0) gf &= ~(GF_FACTORING | GF_NEWSCEN);
+        if (age <= 0) {
+            gf &= ~(GF_FACTORING | GF_NEWSCEN);
+            // factor cache: the scenario that factorized the buffer found the matrix singular
+            if (w.lu_ix && w.s_status[grp] == ST_ACTIVE && !uses_shared_lu(w, grp)) {
+                const int buf = w.lu_ix[grp];
+                if (buf >= 0 && w.fc_sing[buf]) w.s_status[grp] = ST_SINGULAR;
+            }
+        }
     } else if (gf & GF_PENDING) {
         gf = (gf & ~GF_PENDING) | GF_FACTORING;
         w.g_fage[grp] = w.depth;
@@ -2513,8 +2690,8 @@ struct WsLayout {
     size_t total = 0;
     size_t off_scale, off_sint, off_gint, off_btype, off_Qg, off_VVant, off_Pcur, off_rhs, off_xb, off_lu, off_Vh, off_Hh, off_Eh;
     size_t off_var_s, off_ploss, off_zb, off_Qh, off_vre, off_qcur, off_lu_shared, off_shprep, off_Pb;
-    size_t off_sw_ent, off_sw_q;
-    int sw_cap;
+    size_t off_sw_ent, off_sw_q, off_fc;
+    int sw_cap, fc_T;
     int G, ngroups, Bp, K;
 };
 
@@ -2559,6 +2736,11 @@ WsLayout layout(const helm_plan *pl, int B, const helm_params *prm) {
         L.off_vre = take(per * sizeof(double));
         L.off_qcur = take(per * sizeof(double));
     }
+    // factor cache: [lu_ix | fc_do | fc_ref | fc_stamp | fc_sing | fc_pend][ngroups] ints, fc_tbuf[T] ints, fc_ctr[16] ints,
+    // then [fc_bkey | fc_hash][ngroups] and fc_tkey[T] 64-bit words
+    L.fc_T = 1024;
+    while (L.fc_T < 4 * L.ngroups) L.fc_T <<= 1;
+    L.off_fc = take(sizeof(int) * ((size_t)6 * L.ngroups + L.fc_T + 16) + 8 + sizeof(unsigned long long) * ((size_t)2 * L.ngroups + L.fc_T));
     L.off_sw_ent = L.off_sw_q = 0;
     L.sw_cap = 0;
     if (prm->record_switches) {
@@ -2596,6 +2778,8 @@ WorkDev bind(const helm_plan *pl, const WsLayout &L, int B, const helm_params *p
     w.xb = (double2 *)(b + L.off_xb);
     w.lu = (double2 *)(b + L.off_lu);
     w.lu_shared = nullptr;
+    w.lu_ix = nullptr; w.fc_do = nullptr; w.fc_ref = w.fc_stamp = w.fc_sing = w.fc_tbuf = w.fc_pend = w.fc_ctr = nullptr;
+    w.fc_bkey = w.fc_tkey = w.fc_hash = nullptr; w.fc_tmask = 0;
     w.Vh = (double2 *)(b + L.off_Vh);
     w.Hh = (double2 *)(b + L.off_Hh);
     w.Eh = (double2 *)(b + L.off_Eh);
@@ -2629,9 +2813,9 @@ constexpr int T_ELEM = 256;   // threads per CTA of the per-(item, scenario) ker
 constexpr int WPB_SOLVE = 4;  // warps (= scenario groups) per CTA of the factor / solve kernels
 
 enum { KI_ASM = 0, KI_FACTOR, KI_SOLVE, KI_RHS, KI_ADV, KI_QLIM, KI_PEND, KI_INIT, KI_BEGIN,
-       KI_SOLVE_SIDE, KI_BPREP, KI_BFIN, KI_BP, KI_VPRE, KI_PV1C_MAIN, KI_PV1C_SIDE, KI_EPS, KI_COUNT };
+       KI_SOLVE_SIDE, KI_BPREP, KI_BFIN, KI_BP, KI_VPRE, KI_PV1C_MAIN, KI_PV1C_SIDE, KI_EPS, KI_FCACHE, KI_COUNT };
 // slot of helm_stats.ms_kernel a kernel is accounted under in profile mode (-1: not accounted)
-inline int stat_slot(int ki) { return ki < 8 ? ki : (ki == KI_EPS ? 8 : -1); }
+inline int stat_slot(int ki) { return ki < 8 ? ki : (ki == KI_EPS ? 8 : (ki == KI_FCACHE ? 9 : -1)); }
 
 template <int G>
 void launch_kernel(int which, const PlanDev &p, const WorkDev &w, cudaStream_t st) {
@@ -2640,6 +2824,7 @@ void launch_kernel(int which, const PlanDev &p, const WorkDev &w, cudaStream_t s
     switch (which) {
         case KI_ASM: k_assemble<G><<<std::min(w.ngroups, 592), 256, 0, st>>>(p, w); break;
         case KI_BEGIN: k_step_begin<<<gridGrp, 128, 0, st>>>(w); break;
+        case KI_FCACHE: k_fcache<<<1, 1024, 0, st>>>(p, w); break;
         case KI_FACTOR:
             if (G == 1 && p.use_coop_factor) {
                 size_t smem = WPB_FACTOR * factor_smem_per_warp(p.cap_upd, p.cap_ent, p.cap_rowblk);
@@ -2772,6 +2957,7 @@ void launch_step(int G, const PlanDev &p, const WorkDev &w_in, const StepCtx &c,
     static const bool nofork = getenv("HELM_B200_NOFORK") != nullptr;   // A/B switch: serial step
     if (nofork) {
         launch_any(G, KI_BEGIN, p, w, c.st);
+        if (w.lu_ix) launch_any(G, KI_FCACHE, p, w, c.st);
         for (int k = 0; k < q.side_len; ++k) launch_any(G, q.side_seq[k], p, w, c.st);
         for (int k = 0; k < q.main_len; ++k) launch_any(G, q.main_seq[k], p, w, c.st);
         return;
@@ -2780,6 +2966,7 @@ void launch_step(int G, const PlanDev &p, const WorkDev &w_in, const StepCtx &c,
     // k + depth - 1, and the groups it factorizes rejoin at the k_step_begin of step k + depth.
     const int sl = (int)(step % D);
     launch_any(G, KI_BEGIN, p, w, c.st);
+    if (w.lu_ix) launch_any(G, KI_FCACHE, p, w, c.st);    // on the main stream: the cache is updated by one step at a time
     cudaEventRecord(c.fork, c.st);
     cudaStreamWaitEvent(c.side[sl], c.fork, 0);
     for (int k = 0; k < q.side_len; ++k) launch_any(G, q.side_seq[k], p, w, c.side[sl]);
@@ -2800,6 +2987,7 @@ void launch_step_profiled(int G, const PlanDev &p, const WorkDev &w_in, cudaStre
     int seq[STEP_LEN_MAX];
     int n = 0;
     seq[n++] = KI_BEGIN;
+    if (w.lu_ix) seq[n++] = KI_FCACHE;
     for (int k = 0; k < q.side_len; ++k) seq[n++] = q.side_seq[k];
     for (int k = 0; k < q.main_len; ++k) seq[n++] = q.main_seq[k];
     for (int k = 0; k < n; ++k) {
@@ -3152,6 +3340,19 @@ int helm_solve_batch_device(helm_plan *pl, int32_t B, const double *d_scale, con
         CUDA_TRY(cudaStreamSynchronize(st));
         if (pl->h_pinned[0] == ST_ACTIVE) w.lu_shared = w2.lu;      // singular base matrix: every scenario factorizes (and fails) itself
     }
+    // Factor cache for the later passes (same conditions; HELM_B200_NO_FCACHE: A/B switch)
+    if (w.lu_shared && getenv("HELM_B200_NO_FCACHE") == nullptr) {
+        int *fi = (int *)((char *)d_ws + L.off_fc);
+        const size_t ng = (size_t)L.ngroups;
+        w.lu_ix = fi; w.fc_do = fi + ng; w.fc_ref = fi + 2 * ng; w.fc_stamp = fi + 3 * ng; w.fc_sing = fi + 4 * ng; w.fc_pend = fi + 5 * ng;
+        w.fc_tbuf = fi + 6 * ng; w.fc_ctr = w.fc_tbuf + L.fc_T;
+        const size_t nints = 6 * ng + L.fc_T + 16;
+        unsigned long long *fq = (unsigned long long *)((char *)d_ws + L.off_fc + (nints * sizeof(int) + 7) / 8 * 8);
+        w.fc_bkey = fq; w.fc_hash = fq + ng; w.fc_tkey = fq + 2 * ng;
+        w.fc_tmask = L.fc_T - 1;
+        CUDA_TRY(cudaMemsetAsync(fi, 0, (char *)(w.fc_tkey + L.fc_T) - (char *)fi, st));
+        CUDA_TRY(cudaMemsetAsync(w.lu_ix, 0xFF, sizeof(int) * ng, st));
+    }
 
     helm_stats local;
     memset(&local, 0, sizeof(local));
@@ -3183,7 +3384,7 @@ int helm_solve_batch_device(helm_plan *pl, int32_t B, const double *d_scale, con
         memcpy(&mm, &prm->mismatch, sizeof(mm));
         const std::vector<unsigned long long> key = {
             u(d_ws), (unsigned long long)ws_bytes, (unsigned long long)B, u(d_scale), u(d_vout), u(d_status), u(d_ncoef), u(d_nswitch),
-            u(st), u(w.outage_in), u(w.lu_shared), u(w.tl), mm, (unsigned long long)prm->max_coefficients,
+            u(st), u(w.outage_in), u(w.lu_shared), u(w.lu_ix), u(w.tl), mm, (unsigned long long)prm->max_coefficients,
             (unsigned long long)prm->enforce_q_limits, (unsigned long long)L.G, (unsigned long long)L.ngroups,
             (unsigned long long)prm->pv_bus_model, (unsigned long long)prm->dsb_method, (unsigned long long)prm->dsb_model,
             (unsigned long long)prm->record_switches, (unsigned long long)depth, (unsigned long long)poll_every,
@@ -3228,6 +3429,12 @@ int helm_solve_batch_device(helm_plan *pl, int32_t B, const double *d_scale, con
     cudaEventElapsedTime(&ms, ev0, ev1);
     local.ms_total = ms;
     local.steps = steps;
+    if (w.lu_ix) {                                          // factor cache: acquires served from the table / factorizations
+        int ctr[4] = {0, 0, 0, 0};
+        CUDA_TRY(cudaMemcpy(ctr, w.fc_ctr, sizeof(ctr), cudaMemcpyDeviceToHost));
+        local.ms_kernel[10] = ctr[FC_HITS];
+        local.ms_kernel[11] = ctr[FC_MISS];
+    }
     cudaEventDestroy(ev0);
     cudaEventDestroy(ev1);
     for (auto &e : pev) cudaEventDestroy(e);

@@ -122,7 +122,9 @@ typedef struct helm_stats {
     int64_t kernel_launches;    /* kernels launched (graph nodes count)         */
     int64_t graph_launches;
     double ms_total;            /* device time of the whole solve (CUDA events) */
-    double ms_kernel[12];       /* per-kernel accumulated ms when profile=1: assemble, factor, solve, rhs_conv, advance, qlimit, pass_end, init, eps, (reserved x3) */
+    double ms_kernel[12];       /* per-kernel accumulated ms when profile=1: assemble, factor, solve, rhs_conv, advance, qlimit, pass_end, init, eps, fcache;
+                                   [10], [11]: factor cache counters of the call (always filled): pass starts that found their
+                                   factors in the cache / factorizations performed */
 } helm_stats;
 
 const char *helm_last_error(void);

@@ -44,7 +44,8 @@ def main():
             solves = int(np.sum(np.maximum(res.ncoef - 1, 0)))
             out = dict(case=name, B=B, G=G, ms=round(ms, 2), wall_ms=round(wall * 1e3, 1),
                        cases_per_s=round(B / ms * 1e3, 1), conv=int(res.converged.sum()),
-                       steps=res.stats['steps'], scen_solves=solves)
+                       steps=res.stats['steps'], scen_solves=solves,
+                       fc=[res.stats.get('factor_cache_hits'), res.stats.get('factorizations')])
             if profile:
                 out['ms_kernel'] = {k: round(v, 2) for k, v in res.stats['ms_kernel'].items()}
             print(json.dumps(out), flush=True)
