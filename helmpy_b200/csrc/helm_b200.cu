@@ -980,6 +980,9 @@ __device__ __forceinline__ Blk256 ld_blk_stream(const double2 *lu, int slot) {
     return r;
 }
 
+#ifndef ROWS_STREAM
+#define ROWS_STREAM 1      // evict-first hint on the factor loads of k_solve_rows
+#endif
 #ifndef ROWS_REGS
 #define ROWS_REGS 64       // 28 warps per SM and room for a factorization CTA beside them, as k_solve_flat
 #endif
@@ -1031,7 +1034,7 @@ __global__ void __maxnreg__(ROWS_REGS) k_solve_rows(PlanDev p, WorkDev w) {
     Blk256 m[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) m[t] = Blk256{0.0, 0.0, 0.0, 0.0};
-    rows_fetch<0>(lu, d.z, m);
+    rows_fetch<0, ROWS_STREAM != 0>(lu, d.z, m);
     // (L2 evict-last hints on the accesses to x: 288 -> 283 ms per 16 384 scenarios, dropped)
 #define LDX(ptr) (*(ptr))
 #define STX(ptr, v) (*(ptr) = (v))
@@ -1057,7 +1060,7 @@ __global__ void __maxnreg__(ROWS_REGS) k_solve_rows(PlanDev p, WorkDev w) {
         if (c1 != Sy::RL_NONE) { v.x -= m[1].a * x1.x + m[1].b * x1.y; v.y -= m[1].c * x1.x + m[1].d * x1.y; }
         if (c2 != Sy::RL_NONE) { v.x -= m[2].a * x2.x + m[2].b * x2.y; v.y -= m[2].c * x2.x + m[2].d * x2.y; }
         if (ROWS_NB > 3 && c3 != Sy::RL_NONE) { v.x -= m[3].a * x3.x + m[3].b * x3.y; v.y -= m[3].c * x3.x + m[3].d * x3.y; }
-        rows_fetch<1>(lu, f1, m);                                     // m[0] may still be this wave's pivot
+        rows_fetch<1, ROWS_STREAM != 0>(lu, f1, m);                                     // m[0] may still be this wave's pivot
         const int span = (d.w >> 19) & 31, rounds = (d.w >> 27) & 7;
         for (int r = 0; r < rounds; ++r) {
             const int o = 1 << r;
@@ -1070,7 +1073,7 @@ __global__ void __maxnreg__(ROWS_REGS) k_solve_rows(PlanDev p, WorkDev w) {
             if (isu) v = make_double2(m[0].a * v.x + m[0].b * v.y, m[0].c * v.x + m[0].d * v.y);
             STX(xb + row, v);
         }
-        if (f1 >> 27) m[0] = ld_blk_stream(lu, f1 & 0xFFFFFF);
+        if (f1 >> 27) m[0] = ld_blk_stream<ROWS_STREAM != 0>(lu, f1 & 0xFFFFFF);
         d = dn;
     }
 #undef LDX
@@ -2344,7 +2347,7 @@ __global__ void k_pass_end(WorkDev w) {
 // existing one (nothing to factorize) or, for a vector not seen before, the buffer that has been unused
 // for the longest time, which its scenario then factorizes in the side branch.  Scenarios with a branch
 // outage have their own matrix: a buffer of their own, not entered in the table.
-enum : int { FC_STEP = 0, FC_HITS = 1, FC_MISS = 2, FC_USED = 3 };   // fc_ctr: step counter, acquires served from the table, factorizations, non-empty table slots
+enum : int { FC_STEP = 0, FC_HITS = 1, FC_MISS = 2, FC_USED = 3, FC_NEXT = 4 };   // fc_ctr: step counter, acquires served from the table, factorizations, non-empty table slots, first buffer never used
 __device__ __forceinline__ unsigned long long fc_mix(unsigned long long x) {
     x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
     x ^= x >> 27; x *= 0x94D049BB133111EBull;
@@ -2369,15 +2372,50 @@ __device__ __forceinline__ void fc_insert(const WorkDev &w, unsigned long long k
     w.fc_tbuf[slot] = buf;
 }
 
+// A (many CTAs, one warp per scenario of the step's factorization list): give the old buffer back; key of
+// the new bus-type vector (0: no buffer needed, 1: a buffer of its own, not shared)
+__global__ void __launch_bounds__(256) k_fchash(PlanDev p, WorkDev w) {
+    const int fi = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (fi >= w.fact_count[w.parity]) return;
+    const int grp = w.fact_list[(size_t)w.parity * w.ngroups + fi];
+    const int N = p.N;
+    if (lane == 0) {
+        const int old = w.lu_ix[grp];
+        if (old >= 0) {
+            if (atomicSub(&w.fc_ref[old], 1) == 1) w.fc_stamp[old] = w.fc_ctr[FC_STEP] + 1;
+            w.lu_ix[grp] = -1;
+        }
+        w.fc_do[grp] = 0;
+    }
+    unsigned long long key;
+    if (w.s_status[grp] != ST_ACTIVE || uses_shared_lu(w, grp)) key = 0;
+    else if (w.o_b[grp] >= 0) key = 1;
+    else {
+        const unsigned char *bt = w.btype + (size_t)grp * N;
+        unsigned long long h = 0;
+        int i = lane;
+        for (; i + 96 < N; i += 128) {                              // four loads in flight
+            const unsigned b0 = bt[i], b1 = bt[i + 32], b2 = bt[i + 64], b3 = bt[i + 96];
+            h += fc_mix(((unsigned long long)(i + 1) << 8) | b0) + fc_mix(((unsigned long long)(i + 33) << 8) | b1) +
+                 fc_mix(((unsigned long long)(i + 65) << 8) | b2) + fc_mix(((unsigned long long)(i + 97) << 8) | b3);
+        }
+        for (; i < N; i += 32) h += fc_mix(((unsigned long long)(i + 1) << 8) | bt[i]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xFFFFFFFFu, h, o);
+        key = h < 2 ? h + 2 : h;
+    }
+    if (lane == 0) w.fc_hash[fi] = key;
+}
+
 __global__ void __launch_bounds__(1024) k_fcache(PlanDev p, WorkDev w) {
     const int nfact = w.fact_count[w.parity];
     if (nfact == 0) return;
     const int *list = w.fact_list + (size_t)w.parity * w.ngroups;
     const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
-    const int P = w.ngroups, N = p.N;
-    __shared__ int s_npend, s_first, s_now;
+    const int P = w.ngroups;
+    __shared__ int s_npend, s_first, s_next;
     __shared__ unsigned long long s_red[32];
-    if (tid == 0) { s_npend = 0; s_now = ++w.fc_ctr[FC_STEP]; }
+    if (tid == 0) { s_npend = 0; w.fc_ctr[FC_STEP] += 1; }
     // deleted entries pile up when buffers are recycled: rebuild the table from the buffers' keys
     if (w.fc_ctr[FC_USED] > (w.fc_tmask + 1) / 2) {
         __syncthreads();
@@ -2390,42 +2428,15 @@ __global__ void __launch_bounds__(1024) k_fcache(PlanDev p, WorkDev w) {
         }
     }
     __syncthreads();
-    const int now = s_now;
-    // A: give the old buffer back; key of the new bus-type vector (0: no buffer needed, 1: a buffer of its own)
-    for (int fi = wp; fi < nfact; fi += 32) {
-        const int grp = list[fi];
-        if (lane == 0) {
-            const int old = w.lu_ix[grp];
-            if (old >= 0) {
-                if (atomicSub(&w.fc_ref[old], 1) == 1) w.fc_stamp[old] = now;
-                w.lu_ix[grp] = -1;
-            }
-        }
-        unsigned long long key;
-        if (w.s_status[grp] != ST_ACTIVE || uses_shared_lu(w, grp)) key = 0;
-        else if (w.o_b[grp] >= 0) key = 1;
-        else {
-            const unsigned char *bt = w.btype + (size_t)grp * N;
-            unsigned long long h = 0;
-            for (int i = lane; i < N; i += 32) h += fc_mix(((unsigned long long)(i + 1) << 8) | bt[i]);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xFFFFFFFFu, h, o);
-            key = h < 2 ? h + 2 : h;
-        }
-        if (lane == 0) w.fc_hash[fi] = key;
-    }
-    __syncthreads();
     // B: vectors already in the table
     for (int fi = tid; fi < nfact; fi += 1024) {
         const unsigned long long key = w.fc_hash[fi];
-        const int grp = list[fi];
-        w.fc_do[grp] = 0;
         if (key == 0) continue;
-        int slot = key > 1 ? fc_find(w, key) : -1;
+        const int slot = key > 1 ? fc_find(w, key) : -1;
         if (slot >= 0) {
             const int buf = w.fc_tbuf[slot];
             atomicAdd(&w.fc_ref[buf], 1);
-            w.lu_ix[grp] = buf;
+            w.lu_ix[list[fi]] = buf;
             atomicAdd(&w.fc_ctr[FC_HITS], 1);
         } else {
             w.fc_pend[atomicAdd(&s_npend, 1)] = fi;
@@ -2433,10 +2444,10 @@ __global__ void __launch_bounds__(1024) k_fcache(PlanDev p, WorkDev w) {
     }
     __syncthreads();
     const int npend = s_npend;
-    // C: new vectors, one per round: the first pending scenario takes the least recently used free buffer
-    // and enters its key; every other pending scenario with that key then finds it
+    // C: new vectors, one per round: the first pending scenario takes a buffer and enters its key; every
+    // other pending scenario with that key then finds it
     for (int round = 0; round <= npend; ++round) {
-        if (tid == 0) s_first = 0x7FFFFFFF;
+        if (tid == 0) { s_first = 0x7FFFFFFF; s_next = w.fc_ctr[FC_NEXT]; }
         __syncthreads();
         for (int i = tid; i < npend; i += 1024) {
             const int fi = w.fc_pend[i];
@@ -2444,9 +2455,9 @@ __global__ void __launch_bounds__(1024) k_fcache(PlanDev p, WorkDev w) {
             const unsigned long long key = w.fc_hash[fi];
             const int slot = (round > 0 && key > 1) ? fc_find(w, key) : -1;
             if (slot >= 0) {
-                const int buf = w.fc_tbuf[slot], grp = list[fi];
+                const int buf = w.fc_tbuf[slot];
                 atomicAdd(&w.fc_ref[buf], 1);
-                w.lu_ix[grp] = buf;
+                w.lu_ix[list[fi]] = buf;
                 atomicAdd(&w.fc_ctr[FC_HITS], 1);
                 w.fc_pend[i] = -1;
             } else {
@@ -2456,19 +2467,24 @@ __global__ void __launch_bounds__(1024) k_fcache(PlanDev p, WorkDev w) {
         __syncthreads();
         const int first = s_first;
         if (first == 0x7FFFFFFF) break;
-        // free buffer with the oldest release stamp
-        unsigned long long best = ~0ull;
-        for (int b = tid; b < P; b += 1024)
-            if (w.fc_ref[b] == 0) best = min(best, ((unsigned long long)(unsigned)w.fc_stamp[b] << 32) | (unsigned)b);
+        // a buffer never used so far, else the free buffer with the oldest release stamp
+        int buf = s_next;                                   // (block-uniform: the branch below has barriers)
+        if (buf >= P) {
+            unsigned long long best = ~0ull;
+            for (int b = tid; b < P; b += 1024)
+                if (w.fc_ref[b] == 0) best = min(best, ((unsigned long long)(unsigned)w.fc_stamp[b] << 32) | (unsigned)b);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xFFFFFFFFu, best, o));
-        if (lane == 0) s_red[wp] = best;
-        __syncthreads();
-        if (tid == 0) {
+            for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xFFFFFFFFu, best, o));
+            if (lane == 0) s_red[wp] = best;
+            __syncthreads();
+            best = s_red[0];
             for (int k = 1; k < 32; ++k) best = min(best, s_red[k]);
+            buf = (int)(best & 0xFFFFFFFFu);                // exists: every scenario holds at most one buffer, and this one holds none
+        }
+        if (tid == 0) {
+            if (buf == s_next && buf < P) w.fc_ctr[FC_NEXT] = buf + 1;
             const int fi = w.fc_pend[first], grp = list[fi];
             const unsigned long long key = w.fc_hash[fi];
-            const int buf = (int)(best & 0xFFFFFFFFu);      // a free buffer exists: every scenario holds at most one, and this one holds none
             const unsigned long long oldkey = w.fc_bkey[buf];
             if (oldkey > 1) {
                 const int os = fc_find(w, oldkey);
@@ -2482,7 +2498,6 @@ __global__ void __launch_bounds__(1024) k_fcache(PlanDev p, WorkDev w) {
             w.fc_do[grp] = 1;
             w.fc_ctr[FC_MISS] += 1;
             w.fc_pend[first] = -1;
-            __threadfence_block();
         }
         __syncthreads();
     }
@@ -2824,7 +2839,10 @@ void launch_kernel(int which, const PlanDev &p, const WorkDev &w, cudaStream_t s
     switch (which) {
         case KI_ASM: k_assemble<G><<<std::min(w.ngroups, 592), 256, 0, st>>>(p, w); break;
         case KI_BEGIN: k_step_begin<<<gridGrp, 128, 0, st>>>(w); break;
-        case KI_FCACHE: k_fcache<<<1, 1024, 0, st>>>(p, w); break;
+        case KI_FCACHE:
+            k_fchash<<<(w.ngroups + 7) / 8, 256, 0, st>>>(p, w);
+            k_fcache<<<1, 1024, 0, st>>>(p, w);
+            break;
         case KI_FACTOR:
             if (G == 1 && p.use_coop_factor) {
                 size_t smem = WPB_FACTOR * factor_smem_per_warp(p.cap_upd, p.cap_ent, p.cap_rowblk);
