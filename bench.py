@@ -547,9 +547,17 @@ def roofline_model(info, ncoef, stats, N, shared_first_pass=True):
     out = {}
     ms = stats['ms_kernel']
     steps = max(1, stats['steps'])
+    # factor cache (round 2): pass starts of the later passes served by an existing factorization (hits)
+    # and factorizations performed; R = scenarios sharing one factorization of a later pass
+    hits, nfac = float(stats.get('factor_cache_hits', 0) or 0), float(stats.get('factorizations', 0) or 0)
+    cached = shared_first_pass and nfac > 0 and hits > 0
+    R_later = (hits + nfac) / nfac if cached else 1.0
+    if cached:
+        passes_factored = nfac
     # K2 solve: rhs read + x write (16 B each per bus) at every order; LU blocks (32 B each) only
-    # when the scenario reads private factors (passes >= 2 with the shared first-pass factors)
-    b_solve = orders_private * 32.0 * nslots + orders * 32.0 * N
+    # when the scenario reads factors that are not shared by the whole batch (passes >= 2 with the shared
+    # first-pass factors), divided by R (12 nnz / R)
+    b_solve = orders_private * 32.0 * nslots / R_later + orders * 32.0 * N
     # K1 k_rhs_conv at order j, per bus (x read, V[j], H[j], rhs written: 64 B at every order):
     #   PV bus: histories V and CC, read j each (32 j).  PQ bus, blocked W recurrence (block 4):
     #   j < 4 or j % 4 == 0: histories V and W read j each (32 j), at a block start also three
@@ -575,10 +583,11 @@ def roofline_model(info, ncoef, stats, N, shared_first_pass=True):
     knames = {'solve': 'k_solve_rows', 'rhs_conv': 'k_rhs_conv', 'eps': 'k_eps', 'factor': 'k_factor_coop'}
     models = {
         'solve': 'SURVEY 8(d): 32 B per LU block / R + 32 B per bus, R = scenarios sharing the factors '
-                 '(first-pass orders read one shared copy: charged no factor bytes)',
+                 '(first-pass orders read one shared copy: charged no factor bytes; later passes: R = pass starts per '
+                 'factorization of the factor cache)',
         'rhs_conv': 'own algorithm: history walks of the blocked W recurrence and the PV convolutions + 64 B per bus-order',
         'eps': 'own algorithm: epsilon anti-diagonal read and written at even orders + 64 B per bus',
-        'factor': '96 B per LU block per factorized pass (first passes share one factorization)',
+        'factor': '96 B per LU block per factorization performed (first passes share one, later passes share through the factor cache)',
     }
     for name, b in (('solve', b_solve), ('rhs_conv', b_rhs), ('eps', b_eps), ('factor', b_fac)):
         t = ms.get(name, 0.0)
@@ -590,6 +599,9 @@ def roofline_model(info, ncoef, stats, N, shared_first_pass=True):
         out[name]['gbs_8d'] = (b / (t * 1e-3) / 1e9) if t > 0 else 0.0
     out['solve']['orders'] = orders
     out['solve']['orders_on_shared_first_pass_factors'] = orders - orders_private
+    out['solve']['scenarios_per_factorization_later_passes'] = R_later
+    out['solve']['bytes_private_factors'] = orders_private * 32.0 * nslots + orders * 32.0 * N   # what the solve would read without the factor cache
+    out['factor']['factorizations'] = passes_factored
     return out
 
 

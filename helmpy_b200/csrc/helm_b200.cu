@@ -130,7 +130,7 @@ struct WorkDev {
     // null: no cache, slot g owns buffer g.
     int *lu_ix;                       // [ngroups] pool buffer (-1: none / shared first-pass factors)
     int *fc_do;                       // [ngroups] 1: the slot's scenario factorizes its buffer in this side branch
-    int *fc_ref, *fc_stamp, *fc_sing; // [ngroups] per buffer: scenarios using it, step of its last release, singular matrix
+    int *fc_ref, *fc_stamp, *fc_sing, *fc_rdy; // [ngroups] per buffer: scenarios using it, step of its last release, singular matrix, first step its factors may be read
     int *fc_tbuf, *fc_pend, *fc_ctr;  // hash table values [T], pending list [ngroups], counters [16]
     unsigned long long *fc_bkey, *fc_tkey, *fc_hash;   // key of a buffer [ngroups], table keys [T], keys of the step's list [ngroups]
     int fc_tmask;                     // T - 1
@@ -621,7 +621,7 @@ __global__ void __launch_bounds__(WPB * 32) k_factor_coop(PlanDev p, WorkDev w) 
         const int grp = w.fact_list[(size_t)w.parity * w.ngroups + fi];
         if (w.s_status[grp] != ST_ACTIVE) continue;         // CTA-uniform
         if (!w.skip_asm) {
-            if (w.g_flags[grp] & GF_NEWSCEN) {
+            if (!w.lu_ix && (w.g_flags[grp] & GF_NEWSCEN)) {   // (with the factor cache: done by k_fchash)
                 asm_reset<1>(p, w, grp, threadIdx.x, WPB * 32);
                 __syncthreads();
             }
@@ -664,7 +664,7 @@ __global__ void __launch_bounds__(WPB * 32) k_factor_coop(PlanDev p, WorkDev w) 
     // assembly of A by the same warp (no separate kernel in front: the factorization starts at the
     // beginning of the step, while the main branch's solve is being dispatched)
     if (!w.skip_asm) {
-        if (w.g_flags[grp] & GF_NEWSCEN) {
+        if (!w.lu_ix && (w.g_flags[grp] & GF_NEWSCEN)) {     // (with the factor cache: done by k_fchash)
             asm_reset<1>(p, w, grp, lane, 32);
             __syncwarp();
         }
@@ -2382,10 +2382,17 @@ __global__ void __launch_bounds__(256) k_fchash(PlanDev p, WorkDev w) {
     if (lane == 0) {
         const int old = w.lu_ix[grp];
         if (old >= 0) {
-            if (atomicSub(&w.fc_ref[old], 1) == 1) w.fc_stamp[old] = w.fc_ctr[FC_STEP] + 1;
+            if (atomicSub(&w.fc_ref[old], 1) == 1) w.fc_stamp[old] = w.fc_ctr[FC_STEP];
             w.lu_ix[grp] = -1;
         }
         w.fc_do[grp] = 0;
+        w.g_fage[grp] = 1;                                   // nothing to wait for unless k_fcache says so
+    }
+    // a scenario that has just taken over the slot starts from the base bus types (with the cache this
+    // happens here, ahead of k_init on the main stream, instead of in the factorization kernel)
+    if (w.g_flags[grp] & GF_NEWSCEN) {
+        asm_reset<1>(p, w, grp, lane, 32);
+        __syncwarp();
     }
     unsigned long long key;
     if (w.s_status[grp] != ST_ACTIVE || uses_shared_lu(w, grp)) key = 0;
@@ -2415,7 +2422,8 @@ __global__ void __launch_bounds__(1024) k_fcache(PlanDev p, WorkDev w) {
     const int P = w.ngroups;
     __shared__ int s_npend, s_first, s_next;
     __shared__ unsigned long long s_red[32];
-    if (tid == 0) { s_npend = 0; w.fc_ctr[FC_STEP] += 1; }
+    if (tid == 0) s_npend = 0;
+    const int now = w.fc_ctr[FC_STEP];                      // (k_step_begin counts the steps)
     // deleted entries pile up when buffers are recycled: rebuild the table from the buffers' keys
     if (w.fc_ctr[FC_USED] > (w.fc_tmask + 1) / 2) {
         __syncthreads();
@@ -2437,6 +2445,7 @@ __global__ void __launch_bounds__(1024) k_fcache(PlanDev p, WorkDev w) {
             const int buf = w.fc_tbuf[slot];
             atomicAdd(&w.fc_ref[buf], 1);
             w.lu_ix[list[fi]] = buf;
+            w.g_fage[list[fi]] = max(1, w.fc_rdy[buf] - now);   // factors in flight (previous step's side branch): wait for its join
             atomicAdd(&w.fc_ctr[FC_HITS], 1);
         } else {
             w.fc_pend[atomicAdd(&s_npend, 1)] = fi;
@@ -2458,6 +2467,7 @@ __global__ void __launch_bounds__(1024) k_fcache(PlanDev p, WorkDev w) {
                 const int buf = w.fc_tbuf[slot];
                 atomicAdd(&w.fc_ref[buf], 1);
                 w.lu_ix[list[fi]] = buf;
+                w.g_fage[list[fi]] = max(1, w.fc_rdy[buf] - now);
                 atomicAdd(&w.fc_ctr[FC_HITS], 1);
                 w.fc_pend[i] = -1;
             } else {
@@ -2494,8 +2504,10 @@ __global__ void __launch_bounds__(1024) k_fcache(PlanDev p, WorkDev w) {
             if (key > 1) fc_insert(w, key, buf);
             w.fc_ref[buf] = 1;
             w.fc_sing[buf] = 0;
+            w.fc_rdy[buf] = now + w.depth;                  // its side branch is joined at the end of step now + depth - 1
             w.lu_ix[grp] = buf;
             w.fc_do[grp] = 1;
+            w.g_fage[grp] = w.depth;
             w.fc_ctr[FC_MISS] += 1;
             w.fc_pend[first] = -1;
         }
@@ -2516,6 +2528,7 @@ __global__ void k_step_begin(WorkDev w) {
         w.fact_count[(w.parity + 1) % (w.depth + 1)] = 0;
         w.solve_count[(w.parity + 1) % (w.depth + 1)] = 0;
         *w.pend_count = 0;
+        if (w.fc_ctr) w.fc_ctr[FC_STEP] += 1;                // factor cache: step counter
     }
     int gf = w.g_flags[grp];
     if (gf & GF_FACTORING) {
@@ -2751,11 +2764,11 @@ WsLayout layout(const helm_plan *pl, int B, const helm_params *prm) {
         L.off_vre = take(per * sizeof(double));
         L.off_qcur = take(per * sizeof(double));
     }
-    // factor cache: [lu_ix | fc_do | fc_ref | fc_stamp | fc_sing | fc_pend][ngroups] ints, fc_tbuf[T] ints, fc_ctr[16] ints,
+    // factor cache: [lu_ix | fc_do | fc_ref | fc_stamp | fc_sing | fc_pend | fc_rdy][ngroups] ints, fc_tbuf[T] ints, fc_ctr[16] ints,
     // then [fc_bkey | fc_hash][ngroups] and fc_tkey[T] 64-bit words
     L.fc_T = 1024;
     while (L.fc_T < 4 * L.ngroups) L.fc_T <<= 1;
-    L.off_fc = take(sizeof(int) * ((size_t)6 * L.ngroups + L.fc_T + 16) + 8 + sizeof(unsigned long long) * ((size_t)2 * L.ngroups + L.fc_T));
+    L.off_fc = take(sizeof(int) * ((size_t)7 * L.ngroups + L.fc_T + 16) + 8 + sizeof(unsigned long long) * ((size_t)2 * L.ngroups + L.fc_T));
     L.off_sw_ent = L.off_sw_q = 0;
     L.sw_cap = 0;
     if (prm->record_switches) {
@@ -2793,7 +2806,7 @@ WorkDev bind(const helm_plan *pl, const WsLayout &L, int B, const helm_params *p
     w.xb = (double2 *)(b + L.off_xb);
     w.lu = (double2 *)(b + L.off_lu);
     w.lu_shared = nullptr;
-    w.lu_ix = nullptr; w.fc_do = nullptr; w.fc_ref = w.fc_stamp = w.fc_sing = w.fc_tbuf = w.fc_pend = w.fc_ctr = nullptr;
+    w.lu_ix = nullptr; w.fc_do = nullptr; w.fc_ref = w.fc_stamp = w.fc_sing = w.fc_rdy = w.fc_tbuf = w.fc_pend = w.fc_ctr = nullptr;
     w.fc_bkey = w.fc_tkey = w.fc_hash = nullptr; w.fc_tmask = 0;
     w.Vh = (double2 *)(b + L.off_Vh);
     w.Hh = (double2 *)(b + L.off_Hh);
@@ -2941,11 +2954,15 @@ struct StepSeq {
 StepSeq make_seq(const WorkDev &w, bool fused_asm) {
     StepSeq q;
     const bool dsb = w.dsb_method != 0, pv1 = w.pv_model == 1;
+    // factor cache: most pass starts have nothing to factorize and rejoin after ONE step, so their germ
+    // and first right-hand side (k_init) are computed on the main stream, not behind the factorizations
+    const bool init_on_main = w.lu_ix != nullptr;
     if (!fused_asm) q.side_seq[q.side_len++] = KI_ASM;     // k_factor_coop assembles A itself
     q.side_seq[q.side_len++] = KI_FACTOR;
     if (dsb) { q.side_seq[q.side_len++] = KI_BPREP; q.side_seq[q.side_len++] = KI_SOLVE_SIDE; q.side_seq[q.side_len++] = KI_BFIN; }
-    q.side_seq[q.side_len++] = KI_INIT;
+    if (!init_on_main) q.side_seq[q.side_len++] = KI_INIT;
     if (pv1) q.side_seq[q.side_len++] = KI_PV1C_SIDE;
+    if (init_on_main) q.main_seq[q.main_len++] = KI_INIT;
     q.main_seq[q.main_len++] = KI_SOLVE;
     if (dsb) q.main_seq[q.main_len++] = KI_BP;
     if (dsb || pv1) q.main_seq[q.main_len++] = KI_VPRE;
@@ -3363,8 +3380,9 @@ int helm_solve_batch_device(helm_plan *pl, int32_t B, const double *d_scale, con
         int *fi = (int *)((char *)d_ws + L.off_fc);
         const size_t ng = (size_t)L.ngroups;
         w.lu_ix = fi; w.fc_do = fi + ng; w.fc_ref = fi + 2 * ng; w.fc_stamp = fi + 3 * ng; w.fc_sing = fi + 4 * ng; w.fc_pend = fi + 5 * ng;
-        w.fc_tbuf = fi + 6 * ng; w.fc_ctr = w.fc_tbuf + L.fc_T;
-        const size_t nints = 6 * ng + L.fc_T + 16;
+        w.fc_rdy = fi + 6 * ng;
+        w.fc_tbuf = fi + 7 * ng; w.fc_ctr = w.fc_tbuf + L.fc_T;
+        const size_t nints = 7 * ng + L.fc_T + 16;
         unsigned long long *fq = (unsigned long long *)((char *)d_ws + L.off_fc + (nints * sizeof(int) + 7) / 8 * 8);
         w.fc_bkey = fq; w.fc_hash = fq + ng; w.fc_tkey = fq + 2 * ng;
         w.fc_tmask = L.fc_T - 1;
@@ -3390,7 +3408,7 @@ int helm_solve_batch_device(helm_plan *pl, int32_t B, const double *d_scale, con
     }
     const StepCtx ctx{st, pl->side, pl->ev_fork, pl->ev_join, depth};
     const StepSeq seq = make_seq(w, L.G == 1 && p.use_coop_factor);
-    const int STEP_LEN = 1 + seq.main_len + seq.side_len;
+    const int STEP_LEN = 1 + seq.main_len + seq.side_len + (w.lu_ix ? 2 : 0);
     // `count` steps starting at step index `first`; every side branch is joined back into st
     auto launch_batch = [&](long first, int count) {
         for (int rep = 0; rep < count; ++rep) launch_step(L.G, p, w, ctx, seq, first + rep, rep == count - 1);

@@ -229,6 +229,45 @@ def test_large_batch_solve_kernels_agree(hb):
         assert np.max(np.abs(np.array(a[1]) - np.array(b[1]))) < 1e-10
 
 
+@pytest.mark.gpu
+def test_factor_cache_equals_private_factorizations(hb, monkeypatch):
+    """Scenarios whose bus types agree share one factorization (k_fcache).  The result is the same as with
+    one factorization per scenario and pass, bit for bit (same matrix, same kernel, same schedule) -- also
+    when the pool is smaller than the number of distinct matrices and buffers are recycled, with N-1
+    scenarios (never shared) in the batch, and the oracle agrees."""
+    case = load_case('case1354pegase')
+    scales = np.random.default_rng(17).uniform(0.85, 1.04, 1500)
+    for resident in (64, 1200):
+        monkeypatch.delenv('HELM_B200_NO_FCACHE', raising=False)
+        a = hb.helm_batch(case, scales, mismatch=1e-8, max_coefficients=40, max_resident=resident)
+        monkeypatch.setenv('HELM_B200_NO_FCACHE', '1')
+        b = hb.helm_batch(case, scales, mismatch=1e-8, max_coefficients=40, max_resident=resident)
+        monkeypatch.delenv('HELM_B200_NO_FCACHE')
+        assert a.converged.all() and np.array_equal(a.ncoef, b.ncoef) and np.array_equal(a.nswitch, b.nswitch)
+        assert np.array_equal(a.V, b.V)
+        assert b.stats['factorizations'] == 0 and a.stats['factorizations'] > 0
+        # most pass starts found their factors; with 64 buffers more matrices than buffers were seen, so
+        # buffers were recycled and some matrices factorized again
+        if resident == 64:
+            assert a.stats['factorizations'] > 64 and a.stats['factor_cache_hits'] > a.stats['factorizations']
+        else:
+            assert a.stats['factor_cache_hits'] > 5 * a.stats['factorizations']
+    for bsel in (0, 700, 1499):
+        Vo, info = ho.helm_oracle(case, mismatch=1e-8, scale=float(scales[bsel]), max_coefficients=40)
+        assert a.list_coef(bsel) == info['list_coef']
+        dmag, dang = polar_err(a.V[bsel], Vo)
+        assert dmag <= TOL_MAG and dang <= TOL_ANG
+    # outages in the batch: their matrices are their own
+    safe = hb.non_islanding_branches(case)
+    outages = np.full(300, -1, dtype=np.int32)
+    outages[::3] = safe[:100]
+    sc = scales[:300]
+    c = hb.helm_batch(case, sc, mismatch=1e-8, max_coefficients=40, outages=outages)
+    monkeypatch.setenv('HELM_B200_NO_FCACHE', '1')
+    d = hb.helm_batch(case, sc, mismatch=1e-8, max_coefficients=40, outages=outages)
+    assert np.array_equal(c.status, d.status) and np.array_equal(c.ncoef, d.ncoef) and np.array_equal(c.V, d.V)
+
+
 def _numbers(text):
     import re
     return [float(x) for x in re.findall(r'[-+]?\d+\.\d+(?:[eE][-+]?\d+)?', text.replace('+   ', '+').replace('-   ', '-'))]
