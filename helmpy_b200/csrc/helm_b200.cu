@@ -987,6 +987,9 @@ __device__ __forceinline__ Blk256 ld_blk_stream(const double2 *lu, int slot) {
 #define ROWS_REGS 64       // 28 warps per SM and room for a factorization CTA beside them, as k_solve_flat
 #endif
 #define ROWS_NB (helm::Symbolic::RL_BLOCKS)      // blocks per lane and wave
+#ifndef ROWS_F2
+#define ROWS_F2 0          // fetch word two waves ahead: measured slower (226 -> 236-251 ms per 16 384 scenarios), kept for A/B builds
+#endif
 #ifndef ROWS_PIN
 #define ROWS_PIN 1
 #endif
@@ -1004,6 +1007,42 @@ __device__ __forceinline__ void rows_fetch(const double2 *lu, const int f, Blk25
     if (cnt > 1) m[1] = ld_blk_stream<STREAM>(lu, slot + k);
     if (cnt > 2) m[2] = ld_blk_stream<STREAM>(lu, slot + 2 * k);
     if (ROWS_NB > 3 && cnt > 3) m[3] = ld_blk_stream<STREAM>(lu, slot + 3 * k);
+}
+
+// one wave of k_solve_rows: record d, its blocks in m; fn = fetch word of the NEXT wave, whose blocks replace m
+// (m[0] last: it may be this wave's pivot)
+__device__ __forceinline__ void rows_wave(const double2 *lu, const double2 *rhs, double2 *xb, const int4 d, const int fn, Blk256 (&m)[4]) {
+    using Sy = helm::Symbolic;
+    if (d.w & Sy::RL_SYNC) __syncwarp();
+    const unsigned c0 = (unsigned)d.x & 0xFFFFu, c1 = (unsigned)d.x >> 16, c2 = (unsigned)d.y & 0xFFFFu, c3 = (unsigned)d.y >> 16;
+    const bool isu = (d.w & Sy::RL_ISU) != 0, head = (d.w & Sy::RL_HEAD) != 0;
+    const int row = d.w & 0xFFFF;
+    double2 x0 = make_double2(0.0, 0.0), x1 = x0, x2 = x0, x3 = x0;
+    // v = (first lane of a row: what the row sum is subtracted from) - sum of the lane's blocks
+    double2 v = x0;
+    if (c0 < Sy::RL_DIAG) x0 = xb[c0];
+    if (c1 != Sy::RL_NONE) x1 = xb[c1];
+    if (c2 != Sy::RL_NONE) x2 = xb[c2];
+    if (ROWS_NB > 3 && c3 != Sy::RL_NONE) x3 = xb[c3];
+    if (head) v = isu ? xb[row] : __ldcs(rhs + row);
+    if (c0 < Sy::RL_DIAG) { v.x -= m[0].a * x0.x + m[0].b * x0.y; v.y -= m[0].c * x0.x + m[0].d * x0.y; }
+    if (c1 != Sy::RL_NONE) { v.x -= m[1].a * x1.x + m[1].b * x1.y; v.y -= m[1].c * x1.x + m[1].d * x1.y; }
+    if (c2 != Sy::RL_NONE) { v.x -= m[2].a * x2.x + m[2].b * x2.y; v.y -= m[2].c * x2.x + m[2].d * x2.y; }
+    if (ROWS_NB > 3 && c3 != Sy::RL_NONE) { v.x -= m[3].a * x3.x + m[3].b * x3.y; v.y -= m[3].c * x3.x + m[3].d * x3.y; }
+    rows_fetch<1, ROWS_STREAM != 0>(lu, fn, m);
+    const int span = (d.w >> 19) & 31, rounds = (d.w >> 27) & 7;
+    for (int r = 0; r < rounds; ++r) {
+        const int o = 1 << r;
+        const double tx = __shfl_down_sync(0xFFFFFFFFu, v.x, o);
+        const double ty = __shfl_down_sync(0xFFFFFFFFu, v.y, o);
+        add_if_le(v, tx, ty, o, span);
+    }
+    if (head) {
+        // U rows: the head lane's first block is the inverted pivot
+        if (isu) v = make_double2(m[0].a * v.x + m[0].b * v.y, m[0].c * v.x + m[0].d * v.y);
+        xb[row] = v;
+    }
+    if (fn >> 27) m[0] = ld_blk_stream<ROWS_STREAM != 0>(lu, fn & 0xFFFFFF);
 }
 
 template <int WPB>
@@ -1030,54 +1069,37 @@ __global__ void __maxnreg__(ROWS_REGS) k_solve_rows(PlanDev p, WorkDev w) {
     double2 *xb = w.xb + (size_t)grp * p.N;
     const int4 *desc = p.rl_desc + lane;
 #endif
-    int4 d = __ldg(desc);
+    int4 da = __ldg(desc), db;
     Blk256 m[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) m[t] = Blk256{0.0, 0.0, 0.0, 0.0};
-    rows_fetch<0, ROWS_STREAM != 0>(lu, d.z, m);
+    rows_fetch<0, ROWS_STREAM != 0>(lu, da.z, m);
     // (L2 evict-last hints on the accesses to x: 288 -> 283 ms per 16 384 scenarios, dropped)
-#define LDX(ptr) (*(ptr))
-#define STX(ptr, v) (*(ptr) = (v))
-    for (int r = lane; r < p.n_rows_nol; r += 32) STX(xb + r, __ldcs(rhs + r));     // rows without L entries: y = rhs
-#pragma unroll ROWS_UNROLL_N
-    while (!(d.w & Sy::RL_STOP)) {                                    // the table ends with idle waves that say stop
-        desc += 32;
-        const int4 dn = __ldg(desc);
-        const int f1 = dn.z;                                          // (reading the fetch word two waves ahead was measured slower)
-        if (d.w & Sy::RL_SYNC) __syncwarp();
-        const unsigned c0 = (unsigned)d.x & 0xFFFFu, c1 = (unsigned)d.x >> 16, c2 = (unsigned)d.y & 0xFFFFu, c3 = (unsigned)d.y >> 16;
-        const bool isu = (d.w & Sy::RL_ISU) != 0, head = (d.w & Sy::RL_HEAD) != 0;
-        const int row = d.w & 0xFFFF;
-        double2 x0 = make_double2(0.0, 0.0), x1 = x0, x2 = x0, x3 = x0;
-        // v = (first lane of a row: what the row sum is subtracted from) - sum of the lane's blocks
-        double2 v = x0;
-        if (c0 < Sy::RL_DIAG) x0 = LDX(xb + c0);
-        if (c1 != Sy::RL_NONE) x1 = LDX(xb + c1);
-        if (c2 != Sy::RL_NONE) x2 = LDX(xb + c2);
-        if (ROWS_NB > 3 && c3 != Sy::RL_NONE) x3 = LDX(xb + c3);
-        if (head) v = isu ? LDX(xb + row) : __ldcs(rhs + row);
-        if (c0 < Sy::RL_DIAG) { v.x -= m[0].a * x0.x + m[0].b * x0.y; v.y -= m[0].c * x0.x + m[0].d * x0.y; }
-        if (c1 != Sy::RL_NONE) { v.x -= m[1].a * x1.x + m[1].b * x1.y; v.y -= m[1].c * x1.x + m[1].d * x1.y; }
-        if (c2 != Sy::RL_NONE) { v.x -= m[2].a * x2.x + m[2].b * x2.y; v.y -= m[2].c * x2.x + m[2].d * x2.y; }
-        if (ROWS_NB > 3 && c3 != Sy::RL_NONE) { v.x -= m[3].a * x3.x + m[3].b * x3.y; v.y -= m[3].c * x3.x + m[3].d * x3.y; }
-        rows_fetch<1, ROWS_STREAM != 0>(lu, f1, m);                                     // m[0] may still be this wave's pivot
-        const int span = (d.w >> 19) & 31, rounds = (d.w >> 27) & 7;
-        for (int r = 0; r < rounds; ++r) {
-            const int o = 1 << r;
-            const double tx = __shfl_down_sync(0xFFFFFFFFu, v.x, o);
-            const double ty = __shfl_down_sync(0xFFFFFFFFu, v.y, o);
-            add_if_le(v, tx, ty, o, span);
-        }
-        if (head) {
-            // U rows: the head lane's first block is the inverted pivot
-            if (isu) v = make_double2(m[0].a * v.x + m[0].b * v.y, m[0].c * v.x + m[0].d * v.y);
-            STX(xb + row, v);
-        }
-        if (f1 >> 27) m[0] = ld_blk_stream<ROWS_STREAM != 0>(lu, f1 & 0xFFFFFF);
-        d = dn;
+    for (int r = lane; r < p.n_rows_nol; r += 32) xb[r] = __ldcs(rhs + r);     // rows without L entries: y = rhs
+#if ROWS_F2
+    // The fetch word is read TWO waves ahead, so that the block requests of the next wave never wait for
+    // a record (one L2 round trip less on every wave's chain: with the factor cache the solve is bound by
+    // L2 latency, not by DRAM); two waves per trip, so that no look-ahead value is copied between
+    // registers (a copy waits for the load it copies).  The table ends with two idle waves that say stop.
+    int fa, fb = __ldg(&desc[32].z);
+    while (true) {
+        if (da.w & Sy::RL_STOP) break;
+        db = __ldg(desc + 32); fa = __ldg(&desc[64].z);
+        rows_wave(lu, rhs, xb, da, fb, m);
+        if (db.w & Sy::RL_STOP) break;
+        desc += 64;
+        da = __ldg(desc); fb = __ldg(&desc[32].z);
+        rows_wave(lu, rhs, xb, db, fa, m);
     }
-#undef LDX
-#undef STX
+#else
+#pragma unroll ROWS_UNROLL_N
+    while (!(da.w & Sy::RL_STOP)) {                                   // the table ends with idle waves that say stop
+        desc += 32;
+        db = __ldg(desc);
+        rows_wave(lu, rhs, xb, da, db.z, m);
+        da = db;
+    }
+#endif
 }
 
 // ---- K2 (G = 1), row-lane solve with x in shared memory ---------------------------------------------
