@@ -215,8 +215,9 @@ int helm_debug_factor_solve(helm_plan *plan, int32_t n_scen, int32_t group,
                             double *h_x /* [n_scen*2*n_bus] */);
 
 /* Microbenchmark: device time (ms) of one triangular solve of one scenario of the plan's grid with
- * one kernel alone on the GPU: kernel 0 = k_solve_one, 1 = k_solve_cta, 2 = k_solve_flat.  `ablation`
- * (k_solve_one only; 0 = the real kernel) switches parts of the kernel off for timing: 1 no shuffle
+ * one kernel alone on the GPU: kernel 0 = k_solve_one, 1 = k_solve_cta, 2 = k_solve_flat, 3 = k_solve_rows_cta,
+ * 4 = k_solve_rows, 5 = k_solve_rows_deep.  `ablation`
+ * (k_solve_one and k_solve_rows_cta only; 0 = the real kernel) switches parts of the kernel off for timing: 1 no shuffle
  * reduction, 2 no operand copies after the first, 4 no gather of x, 8 no block barriers, 16 no thin
  * segments, 32 no wide segments — results are then wrong, only the time is meaningful. */
 int helm_debug_solve_time(helm_plan *plan, int32_t kernel, int32_t ablation, int32_t reps, double *ms_per_solve);
