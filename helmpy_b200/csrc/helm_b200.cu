@@ -1024,7 +1024,7 @@ __device__ __forceinline__ void rows_wave(const double2 *lu, const double2 *rhs,
     if (c1 != Sy::RL_NONE) x1 = xb[c1];
     if (c2 != Sy::RL_NONE) x2 = xb[c2];
     if (ROWS_NB > 3 && c3 != Sy::RL_NONE) x3 = xb[c3];
-    if (head) v = isu ? xb[row] : __ldcs(rhs + row);
+    if (head) v = (isu || d.w < 0) ? xb[row] : __ldcs(rhs + row);   // d.w < 0: RL_CONT, a later piece of a long row
     if (c0 < Sy::RL_DIAG) { v.x -= m[0].a * x0.x + m[0].b * x0.y; v.y -= m[0].c * x0.x + m[0].d * x0.y; }
     if (c1 != Sy::RL_NONE) { v.x -= m[1].a * x1.x + m[1].b * x1.y; v.y -= m[1].c * x1.x + m[1].d * x1.y; }
     if (c2 != Sy::RL_NONE) { v.x -= m[2].a * x2.x + m[2].b * x2.y; v.y -= m[2].c * x2.x + m[2].d * x2.y; }
@@ -1038,8 +1038,8 @@ __device__ __forceinline__ void rows_wave(const double2 *lu, const double2 *rhs,
         add_if_le(v, tx, ty, o, span);
     }
     if (head) {
-        // U rows: the head lane's first block is the inverted pivot
-        if (isu) v = make_double2(m[0].a * v.x + m[0].b * v.y, m[0].c * v.x + m[0].d * v.y);
+        // U rows: the head lane's first block is the inverted pivot (of a long row: in its last piece only)
+        if (c0 == Sy::RL_DIAG) v = make_double2(m[0].a * v.x + m[0].b * v.y, m[0].c * v.x + m[0].d * v.y);
         xb[row] = v;
     }
     if (fn >> 27) m[0] = ld_blk_stream<ROWS_STREAM != 0>(lu, fn & 0xFFFFFF);
@@ -1165,7 +1165,7 @@ __device__ __forceinline__ void rc_wave(const double2 *lu, double2 *xs, const in
         add_if_le(v, tx, ty, o, span);
     }
     if (head) {
-        if (isu) v = make_double2(m[0].a * v.x + m[0].b * v.y, m[0].c * v.x + m[0].d * v.y);
+        if (c0 == Sy::RL_DIAG) v = make_double2(m[0].a * v.x + m[0].b * v.y, m[0].c * v.x + m[0].d * v.y);
         xs[row] = v;
     }
     if (fn >> 27) m[0] = ld_blk_stream<STREAM>(lu, fn & 0xFFFFFF);
@@ -1282,7 +1282,7 @@ __device__ __forceinline__ void rcd_wave(const RcDeep &c, const int4 d, const in
         add_if_le(v, tx, ty, o, span);
     }
     if (head) {
-        if (isu) v = make_double2(m[0].a * v.x + m[0].b * v.y, m[0].c * v.x + m[0].d * v.y);
+        if (c0 == Sy::RL_DIAG) v = make_double2(m[0].a * v.x + m[0].b * v.y, m[0].c * v.x + m[0].d * v.y);
         xs[row] = v;
     }
     if (f2 >> 27) m[0] = ld_blk_stream<false>(c.lu, f2 & 0xFFFFFF);

@@ -19,6 +19,7 @@
 #include "symbolic.h"
 
 #include <algorithm>
+#include <functional>
 #include <cstdlib>
 #include <queue>
 #include <utility>
@@ -486,14 +487,14 @@ bool build_symbolic(int N, const int32_t *adj_ptr, const int32_t *adj_idx, const
         const int RL_T = getenv("HELM_B200_ROWS_T") ? std::max(1, std::min(Symbolic::RL_BLOCKS, atoi(getenv("HELM_B200_ROWS_T")))) : Symbolic::RL_BLOCKS;
         S.rl_desc.clear();
         S.rl_nwaves = 0;
-        struct Row { int slot0, n, row, k, diag; const int *cols; };
+        struct Row { int slot0, n, row, k, diag; const int *cols; bool cont; };
         bool ok = N < Symbolic::RL_DIAG && S.nslots < (1 << 24);
-        auto emit_level = [&](std::vector<Row> &rows, bool isU) {
+        const int CAP = 32 * RL_T;                        // blocks of a row one wave can take
+        auto emit_rows = [&](std::vector<Row> &rows, bool isU) {      // one level (or one round of pieces of long rows)
             for (Row &r : rows) {
                 int want = (r.n + RL_T - 1) / RL_T, k = 1;
                 while (k < want && k < 32) k <<= 1;
                 r.k = k;
-                if (r.n > RL_T * k) ok = false;
             }
             std::stable_sort(rows.begin(), rows.end(), [](const Row &a, const Row &b) { return a.k > b.k; });
             size_t i = 0;
@@ -520,19 +521,19 @@ bool build_symbolic(int N, const int32_t *adj_ptr, const int32_t *adj_idx, const
                     for (int sub = 0; sub < r.k; ++sub, ++lane) {
                         int c[4];
                         for (int t = 0; t < 4; ++t) {
-                            const int b = sub + t * r.k;           // block of the row: [pivot |] entries
+                            const int b = sub + t * r.k;           // block of the piece: [pivot |] entries
                             if (b >= r.n) c[t] = Symbolic::RL_NONE;
                             else if (r.diag && b == 0) c[t] = Symbolic::RL_DIAG;
                             else c[t] = r.cols[b - r.diag];
                         }
                         int *d = &S.rl_desc[d0 + 4 * lane];
-                        d[0] = c[0] | (c[1] << 16);
-                        d[1] = c[2] | (c[3] << 16);
                         int cnt = 0;
                         while (cnt < 4 && c[cnt] != Symbolic::RL_NONE) ++cnt;
+                        d[0] = c[0] | (c[1] << 16);
+                        d[1] = c[2] | (c[3] << 16);
                         d[2] = (r.slot0 + sub) | (klog << 24) | (cnt << 27);
                         d[3] = (sub == 0 ? r.row : Symbolic::RL_NONE) | (klog << 16) | ((r.k - 1 - sub) << 19) |
-                               (sub == 0 ? Symbolic::RL_HEAD : 0) | wflags;
+                               (sub == 0 ? Symbolic::RL_HEAD : 0) | wflags | (r.cont ? Symbolic::RL_CONT : 0);
                     }
                 }
                 for (; lane < 32; ++lane) {            // idle lanes: nothing to load, nothing to store
@@ -543,19 +544,62 @@ bool build_symbolic(int N, const int32_t *adj_ptr, const int32_t *adj_idx, const
                 }
             }
         };
+        // rows: whole rows {first slot, blocks incl. the pivot if diag, row, -, diag, columns}.  A row longer than CAP
+        // is cut: the pieces WITHOUT the pivot first (each a level of its own, the first one in the row's
+        // level), the piece that starts with the pivot last.
+        auto emit_level = [&](std::vector<Row> &rows, bool isU) {
+            std::vector<Row> now, later;
+            bool more = false;
+            for (const Row &r : rows) {
+                if (r.n <= CAP) { now.push_back(r); continue; }
+                more = true;
+                // tail piece of CAP blocks now, the rest (which keeps the pivot at its front) later
+                Row tail = r;
+                tail.slot0 = r.slot0 + (r.n - CAP);
+                tail.n = CAP;
+                tail.cols = r.cols + (r.n - CAP) - r.diag;
+                tail.diag = 0;
+                now.push_back(tail);
+                Row rest = r;
+                rest.n = r.n - CAP;
+                rest.cont = true;
+                later.push_back(rest);
+            }
+            emit_rows(now, isU);
+            if (more) {
+                std::function<void(std::vector<Row> &)> again = [&](std::vector<Row> &v) {
+                    std::vector<Row> n2, l2;
+                    for (const Row &r : v) {
+                        if (r.n <= CAP) { n2.push_back(r); continue; }
+                        Row tail = r;
+                        tail.slot0 = r.slot0 + (r.n - CAP);
+                        tail.n = CAP;
+                        tail.cols = r.cols + (r.n - CAP) - r.diag;
+                        tail.diag = 0;
+                        n2.push_back(tail);
+                        Row rest = r;
+                        rest.n = r.n - CAP;
+                        l2.push_back(rest);
+                    }
+                    emit_rows(n2, isU);
+                    if (!l2.empty()) again(l2);
+                };
+                again(later);
+            }
+        };
         std::vector<Row> rows;
         for (int l = 0; l < nLlev; ++l) {
             rows.clear();
             for (int r = S.llev_ptr[l]; r < S.llev_ptr[l + 1]; ++r) {
                 const int n = S.lptr[r + 1] - S.lptr[r];
-                if (n > 0) rows.push_back(Row{S.lptr[r], n, r, 1, 0, S.lcol.data() + S.lptr[r]});
+                if (n > 0) rows.push_back(Row{S.lptr[r], n, r, 1, 0, S.lcol.data() + S.lptr[r], false});
             }
             emit_level(rows, false);
         }
         for (int l = 0; l < nUlev; ++l) {
             rows.clear();
             for (int q = S.ulev_ptr[l]; q < S.ulev_ptr[l + 1]; ++q)
-                rows.push_back(Row{S.slotD(q), 1 + S.uptr[q + 1] - S.uptr[q], S.urow[q], 1, 1, S.ucol.data() + S.uptr[q]});
+                rows.push_back(Row{S.slotD(q), 1 + S.uptr[q + 1] - S.uptr[q], S.urow[q], 1, 1, S.ucol.data() + S.uptr[q], false});
             emit_level(rows, true);
         }
         if (ok) {

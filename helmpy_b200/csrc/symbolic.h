@@ -66,8 +66,10 @@ struct Symbolic {
     // c_t: column of the lane's t-th block (RL_NONE: no block, RL_DIAG: the row's inverted pivot);
     // flags: lanes-per-row log2 in bits 16-18, span (lanes after this one in the row's group) in
     // bits 19-23, then RL_HEAD / RL_SYNC / RL_ISU, shuffle rounds of the wave in bits 27-29.
-    // The table ends with two idle waves (look-ahead), the first of which says RL_STOP.
-    // Empty (rl_nwaves = 0) when a row or the grid is too large for the packed record.
+    // A row of more than 32 * RL_BLOCKS blocks is cut into pieces that run in consecutive one-wave levels,
+    // each continuing from the partial result in x[row]; the piece with the pivot comes last.
+    // The table ends with two idle waves (look-ahead) that say RL_STOP.
+    // Empty (rl_nwaves = 0) when the grid is too large for the packed record (16-bit columns, 24-bit slots).
     std::vector<int> rl_desc;
     int rl_nwaves = 0;
     // k_solve_rows_cta (one CTA of RC_WARPS warps per scenario, x in shared memory): the waves of a level
@@ -88,6 +90,7 @@ struct Symbolic {
     static constexpr int RL_BLOCKS = HELM_RL_BLOCKS;
     static constexpr int RL_NONE = 0xFFFF, RL_DIAG = 0xFFFE;
     static constexpr int RL_HEAD = 1 << 24, RL_SYNC = 1 << 25, RL_ISU = 1 << 26, RL_STOP = 1 << 30;
+    static constexpr int RL_CONT = (int)0x80000000u;           // a further piece of a row too long for one wave: the head lane continues from x[row]
 
     inline int slotD(int q) const { return nL + uptr[q] + q; }
     inline int slotU(int q, int t) const { return nL + uptr[q] + q + 1 + t; }

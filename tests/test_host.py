@@ -277,7 +277,7 @@ def test_flat_wave_schedule_solves(name):
     assert np.allclose(y, x, rtol=1e-9, atol=1e-9)
 
 
-@pytest.mark.parametrize('name', ['case9', 'case118', 'case1354pegase', 'case2869pegase', 'tiled'])
+@pytest.mark.parametrize('name', ['case9', 'case118', 'case1354pegase', 'case2869pegase', 'tiled', 'long_rows'])
 def test_row_lane_schedule_solves(name):
     """The packed per-lane records of k_solve_rows (symbolic.cpp 4b-rows), emulated lane by lane on the
     host: every L entry, pivot and U entry is used exactly once, no lane gathers a value written inside
@@ -285,6 +285,9 @@ def test_row_lane_schedule_solves(name):
     if name == 'tiled':
         import synth
         case = synth.tiled_case(['case1354pegase', 'case2869pegase', 'case118'])
+    elif name == 'long_rows':       # 13.6 k buses: rows of up to 120 blocks, cut into pieces (BASELINE config 5's grid)
+        import synth
+        case = synth.tiled_case(['case2869pegase'] * 4 + ['case1354pegase'] + ['case118'] * 7)
     else:
         case = load_case(name)
     S = _lib.symbolic_arrays(case.adj_ptr, case.adj_idx, case.bus_types_code())
@@ -292,6 +295,8 @@ def test_row_lane_schedule_solves(name):
     lptr, lcol, uptr, ucol, urow = S['lptr'], S['lcol'], S['uptr'], S['ucol'], S['urow']
     nL = int(lptr[-1])
     nslots = nL + int(uptr[-1]) + N
+    if name == 'long_rows':
+        assert int(np.diff(lptr).max()) > 96
     desc = S['rl_desc'].reshape(-1, 32, 4)
     assert len(desc) >= 2
     nw = len(desc) - 2                      # the last two records are the idle look-ahead waves
@@ -317,21 +322,30 @@ def test_row_lane_schedule_solves(name):
     while nol < N and lptr[nol + 1] == lptr[nol]:
         nol += 1
     y[:nol] = rhs[:nol]
-    final_u = np.zeros(N, dtype=bool)
+    qof = S['qof']
+    left_l = np.diff(lptr).astype(int)                      # blocks of the row still to be summed, forward
+    left_u = np.array([uptr[qof[r] + 1] - uptr[qof[r]] + 1 for r in range(N)], dtype=int)   # backward, with the pivot
+    started = np.zeros(N, dtype=bool)                       # a piece of the row has run in the current phase
     this_level = set()
     slot_col = S['slot_col']
     seen_u = False
+    npieces = 0
     for w in range(nw):
         d = desc[w]
         flags = d[:, 3]
         is_u = bool(flags[0] & (1 << 26))
         assert ((flags >> 25) & 3 == (flags[0] >> 25) & 3).all() and ((flags >> 27) & 7 == (flags[0] >> 27) & 7).all()
         assert is_u or not seen_u
+        if is_u and not seen_u:
+            assert (left_l == 0).all()
+            started[:] = False
         seen_u = is_u
+        left = left_u if is_u else left_l
         rounds = (int(flags[0]) >> 27) & 7
         if flags[0] & (1 << 25):
             this_level = set()
         part = np.zeros((32, 2))
+        nblk = np.zeros(32, dtype=int)
         dinv = {}
         for lane in range(32):
             k = 1 << ((int(flags[lane]) >> 16) & 7)
@@ -344,14 +358,17 @@ def test_row_lane_schedule_solves(name):
                     continue
                 slot = (fw & 0xFFFFFF) + t * k
                 covered[slot] += 1
+                nblk[lane] += 1
                 if c == 0xFFFE:
                     assert is_u and t == 0 and (flags[lane] & (1 << 24))
                     dinv[lane] = lu[slot]
                     continue
                 assert slot_col[slot] == c
-                assert not np.isnan(y[c]).any(), 'gather of a value that is not yet final'
                 assert c not in this_level, 'gather inside the level that writes the value'
-                assert final_u[c] or not is_u
+                if is_u:
+                    assert left_u[c] == 0, 'gather of a value that is not yet final (backward)'
+                else:
+                    assert left_l[c] == 0 and not np.isnan(y[c]).any(), 'gather of a value that is not yet final (forward)'
                 part[lane] += lu[slot] @ y[c]
         lane = 0
         while lane < 32:
@@ -368,15 +385,70 @@ def test_row_lane_schedule_solves(name):
                 assert ((int(flags[lane + j]) >> 19) & 31) == k - 1 - j and not flags[lane + j] & (1 << 24)
                 assert ((int(flags[lane + j]) >> 16) & 7) == ((f >> 16) & 7)
             v = part[lane:lane + k].sum(axis=0)
-            b = y[row] if is_u else rhs[row]
+            cont = f < 0                            # RL_CONT (sign bit): a later piece of a row too long for one wave
+            assert cont == bool(started[row]), 'the first piece starts from rhs / y, the others continue from x[row]'
+            if cont:
+                assert flags[0] & (1 << 25), 'a continuation is ordered after the piece before it'
+                npieces += 1
+            b = y[row] if (is_u or cont) else rhs[row]
             acc = b - v
-            y[row] = dinv[lane] @ acc if is_u else acc
+            left[row] -= int(nblk[lane:lane + k].sum())
+            assert left[row] >= 0
+            if is_u:
+                assert (lane in dinv) == (left[row] == 0), 'the pivot comes with the last piece'
+            y[row] = dinv[lane] @ acc if lane in dinv else acc
+            started[row] = True
             this_level.add(row)
-            final_u[row] = is_u
             lane += k
     assert (covered == 1).all()
-    assert final_u.all()
+    assert (left_l == 0).all() and (left_u == 0).all()
+    if name == 'long_rows':
+        assert npieces > 0
     assert np.allclose(y, x, rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize('name', ['case118', 'case2869pegase'])
+def test_row_lane_cta_programs(name):
+    """Per-warp programs of k_solve_rows_cta / k_solve_rows_deep (symbolic.cpp, rc_*): every wave belongs to
+    exactly one warp, a warp's waves and segments are in order, the waves of one level share a segment,
+    a segment never mixes levels unless it is a run of one-wave levels (which is warp 0's), and the
+    per-warp record streams are copies of the waves' records followed by the two idle waves."""
+    case = load_case(name)
+    S = _lib.symbolic_arrays(case.adj_ptr, case.adj_idx, case.bus_types_code())
+    desc = S['rl_desc'].reshape(-1, 32, 4)
+    nw = len(desc) - 2
+    W = 7
+    lists = S['rc_lists']
+    off, ent = lists[:W + 1], lists[W + 1:].reshape(-1, 2)
+    rc_desc = S['rc_desc'].reshape(-1, 32, 4)
+    rc_seg = S['rc_seg']
+    nseg = len(S['rc_segend'])
+    assert off[0] == 0 and off[W] == len(ent) and len(rc_desc) >= len(ent) + 6 and len(rc_seg) >= len(ent) + 6
+    level = np.cumsum([(int(desc[w, 0, 3]) >> 25) & 1 for w in range(nw)])       # level index of every wave
+    owner = -np.ones(nw, dtype=int)
+    seg_of = -np.ones(nw, dtype=int)
+    for q in range(W):
+        e = ent[off[q]:off[q + 1]]
+        assert (e[-2:, 0] == [nw, nw + 1]).all() and (e[-2:, 1] == nseg).all()
+        assert (np.diff(e[:-2, 0]) > 0).all() and (np.diff(e[:, 1]) >= 0).all()
+        for i, (wv, sg) in enumerate(e[:-2]):
+            assert owner[wv] == -1
+            owner[wv], seg_of[wv] = q, sg
+        for i, (wv, sg) in enumerate(e):
+            assert (rc_desc[off[q] + i] == desc[wv]).all() and rc_seg[off[q] + i] == sg
+    assert (owner >= 0).all() and seg_of.max() == nseg - 1 and (np.diff(seg_of) >= 0).all()
+    for sg in range(nseg):
+        ws = np.nonzero(seg_of == sg)[0]
+        lv = level[ws]
+        if len(set(lv)) > 1:                        # a run of one-wave levels: one warp, in order
+            assert len(set(lv)) == len(ws) and (owner[ws] == 0).all()
+        else:                                       # one level: dealt round-robin
+            assert (owner[ws] == np.arange(len(ws)) % W).all()
+    # a level never spans two segments
+    for lv in range(1, level.max() + 1):
+        assert len(set(seg_of[level == lv])) == 1
+    segend = S['rc_segend']
+    assert (np.diff(segend) >= 0).all() and segend[-1] <= int(S['lptr'][-1]) + int(S['uptr'][-1]) + case.N
 
 
 def _write_matpower(path, name, buses, branches, gens, base=100.0):
