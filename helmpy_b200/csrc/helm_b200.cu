@@ -1141,7 +1141,7 @@ __device__ __forceinline__ void rc_wave(const double2 *lu, double2 *xs, const in
     }
     if (d.w & Sy::RL_SYNC) __syncwarp();                              // a run of one-wave levels: ordered inside the warp
     const unsigned c0 = (unsigned)d.x & 0xFFFFu, c1 = (unsigned)d.x >> 16, c2 = (unsigned)d.y & 0xFFFFu, c3 = (unsigned)d.y >> 16;
-    const bool isu = (d.w & Sy::RL_ISU) != 0, head = (d.w & Sy::RL_HEAD) != 0;
+    const bool head = (d.w & Sy::RL_HEAD) != 0;
     const int row = d.w & 0xFFFF;
     double2 x0 = make_double2(0.0, 0.0), x1 = x0, x2 = x0, x3 = x0;
     double2 v = x0;
@@ -1260,7 +1260,7 @@ __device__ __forceinline__ void rcd_wave(const RcDeep &c, const int4 d, const in
     double2 *xs = c.xs;
     if (d.w & Sy::RL_SYNC) __syncwarp();
     const unsigned c0 = (unsigned)d.x & 0xFFFFu, c1 = (unsigned)d.x >> 16, c2 = (unsigned)d.y & 0xFFFFu, c3 = (unsigned)d.y >> 16;
-    const bool isu = (d.w & Sy::RL_ISU) != 0, head = (d.w & Sy::RL_HEAD) != 0;
+    const bool head = (d.w & Sy::RL_HEAD) != 0;
     const int row = d.w & 0xFFFF;
     double2 x0 = make_double2(0.0, 0.0), x1 = x0, x2 = x0, x3 = x0;
     double2 v = x0;
@@ -1964,31 +1964,44 @@ __device__ __forceinline__ void eps2_step(Eps2State &st, int t, int j, double2 v
 // following orders read their partial and add the 2i-1 products with the operands that arrived
 // since (V[T+1..j], W[T+1..j-1]) — one memory round trip instead of a walk of the history.
 // Per block of four orders a bus reads 32 T + 384 B instead of 128 T + 320 B.
+// operands of an order between two block starts (j >= 4, j % 4 = i > 0): the partial sum and the 4 i - 4
+// history values that arrived since the block start.  k_rhs_conv requests them as soon as it knows j,
+// together with the rest of its prologue, so that such an order costs ONE memory round trip.
+struct ConvLight { double2 part, w1, vj1, wt1, va, w2, vj2, wt2, vb; };
+__device__ __forceinline__ bool conv_is_light(int j) { return j >= 4 && (j & 3) != 0; }
+__device__ __forceinline__ void conv_light_load(ConvLight &L, int j, const double2 *Vb, const double2 *Hb, const double2 *Pb, size_t plane) {
+    const int i = j & 3, T = j & ~3;
+    L.part = Pb[(size_t)(i - 1) * plane];
+    if (i >= 2) {
+        L.w1 = Hb[plane];                               // W[1]
+        L.vj1 = Vb[(size_t)(j - 1) * plane];            // V[j-1]
+        L.wt1 = Hb[(size_t)(T + 1) * plane];            // W[T+1]
+        L.va = Vb[(size_t)(i - 1) * plane];             // V[i-1]
+    }
+    if (i == 3) {
+        L.w2 = Hb[2 * plane];                           // W[2]
+        L.vj2 = Vb[(size_t)(j - 2) * plane];            // V[j-2]
+        L.wt2 = Hb[(size_t)(T + 2) * plane];            // W[T+2]
+        L.vb = Vb[plane];                               // V[1]
+    }
+}
+__device__ __forceinline__ double2 conv_light_sum(const ConvLight &L, int j, double2 v) {
+    const int i = j & 3;
+    double2 c = cadd(L.part, v);                        // a = 0: W[0] = 1 (helm.py:551)
+    if (i >= 2) c = cadd(cadd(c, cmul(L.w1, L.vj1)), cmul(L.wt1, L.va));
+    if (i == 3) c = cadd(cadd(c, cmul(L.w2, L.vj2)), cmul(L.wt2, L.vb));
+    return c;
+}
+
 template <int KU>
 __device__ __forceinline__ double2 conv_blocked_pq(int j, double2 v, const double2 *Vb, const double2 *Hb,
                                                    double2 *Pb, size_t plane) {
     const double2 zero = make_double2(0.0, 0.0);
-    const int i = j & 3, T = j & ~3;
-    if (j >= 4 && i != 0) {
-        // loads first (all independent), then the few products
-        const double2 part = Pb[(size_t)(i - 1) * plane];
-        double2 w1 = zero, vj1 = zero, wt1 = zero, va = zero, w2 = zero, vj2 = zero, wt2 = zero, vb = zero;
-        if (i >= 2) {
-            w1 = Hb[plane];                               // W[1]
-            vj1 = Vb[(size_t)(j - 1) * plane];            // V[j-1]
-            wt1 = Hb[(size_t)(T + 1) * plane];            // W[T+1]
-            va = Vb[(size_t)(i - 1) * plane];             // V[i-1]
-        }
-        if (i == 3) {
-            w2 = Hb[2 * plane];                           // W[2]
-            vj2 = Vb[(size_t)(j - 2) * plane];            // V[j-2]
-            wt2 = Hb[(size_t)(T + 2) * plane];            // W[T+2]
-            vb = Vb[plane];                               // V[1]
-        }
-        double2 c = cadd(part, v);                        // a = 0: W[0] = 1 (helm.py:551)
-        if (i >= 2) c = cadd(cadd(c, cmul(w1, vj1)), cmul(wt1, va));
-        if (i == 3) c = cadd(cadd(c, cmul(w2, vj2)), cmul(wt2, vb));
-        return c;
+    if (conv_is_light(j)) {                                 // (k_rhs_conv takes this path itself, with early loads)
+        ConvLight L;
+        L.w1 = L.vj1 = L.wt1 = L.va = L.w2 = L.vj2 = L.wt2 = L.vb = zero;
+        conv_light_load(L, j, Vb, Hb, Pb, plane);
+        return conv_light_sum(L, j, v);
     }
     double2 acc0 = zero, acc1 = zero, acc2 = zero, acc3 = zero;
     double2 win1 = zero, win2 = zero, win3 = zero;         // V[T-a+1], V[T-a+2], V[T-a+3] (0 while unknown)
@@ -2051,6 +2064,9 @@ __device__ __forceinline__ void conv_loop_pv(int j, double2 v, double2 PP, const
 
 // 128-thread CTAs (= one history tile), 80 registers: six CTAs per SM.  The epsilon table and the
 // Pade check run in their own kernel (k_eps); this one only carries the convolution state.
+#ifndef CONV_EARLY
+#define CONV_EARLY 1
+#endif
 #ifndef CONV_MINB
 #define CONV_MINB 6
 #define CONV_KU_PQ 4
@@ -2077,6 +2093,14 @@ __global__ void __launch_bounds__(128, CONV_MINB) k_rhs_conv(PlanDev p, WorkDev 
     const int status = w.s_status[sg];
     const int j = w.g_n[grp] + 1;  // order just solved
     const unsigned char bt = w.btype[bi];
+#if CONV_EARLY
+    // an order between two block starts of a PQ bus: its handful of operands is requested here, beside the
+    // rest of the prologue (the flags, j and the bus type come from small L2-resident arrays)
+    ConvLight lt;
+    lt.part = lt.w1 = lt.vj1 = lt.wt1 = lt.va = lt.w2 = lt.vj2 = lt.wt2 = lt.vb = make_double2(0.0, 0.0);
+    const bool light = bt == HELM_BUS_PQ && conv_is_light(j) && status == ST_ACTIVE && !(gf & (GF_DONE | GF_PASSEND | GF_FACTORING));
+    if (light) conv_light_load(lt, j, Vb, Hb, w.Pb + px<G>(N, grp, 0, i, s), plane);
+#endif
     const double2 v = xb[(size_t)i * G + s];
     const double sc = w.scale[sg];
     const double qg = w.Qg[bi];
@@ -2101,7 +2125,11 @@ __global__ void __launch_bounds__(128, CONV_MINB) k_rhs_conv(PlanDev p, WorkDev 
     const double2 zero = make_double2(0.0, 0.0);
     double2 out;
     if (bt == HELM_BUS_PQ) {
+#if CONV_EARLY
+        const double2 aux = light ? conv_light_sum(lt, j, v) : conv_blocked_pq<CONV_KU_PQ>(j, v, Vb, Hb, w.Pb + px<G>(N, grp, 0, i, s), plane);
+#else
         const double2 aux = conv_blocked_pq<CONV_KU_PQ>(j, v, Vb, Hb, w.Pb + px<G>(N, grp, 0, i, s), plane);
+#endif
         double2 wj = make_double2(-aux.x, -aux.y);
         Hb[(size_t)j * plane] = wj;                                               // W[j]
         // RHS of order j+1 (helm.py:367-385)

@@ -1,0 +1,7 @@
+#!/bin/bash
+export HELM_RESIDENT=4096
+for v in "" _cv_8_2_2 _cv_8_4_4 _cv_7_4_4; do
+  echo "variant $v"
+  HELM_B200_LIB=$PWD/helmpy_b200/libhelm_b200$v.so python tools/sweep.py case2869pegase 16384 1 profile 2>&1 | grep '"case"' | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms'], d['ms_kernel']['rhs_conv'], d['ms_kernel']['eps'], d['conv'])"
+  HELM_B200_LIB=$PWD/helmpy_b200/libhelm_b200$v.so python tools/sweep.py case2869pegase 16384 1 2>&1 | grep '"case"' | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['cases_per_s'], d['ms'])"
+done
