@@ -996,7 +996,10 @@ __device__ __forceinline__ Blk256 ld_blk_stream(const double2 *lu, int slot) {
 #ifndef ROWS_UNROLL
 #define ROWS_UNROLL 2
 #endif
-constexpr int ROWS_WPB = 7;
+#ifndef ROWS_WPB_N
+#define ROWS_WPB_N 7
+#endif
+constexpr int ROWS_WPB = ROWS_WPB_N;
 constexpr int ROWS_UNROLL_N = ROWS_UNROLL;
 
 // blocks t = T0 .. of the lane, from the record's fetch word (slot | lanes-per-row log2 << 24 | blocks << 27)
@@ -1124,21 +1127,11 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void *gsrc, unsigned byte
 
 // one wave of a warp of k_solve_rows_cta: record d, blocks m (m[0] of the NEXT wave is requested at the end,
 // the others right after the products), fn = fetch word of the next wave
-__device__ __forceinline__ void prefetch_l1(const void *ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
-
-// fnn = fetch word two waves ahead: small batches (default cache policy) pull those blocks into L1 now, so
-// that the request one wave ahead costs an L1 hit instead of an L2 round trip on the dependent chain
+// (an L1 prefetch of the blocks two waves ahead was measured slower: 115 vs 98 us per solve alone)
 template <bool STREAM>
-__device__ __forceinline__ void rc_wave(const double2 *lu, double2 *xs, const int4 d, int fn, const int fnn, Blk256 (&m)[4], const int abl = 0) {
+__device__ __forceinline__ void rc_wave(const double2 *lu, double2 *xs, const int4 d, int fn, Blk256 (&m)[4], const int abl = 0) {
     using Sy = helm::Symbolic;
     if (abl & 2) fn &= 0xFFFFFF;                                      // timing ablation: no factor loads
-    if (false) {                                                      // measured: 115 vs 98 us per solve alone, slower
-        const int k = 1 << ((fnn >> 24) & 7), cnt = (fnn >> 27) & 7, slot = fnn & 0xFFFFFF;
-        if (cnt > 0) prefetch_l1(lu + 2 * (size_t)slot);
-        if (cnt > 1) prefetch_l1(lu + 2 * (size_t)(slot + k));
-        if (cnt > 2) prefetch_l1(lu + 2 * (size_t)(slot + 2 * k));
-        if (ROWS_NB > 3 && cnt > 3) prefetch_l1(lu + 2 * (size_t)(slot + 3 * k));
-    }
     if (d.w & Sy::RL_SYNC) __syncwarp();                              // a run of one-wave levels: ordered inside the warp
     const unsigned c0 = (unsigned)d.x & 0xFFFFu, c1 = (unsigned)d.x >> 16, c2 = (unsigned)d.y & 0xFFFFu, c3 = (unsigned)d.y >> 16;
     const bool head = (d.w & Sy::RL_HEAD) != 0;
@@ -1205,7 +1198,7 @@ __global__ void __launch_bounds__(RC_T, 4) k_solve_rows_cta(PlanDev p, WorkDev w
     const int4 *desc = p.rc_desc + (size_t)first * 32 + lane;
     const int *sgp = p.rc_seg + first;
     int4 da = __ldg(desc), db;
-    int fa, fb = __ldg(&desc[32].z), fc;                              // fetch word of the next wave
+    int fa, fb = __ldg(&desc[32].z);                                  // fetch word of the next wave
     int sa = __ldg(sgp), sb;
     Blk256 m[4];
 #pragma unroll
@@ -1229,15 +1222,13 @@ __global__ void __launch_bounds__(RC_T, 4) k_solve_rows_cta(PlanDev p, WorkDev w
     while (true) {
         if (da.w & Sy::RL_STOP) break;
         db = __ldg(desc + 32); fa = __ldg(&desc[64].z); sb = __ldg(sgp + 1);
-        fc = __ldg(&desc[96].z);                                      // (may read into the next warp's stream: the table is padded)
         barriers(sa);
-        if (!(abl & 16)) rc_wave<STREAM>(lu, xs, da, fb, fa, m, abl);
+        if (!(abl & 16)) rc_wave<STREAM>(lu, xs, da, fb, m, abl);
         if (db.w & Sy::RL_STOP) break;
         desc += 64; sgp += 2;
-        da = __ldg(desc); sa = __ldg(sgp);
+        da = __ldg(desc); fb = __ldg(&desc[32].z); sa = __ldg(sgp);
         barriers(sb);
-        if (!(abl & 16)) rc_wave<STREAM>(lu, xs, db, fa, fc, m, abl);
-        fb = fc;
+        if (!(abl & 16)) rc_wave<STREAM>(lu, xs, db, fa, m, abl);
     }
     barriers(nsegs);                                                  // every warp passes every barrier
     for (int i = tid; i < N; i += RC_T) xb[i] = xs[i];
