@@ -442,6 +442,13 @@ def run_cuda(args):
             k['frac_of_hbm_peak'] = k['gbs'] / peak
             if 'gbs_8d' in k:
                 k['frac_8d'] = k['gbs_8d'] / peak
+        # the solve with the factor cache: `bytes` divides the factor reads by the measured sharing, which
+        # leaves little more than rhs in / x out -- the kernel then runs against L2 latency, not HBM.  For comparison
+        # with earlier rounds: the rate at which it gets through the factors every scenario would read on its own.
+        sv = kernels['solve']
+        if sv['ms'] > 0:
+            sv['gbs_private_factors'] = sv['bytes_private_factors'] / (sv['ms'] * 1e-3) / 1e9
+            sv['frac_private_factors'] = sv['gbs_private_factors'] / peak
         # dominant kernel = the largest of the main branch (solve -> eps -> rhs_conv is the critical
         # path of a step; the factorization runs beside it in the side branch, two steps deep)
         dom = max((kernels[k] for k in ('solve', 'rhs_conv', 'eps')), key=lambda k: k['ms'])
