@@ -2175,9 +2175,12 @@ __global__ void __launch_bounds__(128, CONV_MINB) k_rhs_conv(PlanDev p, WorkDev 
 #define EPS_MINB 8
 #define EPS_KE 6
 #endif
+#ifndef EPS_T
+#define EPS_T 128           // threads per CTA of k_eps
+#endif
 constexpr int KE = EPS_KE;
 template <int G>
-__global__ void __launch_bounds__(128, EPS_MINB) k_eps(PlanDev p, WorkDev w) {
+__global__ void __launch_bounds__(EPS_T, EPS_MINB * 128 / EPS_T) k_eps(PlanDev p, WorkDev w) {
     TL_SCOPE(w, 3);
     const int grp = blockIdx.y;
     const int gf = w.g_flags[grp];
@@ -2945,7 +2948,7 @@ void launch_kernel(int which, const PlanDev &p, const WorkDev &w, cudaStream_t s
             if (w.pv_model == 1 || w.dsb_method) k_rhs_conv_var<<<gridBus, T_ELEM, 0, st>>>(p, w);
             else k_rhs_conv<G><<<dim3((p.N * G + 127) / 128, w.ngroups), 128, 0, st>>>(p, w);
             break;
-        case KI_EPS: k_eps<G><<<dim3((p.N * G + 127) / 128, w.ngroups), 128, 0, st>>>(p, w); break;
+        case KI_EPS: k_eps<G><<<dim3((p.N * G + EPS_T - 1) / EPS_T, w.ngroups), EPS_T, 0, st>>>(p, w); break;
         case KI_ADV: k_advance<<<gridGrp, 128, 0, st>>>(w); break;
         case KI_QLIM: k_qlimit<G><<<dim3(gridBus.x, std::min(w.ngroups, 512)), T_ELEM, 0, st>>>(p, w); break;
         case KI_PEND: k_pass_end<<<gridGrp, 128, 0, st>>>(w); break;
