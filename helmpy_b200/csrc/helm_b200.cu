@@ -3235,7 +3235,7 @@ int helm_plan_create(const helm_grid_host *g, helm_plan **out) {
             size_t csm = cta_solve_layout(pl->d.N, pl->d.nwaves, pl->d.nschunks).total;
             static size_t csm_set = 48 * 1024;
             pl->d.use_cta_solve = (csm <= 225 * 1024) && getenv("HELM_B200_NO_CTA_SOLVE") == nullptr;
-            pl->d.cta_solve_max_groups = getenv("HELM_B200_CTA_SOLVE_MAX") ? atoi(getenv("HELM_B200_CTA_SOLVE_MAX")) : 888;
+            pl->d.cta_solve_max_groups = getenv("HELM_B200_CTA_SOLVE_MAX") ? atoi(getenv("HELM_B200_CTA_SOLVE_MAX")) : 640;   // measured crossover with the warp-per-scenario solve: between 512 and 800 scenarios (tools/r2_mid.sh)
             {
                 const size_t osm = one_layout(pl->d.N, pl->d.nwaves, pl->d.nsegs, pl->d.nonelist).total;
                 static size_t osm_set = 48 * 1024;

@@ -525,7 +525,7 @@ def test_nr_batch_divergence_and_no_limits(hb):
 @pytest.mark.parametrize('kw', [dict(), dict(pv_bus_model=1), dict(DSB_model=True, DSB_model_method=2),
                                 dict(pv_bus_model=1, DSB_model=True, DSB_model_method=1)])
 def test_large_batch_kernels_agree_with_small_batch(hb, kw):
-    """More than 888 resident scenarios switch to the warp-per-scenario solve on the compacted list,
+    """More than 640 resident scenarios switch to the warp-per-scenario solve on the compacted list,
     the side solves by flag and (default variant) the two-step factorization pipeline; a small batch
     uses the CTA solve and a one-step pipeline.  Same passes, same voltages."""
     case = load_case('case1354pegase')
@@ -653,7 +653,7 @@ def test_per_order_coefficients_match_oracle(hb, name, scale):
 
 def test_benchmark_path_matches_oracle(hb):
     """The path bench.py times — case2869pegase, more scenarios than slots (continuous batching with
-    slot refill), > 888 resident so the warp-per-scenario row-lane solve (k_solve_rows) runs, shared
+    slot refill), > 640 resident so the warp-per-scenario row-lane solve (k_solve_rows) runs, shared
     first-pass factors, two-step factorization pipeline — against the oracle on sampled scenarios:
     status, coefficients per pass, switch count, |dV| and d(angle) <= 1e-8 (reference helm.py:896-985)."""
     case = load_case('case2869pegase')
